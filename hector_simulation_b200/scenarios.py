@@ -1,0 +1,225 @@
+"""Synthetic robot-state batches for the five BASELINE.json configs.
+
+Everything here is *harness*: it restates, in numpy, the cheap host-side data preparation that the
+reference's caller performs before it reaches the C boundary, so that the records fed to the
+solver look like what ``ConvexMPCLocomotion::updateMPCIfNeeded`` would produce:
+
+  * contact table      Gait::mpc_gait            ConvexMPC/GaitGenerator.cpp:85-103
+  * foot positions     leg forward kinematics    src/common/LegController.cpp:108-113,190-194
+                       hip offsets               include/common/Biped.h:9-24
+  * joint-angle chain  (quirk Q7: offsets added in LegController.cpp:111-113 and again in
+                        ConvexMPCLocomotion.cpp:298-313 before the boundary)
+  * r, weights, traj   ConvexMPCLocomotion.cpp:315-406
+
+Output records use the reference's ``update_data_t`` layout (convexMPC_interface.h:19-37).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+K_MAX_GAIT_SEGMENTS = 36
+
+UPDATE_DTYPE = np.dtype(
+    [
+        ("p", "<f4", 3), ("v", "<f4", 3), ("q", "<f4", 4), ("w", "<f4", 3), ("r", "<f4", 6),
+        ("joint_angles", "<f4", 10), ("yaw", "<f4"), ("weights", "<f4", 12),
+        ("traj", "<f4", 12 * K_MAX_GAIT_SEGMENTS), ("Alpha_K", "<f4", 12),
+        ("gait", "u1", K_MAX_GAIT_SEGMENTS), ("hack_pad", "u1", 1000), ("max_iterations", "<i4"),
+        ("rho", "<f8"), ("sigma", "<f8"), ("solver_alpha", "<f8"), ("terminate", "<f8"),
+    ],
+    align=True,
+)
+assert UPDATE_DTYPE.itemsize == 3016
+
+# ConvexMPCLocomotion.cpp:321-322
+MPC_WEIGHTS = np.array([100, 100, 250, 200, 200, 300, 1, 1, 1, 1, 1, 1], dtype=np.float64)
+MPC_ALPHA = np.array([1e-4, 1e-4, 5e-4, 1e-4, 1e-4, 5e-4, 1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-2], dtype=np.float64)
+DT_MPC = 0.001 * 40  # FSMState_Walking.cpp:5, ConvexMPCLocomotion.cpp:20
+F_MAX = 500.0        # ConvexMPCLocomotion.cpp:410
+MU_PASSED = 0.25     # ConvexMPCLocomotion.cpp:410 (ignored by the solver, quirk Q3)
+BODY_HEIGHT = 0.55   # ConvexMPCLocomotion.cpp:54
+
+
+def mpc_gait(n_segments: int, offsets, durations, iteration: int) -> np.ndarray:
+    """Contact table [n_segments*2] of 0/1, order [step][leg] (GaitGenerator.cpp:85-103)."""
+    table = np.zeros(n_segments * 2, dtype=np.int32)
+    for i in range(n_segments):
+        it = (i + iteration) % n_segments
+        for j in range(2):
+            progress = it - offsets[j]
+            if progress < 0:
+                progress += n_segments
+            table[i * 2 + j] = 1 if progress < durations[j] else 0
+    return table
+
+
+def walking_table(horizon: int, iteration: int) -> np.ndarray:
+    # walking(horizonLength, (0,5), (5,5))  ConvexMPCLocomotion.cpp:16, scaled with the horizon for N != 10
+    half = horizon // 2
+    return mpc_gait(horizon, (0, half), (half, horizon - half), iteration)
+
+
+def standing_table(horizon: int) -> np.ndarray:
+    # standing(horizonLength, (0,0), (10,10))  ConvexMPCLocomotion.cpp:17
+    return mpc_gait(horizon, (0, 0), (horizon, horizon), 0)
+
+
+def rpy_to_quat(rpy) -> np.ndarray:
+    """ZYX Euler -> (w,x,y,z), body-to-world (what Gazebo's model_states carries)."""
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = np.cos(r / 2), np.sin(r / 2), np.cos(p / 2), np.sin(p / 2), np.cos(y / 2), np.sin(y / 2)
+    return np.array([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
+                     cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
+
+
+def quat_to_R(q) -> np.ndarray:
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def quat_to_rpy(q) -> np.ndarray:
+    # include/common/Math/orientation_tools.h:208-221
+    a = min(2.0 * (q[2] * q[0] - q[1] * q[3]), 1.00001)
+    a = max(min(a, 1.0), -1.0)
+    return np.array([np.arctan2(2 * (q[0] * q[1] + q[2] * q[3]), 1 - 2 * (q[1] ** 2 + q[2] ** 2)),
+                     np.arcsin(a),
+                     np.arctan2(2 * (q[0] * q[3] + q[1] * q[2]), 1 - 2 * (q[2] ** 2 + q[3] ** 2))])
+
+
+def hip_yaw_location(leg: int) -> np.ndarray:
+    # Biped.h:11-13,19-22
+    return np.array([-0.005, -0.057 if leg == 0 else 0.057, -0.126])
+
+
+def leg_fk(q, leg: int) -> np.ndarray:
+    """Foot position in the hip frame, LegController.cpp:190-194; q already carries the first
+    0.3/-0.6/0.3 * 3.14159 offset (LegController.cpp:111-113)."""
+    q0, q1, q2, q3, q4 = q
+    side = 1.0 if leg == 0 else -1.0
+    s, c = np.sin, np.cos
+    x = (-(3 * c(q0)) / 200
+         - (9 * s(q4) * (c(q3) * (c(q0) * c(q2) - s(q0) * s(q1) * s(q2)) - s(q3) * (c(q0) * s(q2) + c(q2) * s(q0) * s(q1)))) / 250
+         - (11 * c(q0) * s(q2)) / 50 - (side * s(q0)) / 50
+         - (11 * c(q3) * (c(q0) * s(q2) + c(q2) * s(q0) * s(q1))) / 50
+         - (11 * s(q3) * (c(q0) * c(q2) - s(q0) * s(q1) * s(q2))) / 50
+         - (9 * c(q4) * (c(q3) * (c(q0) * s(q2) + c(q2) * s(q0) * s(q1)) + s(q3) * (c(q0) * c(q2) - s(q0) * s(q1) * s(q2)))) / 250
+         - (23 * c(q1) * side * s(q0)) / 1000 - (11 * c(q2) * s(q0) * s(q1)) / 50)
+    y = ((c(q0) * side) / 50
+         - (9 * s(q4) * (c(q3) * (c(q2) * s(q0) + c(q0) * s(q1) * s(q2)) - s(q3) * (s(q0) * s(q2) - c(q0) * c(q2) * s(q1)))) / 250
+         - (3 * s(q0)) / 200 - (11 * s(q0) * s(q2)) / 50
+         - (11 * c(q3) * (s(q0) * s(q2) - c(q0) * c(q2) * s(q1))) / 50
+         - (11 * s(q3) * (c(q2) * s(q0) + c(q0) * s(q1) * s(q2))) / 50
+         - (9 * c(q4) * (c(q3) * (s(q0) * s(q2) - c(q0) * c(q2) * s(q1)) + s(q3) * (c(q2) * s(q0) + c(q0) * s(q1) * s(q2)))) / 250
+         + (23 * c(q0) * c(q1) * side) / 1000 + (11 * c(q0) * c(q2) * s(q1)) / 50)
+    z = ((23 * side * s(q1)) / 1000 - (11 * c(q1) * c(q2)) / 50
+         - (9 * c(q4) * (c(q1) * c(q2) * c(q3) - c(q1) * s(q2) * s(q3))) / 250
+         + (9 * s(q4) * (c(q1) * c(q2) * s(q3) + c(q1) * c(q3) * s(q2))) / 250
+         - (11 * c(q1) * c(q2) * c(q3)) / 50 + (11 * c(q1) * s(q2) * s(q3)) / 50 - 3.0 / 50.0)
+    return np.array([x, y, z])
+
+
+def boundary_inputs(pos, rpy, vel, omega, raw_joints, gait_table, horizon: int = 10,
+                    v_des_body=(0.0, 0.0), yaw_rate: float = 0.0, pos_des_err=(0.0, 0.0),
+                    roll_pitch_des=(0.0, 0.0)) -> dict:
+    """The eleven double-precision arguments of update_problem_data (convexMPC_interface.h:43) that
+    the reference's caller would build for this robot state (ConvexMPCLocomotion.cpp:283-406)."""
+    pos, rpy, vel, omega = (np.asarray(a, dtype=np.float64) for a in (pos, rpy, vel, omega))
+    quat = rpy_to_quat(rpy)
+    R = quat_to_R(quat)  # body -> world = rBody^T
+    est_rpy = quat_to_rpy(quat)
+    # LegController::updateData: first offset (3.14159), FK on the offset angles
+    q_leg = np.asarray(raw_joints, dtype=np.float64).reshape(2, 5).copy()
+    q_leg[:, 2] += 0.3 * 3.14159
+    q_leg[:, 3] -= 0.6 * 3.14159
+    q_leg[:, 4] += 0.3 * 3.14159
+    p_foot = [pos + R @ (hip_yaw_location(i) + leg_fk(q_leg[i], i)) for i in range(2)]
+    # updateMPCIfNeeded: second offset (3.14159265359) + fmod
+    PI = 3.14159265359
+    q = q_leg.reshape(10).copy()
+    for base in (0, 5):
+        q[base + 2] += 0.3 * PI
+        q[base + 3] -= 0.6 * PI
+        q[base + 4] += 0.3 * PI
+    q = np.fmod(q, 2 * PI)
+    r = np.array([p_foot[i % 2][i // 2] - pos[i // 2] for i in range(6)])
+    yaw = est_rpy[2]
+    v_des_world = R @ np.array([v_des_body[0], v_des_body[1], 0.0])
+    max_pos_error = 0.05
+    x_start = pos[0] + float(np.clip(pos_des_err[0], -max_pos_error, max_pos_error))
+    y_start = pos[1] + float(np.clip(pos_des_err[1], -max_pos_error, max_pos_error))
+    traj_initial = np.array([roll_pitch_des[0], roll_pitch_des[1], 0.0, x_start, y_start, BODY_HEIGHT,
+                             0.0, 0.0, yaw_rate, v_des_world[0], v_des_world[1], 0.0])
+    traj = np.zeros(12 * horizon)
+    for i in range(horizon):
+        traj[12 * i: 12 * i + 12] = traj_initial
+        if i == 0:
+            traj[0:3] = est_rpy
+            traj[3:6] = pos
+        else:
+            traj[12 * i + 3] = (traj_initial[3] if v_des_world[0] == 0 else pos[0]) + i * DT_MPC * v_des_world[0]
+            traj[12 * i + 4] = (traj_initial[4] if v_des_world[1] == 0 else pos[1]) + i * DT_MPC * v_des_world[1]
+            traj[12 * i + 2] = traj_initial[2] if yaw_rate == 0 else yaw + i * DT_MPC * yaw_rate
+    return dict(p=pos.copy(), v=vel.copy(), q=quat, w=omega.copy(), r=r, joint_angles=q, yaw=float(yaw),
+                weights=MPC_WEIGHTS.copy(), state_trajectory=traj, Alpha_K=MPC_ALPHA.copy(),
+                gait=np.asarray(gait_table, dtype=np.int32).copy())
+
+
+def to_record(b: dict, horizon: int, out: np.ndarray | None = None) -> np.ndarray:
+    """double -> float narrowing of update_problem_data (convexMPC_interface.cpp:87-99)."""
+    rec = np.zeros((), dtype=UPDATE_DTYPE) if out is None else out
+    rec["p"], rec["v"], rec["q"], rec["w"], rec["r"] = b["p"], b["v"], b["q"], b["w"], b["r"]
+    rec["joint_angles"], rec["yaw"], rec["weights"] = b["joint_angles"], b["yaw"], b["weights"]
+    rec["traj"][: 12 * horizon] = b["state_trajectory"]
+    rec["Alpha_K"] = b["Alpha_K"]
+    rec["gait"][: 2 * horizon] = b["gait"]
+    return rec
+
+
+def stand_inputs(horizon: int = 10) -> dict:
+    """Config 1: spawn pose, double support."""
+    return boundary_inputs((0, 0, BODY_HEIGHT), (0, 0, 0), (0, 0, 0), (0, 0, 0), np.zeros(10),
+                           standing_table(horizon), horizon)
+
+
+def _random_state(rng: np.random.Generator, horizon: int, table, moving: bool) -> dict:
+    rpy = rng.normal(0.0, 0.05, 3)
+    pos = np.array([0.0, 0.0, BODY_HEIGHT]) + rng.normal(0.0, 0.02, 3)
+    vx_cmd = rng.uniform(-0.5, 0.5) if moving else 0.0
+    vel = rng.normal(0.0, 0.1, 3) + np.array([vx_cmd, 0.0, 0.0])
+    omega = rng.normal(0.0, 0.2, 3)
+    joints = rng.normal(0.0, 0.05, 10)
+    yaw_rate = rng.uniform(-0.3, 0.3) if (moving and rng.random() < 0.25) else 0.0
+    err = rng.normal(0.0, 0.03, 2)
+    return boundary_inputs(pos, rpy, vel, omega, joints, table, horizon, v_des_body=(vx_cmd, 0.0),
+                           yaw_rate=yaw_rate, pos_des_err=err)
+
+
+def config_seed(cfg: int) -> int:
+    return 20260923 + cfg
+
+
+def make_batch(cfg: int, batch: int, horizon: int = 10, seed: int | None = None):
+    """-> (records[batch] UPDATE_DTYPE, list of boundary-input dicts).
+
+    cfg 1: stand (every record identical)          cfg 2: walking gait, phase = i mod N
+    cfg 3: 25 % stand / 75 % walk, random phase    cfg 4: like 3 at the given horizon
+    cfg 5: like 2 (initial states of the closed loop)
+    """
+    rng = np.random.default_rng(config_seed(cfg) if seed is None else seed)
+    recs = np.zeros(batch, dtype=UPDATE_DTYPE)
+    inputs = []
+    for i in range(batch):
+        if cfg == 1:
+            b = stand_inputs(horizon)
+        elif cfg in (2, 5):
+            b = _random_state(rng, horizon, walking_table(horizon, i % horizon), moving=True)
+        else:
+            if rng.random() < 0.25:
+                b = _random_state(rng, horizon, standing_table(horizon), moving=False)
+            else:
+                b = _random_state(rng, horizon, walking_table(horizon, int(rng.integers(0, horizon))), moving=True)
+        to_record(b, horizon, recs[i])
+        inputs.append(b)
+    return recs, inputs

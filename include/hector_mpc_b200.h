@@ -1,0 +1,157 @@
+/*
+ * hector_mpc_b200.h — C-ABI of libhector_mpc_b200.so
+ *
+ * A B200 (sm_100a) batched force-and-moment MPC solver that is a drop-in for the
+ * C boundary of DRCL-USC/Hector_Simulation's convex MPC:
+ *
+ *   reference boundary : hector_control/ConvexMPC/convexMPC_interface.h:11-43
+ *   reference caller   : hector_control/ConvexMPC/ConvexMPCLocomotion.cpp:410,415,428-429
+ *
+ * Part 1 re-exports the four reference symbols with identical signatures and semantics
+ * (one robot, blocking solve, result held by the library).  Part 2 is the additive batched
+ * interface (thousands of independent robots per launch).  Plain pointers and sizes only:
+ * no C++/torch types cross this boundary.
+ *
+ * There is NO CPU fallback behind these entry points: if no CUDA device / kernel image is
+ * usable, every entry point reports HMPC_ERR_CUDA (batched API) or aborts with a message
+ * (reference API, which has no error channel — convexMPC_interface.h:39-43).
+ */
+#ifndef HECTOR_MPC_B200_H
+#define HECTOR_MPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define HMPC_EXTERNC extern "C"
+#else
+#define HMPC_EXTERNC
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Part 0 — POD records, byte-compatible with the reference
+ * ---------------------------------------------------------------------------------------- */
+
+#define K_MAX_GAIT_SEGMENTS 36 /* convexMPC_interface.h:3 */
+
+/* convexMPC_interface.h:11-17.  `mu` is carried but ignored by the solver, exactly like the
+ * reference (SolverMPC.cpp:488 shadows it with a local 2.0). */
+struct problem_setup
+{
+  float dt;
+  float mu;
+  float f_max;
+  int horizon;
+};
+
+/* convexMPC_interface.h:19-37 — same member order, types and padding (sizeof == 3016). */
+struct update_data_t
+{
+  float p[3];                          /* CoM position, world                               */
+  float v[3];                          /* CoM velocity, world                               */
+  float q[4];                          /* orientation quaternion (w,x,y,z)                  */
+  float w[3];                          /* angular velocity, world                           */
+  float r[6];                          /* foot - CoM, layout [x0,x1,y0,y1,z0,z1]            */
+  float joint_angles[10];              /* leg0 q0..q4, leg1 q0..q4 (before the solver's offset) */
+  float yaw;
+  float weights[12];                   /* state tracking weights (rpy, p, w, v)             */
+  float traj[12 * K_MAX_GAIT_SEGMENTS];/* reference trajectory, 12 per horizon step         */
+  float Alpha_K[12];                   /* input regularisation [F0 F1 M0 M1]                */
+  unsigned char gait[K_MAX_GAIT_SEGMENTS]; /* contact table, [step][leg], 0/1             */
+  unsigned char hack_pad[1000];
+  int max_iterations;
+  double rho, sigma, solver_alpha, terminate;
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1 — the reference's own entry points (convexMPC_interface.h:39-43)
+ *
+ *   setup_problem        replaces convexMPC_interface.cpp:42-66  (+ resize_qp_mats, SolverMPC.cpp:196-299)
+ *   update_problem_data  replaces convexMPC_interface.cpp:83-103 (+ solve_mpc, SolverMPC.cpp:371-738,
+ *                         + qpOASES QProblem::init, SolverMPC.cpp:702-712)
+ *   get_solution         replaces convexMPC_interface.cpp:105-110
+ *   update_solver_settings replaces convexMPC_interface.cpp:112-118 (stored, otherwise unused)
+ *
+ * Semantics kept: update_problem_data blocks until the wrench is available; get_solution(i),
+ * i in [0, 12*horizon), is step-major [F0(3) F1(3) M0(3) M1(3)] in the world frame and returns
+ * 0.0 before the first solve; swing-leg entries are exactly 0.0.  Single caller thread.
+ * Difference (documented in INTEGRATION.md): horizon > 19 aborts with a message instead of
+ * letting a C++ exception escape (SolverMPC.cpp:140-143).
+ * ---------------------------------------------------------------------------------------- */
+HMPC_EXTERNC void setup_problem(double dt, int horizon, double mu, double f_max);
+HMPC_EXTERNC double get_solution(int index);
+HMPC_EXTERNC void update_solver_settings(int max_iter, double rho, double sigma, double solver_alpha,
+                                         double terminate, double use_jcqp);
+HMPC_EXTERNC void update_problem_data(double* p, double* v, double* q, double* w, double* r,
+                                      double* joint_angles, double yaw, double* weights,
+                                      double* state_trajectory, double* Alpha_K, int* gait);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2 — batched interface (additive; SURVEY.md §8b "batched extension")
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct hmpc_ctx hmpc_ctx;
+
+/* return codes */
+#define HMPC_OK 0
+#define HMPC_ERR_ARG 1      /* bad argument (null pointer, batch > capacity, horizon out of range) */
+#define HMPC_ERR_CUDA 2     /* CUDA runtime error / no device / no sm_100a image; hmpc_last_error() has text */
+#define HMPC_ERR_NOT_CONVERGED 3 /* at least one instance did not reach a KKT point; see status[] */
+
+/* per-instance status word written with every result (never silently stale — contrast
+ * SolverMPC.cpp:714-715, which prints and carries on with stale data):
+ *   bits  0..7  : termination code  (0 = optimal, 1 = iteration cap, 2 = working-set capacity,
+ *                                    3 = infeasible/degenerate step, 4 = Hessian not SPD)
+ *   bits  8..19 : working-set changes performed (comparable to qpOASES nWSR)
+ *   bits 20..27 : number of active constraints at the solution
+ */
+#define HMPC_STATUS_CODE(s) ((s) & 0xff)
+#define HMPC_STATUS_ITERS(s) (((s) >> 8) & 0xfff)
+#define HMPC_STATUS_NACTIVE(s) (((s) >> 20) & 0xff)
+
+#define HMPC_MAX_HORIZON 16 /* dense fp64 working set of one QP must fit one SM's shared memory */
+
+/* Packed device record (HBM layout, one per robot).  Only the bytes that change per tick:
+ *   float state[30]  = p3 v3 q4 w3 r6 joint10 yaw1
+ *   float weights[12], float alpha[12]
+ *   float traj[12*N]
+ *   u8    gait[2*N]   (+ zero padding to a multiple of 16 bytes)
+ * hmpc_record_bytes(N) gives the stride.  N=10: 216 + 98*N = 1196 algorithmic bytes per QP
+ * in+out, 720-byte input stride. */
+HMPC_EXTERNC size_t hmpc_record_bytes(int horizon);
+/* pack n reference records into the device layout (host side helper, pure byte shuffling) */
+HMPC_EXTERNC int hmpc_pack_records(const struct update_data_t* in, int n, int horizon, void* out);
+
+/* create a context on `device` able to hold `max_batch` robots of `horizon` steps */
+HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device);
+HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* ctx);
+HMPC_EXTERNC const char* hmpc_last_error(void);
+
+/* dt / f_max of problem_setup (mu is ignored like the reference).  Defaults 0.04 / 500. */
+HMPC_EXTERNC int hmpc_set_problem(hmpc_ctx* ctx, const struct problem_setup* setup);
+
+/* Host-buffer path (the reference-facing call: H2D + solve + D2H inside).
+ *   in         : B reference records (host)
+ *   wrench_out : [B][12*horizon] doubles, same layout as get_solution (host)
+ *   status     : [B] status words (host), may be NULL
+ * Blocks until results are in host memory. */
+HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* ctx, const struct update_data_t* in, int B,
+                                  double* wrench_out, int* status);
+
+/* Device-resident path: `d_records` = B packed records already in HBM, `d_wrench`
+ * [B][12*horizon] float, `d_status` [B] int, all device pointers; enqueued on `stream`
+ * (a cudaStream_t passed as void*), returns without synchronising. */
+HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench,
+                                   int* d_status, void* stream);
+
+/* number of kernel launches hmpc_solve_device enqueues per call */
+HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
+
+/* Debug/parity hook: run only the assembly stage for B packed device records and write the
+ * full (un-reduced) fp32 QP data per instance: H [n*n] row-major (upper triangle valid,
+ * mirrored), g [n], the 16x12 constraint block [192], lb/ub [16N].  n = 12*horizon. */
+HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* ctx, const void* d_records, int B, float* d_H,
+                                      float* d_g, float* d_Fblk, float* d_lb, float* d_ub,
+                                      void* stream);
+
+#endif /* HECTOR_MPC_B200_H */

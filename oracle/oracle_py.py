@@ -1,0 +1,140 @@
+"""ctypes loader for the parity oracle — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this module.  It wraps oracle/_ref/liboracle_mpc.so: the Eigen-free restatement of the
+reference's ``solve_mpc`` (hector_control/ConvexMPC/SolverMPC.cpp:371-732) linked against the
+reference's own vendored qpOASES 3.2 built unchanged from /root/reference (oracle/Makefile).
+
+Formulation half: *parity unpinned* (the reference has no tests/golden vectors and needs Eigen,
+absent here — see the header of solve_mpc_oracle.cpp).  Solver half: the reference's own code.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "liboracle_mpc.so")
+
+K_MAX_GAIT_SEGMENTS = 36
+
+# numpy mirror of `update_data_t` (convexMPC_interface.h:19-37), C layout incl. padding.
+UPDATE_DTYPE = np.dtype(
+    [
+        ("p", "<f4", 3),
+        ("v", "<f4", 3),
+        ("q", "<f4", 4),
+        ("w", "<f4", 3),
+        ("r", "<f4", 6),
+        ("joint_angles", "<f4", 10),
+        ("yaw", "<f4"),
+        ("weights", "<f4", 12),
+        ("traj", "<f4", 12 * K_MAX_GAIT_SEGMENTS),
+        ("Alpha_K", "<f4", 12),
+        ("gait", "u1", K_MAX_GAIT_SEGMENTS),
+        ("hack_pad", "u1", 1000),
+        ("max_iterations", "<i4"),
+        ("rho", "<f8"),
+        ("sigma", "<f8"),
+        ("solver_alpha", "<f8"),
+        ("terminate", "<f8"),
+    ],
+    align=True,
+)
+assert UPDATE_DTYPE.itemsize == 3016, UPDATE_DTYPE.itemsize
+
+SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
+
+
+def build(force: bool = False) -> str:
+    """Run oracle/Makefile (compiles qpOASES from /root/reference when present)."""
+    if force or not os.path.exists(_LIB_PATH) or os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", _HERE, "-j8"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.oracle_has_qpoases.restype = ctypes.c_int
+        L.oracle_sizeof_update_data.restype = ctypes.c_size_t
+        assert L.oracle_sizeof_update_data() == UPDATE_DTYPE.itemsize
+        _lib = L
+    return _lib
+
+
+def has_qpoases() -> bool:
+    return bool(lib().oracle_has_qpoases())
+
+
+def make_setup(horizon: int = 10, dt: float = 0.04, mu: float = 0.25, f_max: float = 500.0) -> np.ndarray:
+    s = np.zeros(1, dtype=SETUP_DTYPE)
+    s["dt"], s["mu"], s["f_max"], s["horizon"] = dt, mu, f_max, horizon
+    return s
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def solve_batch(records: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False):
+    """-> (q_soln [n,12N] f64, info [n,4] i32 = {rc, nWSR, nv_red, nc_red})."""
+    records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+    n = records.shape[0]
+    N = int(setup["horizon"][0])
+    q = np.zeros((n, 12 * N), dtype=np.float64)
+    info = np.zeros((n, 4), dtype=np.int32)
+    if not has_qpoases():
+        raise RuntimeError("oracle was built without qpOASES (no /root/reference and no prebuilt oracle/_ref)")
+    lib().oracle_solve_batch(_p(records), ctypes.c_int(n), _p(setup), ctypes.c_int(int(assembly_fp64)), _p(q), _p(info))
+    return q, info
+
+
+def time_solves(records: np.ndarray, setup: np.ndarray, total: int) -> np.ndarray:
+    """Per-solve wall seconds of `total` single-thread oracle solves (round-robin over records)."""
+    records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+    out = np.zeros(total, dtype=np.float64)
+    lib().oracle_time_solves(_p(records), ctypes.c_int(records.shape[0]), _p(setup), ctypes.c_int(total), _p(out))
+    return out
+
+
+def formulate_f32(record: np.ndarray, setup: np.ndarray) -> dict:
+    """Un-reduced fp32 QP data + intermediates of ONE record (the reference's arithmetic)."""
+    record = np.ascontiguousarray(record, dtype=UPDATE_DTYPE).reshape(1)
+    N = int(setup["horizon"][0])
+    n = 12 * N
+    out = dict(
+        H=np.zeros((n, n), np.float32), g=np.zeros(n, np.float32), Fblk=np.zeros((16, 12), np.float32),
+        lb=np.zeros(16 * N, np.float32), ub=np.zeros(16 * N, np.float32), x0=np.zeros(13, np.float32),
+        Acd=np.zeros((13, 13), np.float32), Bcd=np.zeros((13, 12), np.float32), Rfoot=np.zeros((2, 3, 3), np.float32),
+        R=np.zeros((3, 3), np.float32), A_qp=np.zeros((13 * N, 13), np.float32),
+    )
+    lib().oracle_formulate_f32(_p(record), _p(setup), _p(out["H"]), _p(out["g"]), _p(out["Fblk"]), _p(out["lb"]),
+                               _p(out["ub"]), _p(out["x0"]), _p(out["Acd"]), _p(out["Bcd"]), _p(out["Rfoot"]),
+                               _p(out["R"]), _p(out["A_qp"]))
+    return out
+
+
+def reduced_qp(record: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False) -> dict:
+    """The reduced QP exactly as handed to qpOASES (SolverMPC.cpp:644-697), doubles."""
+    record = np.ascontiguousarray(record, dtype=UPDATE_DTYPE).reshape(1)
+    N = int(setup["horizon"][0])
+    n, m = 12 * N, 16 * N
+    H = np.zeros(n * n); g = np.zeros(n); A = np.zeros(m * n); lb = np.zeros(m); ub = np.zeros(m)
+    vi = np.zeros(n, np.int32); ci = np.zeros(m, np.int32); nc = ctypes.c_int(0)
+    L = lib()
+    L.oracle_reduced_qp.restype = ctypes.c_int
+    nv = L.oracle_reduced_qp(_p(record), _p(setup), ctypes.c_int(int(assembly_fp64)), _p(H), _p(g), _p(A), _p(lb), _p(ub),
+                             _p(vi), _p(ci), ctypes.byref(nc))
+    nc = nc.value
+    return dict(H=H[: nv * nv].reshape(nv, nv).copy(), g=g[:nv].copy(), A=A[: nc * nv].reshape(nc, nv).copy(),
+                lb=lb[:nc].copy(), ub=ub[:nc].copy(), var_ind=vi[:nv].copy(), con_ind=ci[:nc].copy())

@@ -1,0 +1,573 @@
+/*
+ * solve_mpc_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (Eigen-free) of the reference's per-tick convex-MPC QP formulation,
+ *   hector_control/ConvexMPC/SolverMPC.cpp:371-732   (solve_mpc)
+ *   hector_control/ConvexMPC/SolverMPC.cpp:65-89     (euler_to_rotation)
+ *   hector_control/ConvexMPC/SolverMPC.cpp:133-193   (c2qp)
+ *   hector_control/ConvexMPC/SolverMPC.cpp:302-342   (cross_mat, ct_ss_mats, quat_to_rpy)
+ *   hector_control/ConvexMPC/RobotState.cpp:9-53     (RobotState::set)
+ * handing the reduced QP to the reference's own vendored qpOASES 3.2 (compiled unchanged from
+ * /root/reference by oracle/Makefile into oracle/_ref/) exactly as SolverMPC.cpp:702-712 does.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this.  The product library (libhector_mpc_b200.so) never links or calls it.
+ *
+ * PARITY STATUS: *parity unpinned* for the formulation half.  The reference ships no tests or
+ * golden vectors and its formulation needs Eigen, which is neither vendored nor
+ * installed here, so SolverMPC.cpp cannot be compiled.  This file restates its arithmetic:
+ * `float` wherever the reference uses `fpt`, products as plain sequential sums with separately
+ * rounded multiply and add (the reference is built with -O3 and no -march, i.e. SSE2 without FMA,
+ * hector_control/CMakeLists.txt:7; Eigen's GEBP / coefficient-based products accumulate
+ * sequentially in k), 3x3 inverses by the cofactor formula Eigen uses, trig in double then
+ * narrowed.  The QP-solve half IS the reference (qpOASES built from its own sources).
+ *
+ * Build with -ffp-contract=off and WITHOUT -march=native so no FMA contraction can occur.
+ *
+ * Extension: c2qp's loops are hard-coded to 10 (SolverMPC.cpp:148,161,180);
+ * here they run to `horizon`, which is identical at horizon == 10 and is the documented 10->N
+ * generalisation for the horizon-sweep configs.
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <vector>
+
+#include "../include/hector_mpc_b200.h"
+
+#ifdef ORACLE_WITH_QPOASES
+#include <qpOASES.hpp>
+#endif
+
+namespace {
+
+const double kBigNumber = 5e10;  // SolverMPC.cpp:16
+
+// ---- tiny dense helpers, sequential accumulation, no FMA (file is built -ffp-contract=off) ----
+
+// C(rxc) = A(rxk) * B(kxc), row-major, sum over the inner index in increasing order starting
+// from the first product (Eigen: res = a0*b0; res += a1*b1; ...).
+template <class T>
+void matmul(const T* A, const T* B, T* C, int r, int k, int c)
+{
+  for (int i = 0; i < r; i++)
+    for (int j = 0; j < c; j++) {
+      T acc = A[i * k + 0] * B[0 * c + j];
+      for (int t = 1; t < k; t++) acc = acc + A[i * k + t] * B[t * c + j];
+      C[i * c + j] = acc;
+    }
+}
+
+// Eigen's 3x3 inverse (Eigen/src/LU/InverseImpl.h, compute_inverse<...,3>): cofactors, det from
+// the first cofactor column dotted with the first matrix column, multiply by 1/det.
+template <class T>
+T cofactor3(const T* m, int i, int j)
+{
+  int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+}
+template <class T>
+void inverse3(const T* m, T* inv)
+{
+  T c00 = cofactor3(m, 0, 0), c10 = cofactor3(m, 1, 0), c20 = cofactor3(m, 2, 0);
+  T det = (c00 * m[0] + c10 * m[3]) + c20 * m[6];
+  T invdet = T(1) / det;
+  // inverse(j,i) = cofactor(i,j) / det
+  inv[0] = c00 * invdet;
+  inv[1] = c10 * invdet;
+  inv[2] = c20 * invdet;
+  inv[3] = cofactor3(m, 0, 1) * invdet;
+  inv[4] = cofactor3(m, 1, 1) * invdet;
+  inv[5] = cofactor3(m, 2, 1) * invdet;
+  inv[6] = cofactor3(m, 0, 2) * invdet;
+  inv[7] = cofactor3(m, 1, 2) * invdet;
+  inv[8] = cofactor3(m, 2, 2) * invdet;
+}
+
+// Quaternionf::toRotationMatrix() (Eigen/src/Geometry/Quaternion.h); q = (w,x,y,z).
+template <class T>
+void quat_to_R(const T* q, T* R)
+{
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  T tx = T(2) * x, ty = T(2) * y, tz = T(2) * z;
+  T twx = tx * w, twy = ty * w, twz = tz * w;
+  T txx = tx * x, txy = ty * x, txz = tz * x;
+  T tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = T(1) - (tyy + tzz);
+  R[1] = txy - twz;
+  R[2] = txz + twy;
+  R[3] = txy + twz;
+  R[4] = T(1) - (txx + tzz);
+  R[5] = tyz - twx;
+  R[6] = txz - twy;
+  R[7] = tyz + twx;
+  R[8] = T(1) - (txx + tyy);
+}
+
+// Foot rotation of one leg from its five (offset-corrected) joint angles: SolverMPC.cpp:428-433.
+// Same expression tree as the reference (double arithmetic, narrowed to T on store); written
+// with named sub-terms instead of one literal.
+template <class T>
+void foot_rotation(const T* q, T* Rf)
+{
+  double s0 = sin((double)q[0]), c0 = cos((double)q[0]);
+  double s1 = sin((double)q[1]), c1 = cos((double)q[1]);
+  double s2 = sin((double)q[2]), c2 = cos((double)q[2]);
+  double s3 = sin((double)q[3]), c3 = cos((double)q[3]);
+  double s4 = sin((double)q[4]), c4 = cos((double)q[4]);
+  // recurring brackets of the reference expression
+  double a = c0 * s2 + c2 * s0 * s1;        // (cos(q0)*sin(q2) + cos(q2)*sin(q0)*sin(q1))
+  double b = c0 * c2 - 1.0 * s0 * s1 * s2;  // (cos(q0)*cos(q2) - sin(q0)*sin(q1)*sin(q2))
+  double c = c2 * s0 + c0 * s1 * s2;        // (cos(q2)*sin(q0) + cos(q0)*sin(q1)*sin(q2))
+  double d = s0 * s2 - 1.0 * c0 * c2 * s1;  // (sin(q0)*sin(q2) - cos(q0)*cos(q2)*sin(q1))
+  // the sum q2+q3+q4 is formed in the matrix scalar type (floats in the reference)
+  T q234 = q[2] + q[3] + q[4];
+  Rf[0] = (T)(-1.0 * s4 * (c3 * a + s3 * b) - c4 * (1.0 * s3 * a - c3 * b));
+  Rf[1] = (T)(-1.0 * c1 * s0);
+  Rf[2] = (T)(c4 * (c3 * a + s3 * b) - s4 * (1.0 * s3 * a - c3 * b));
+  Rf[3] = (T)(c4 * (c3 * c - 1.0 * s3 * d) - 1.0 * s4 * (s3 * c + c3 * d));
+  Rf[4] = (T)(c0 * c1);
+  Rf[5] = (T)(c4 * (s3 * c + c3 * d) + s4 * (c3 * c - 1.0 * s3 * d));
+  Rf[6] = (T)(-1.0 * sin((double)q234) * c1);
+  Rf[7] = (T)(s1);
+  Rf[8] = (T)(cos((double)q234) * c1);
+}
+
+}  // namespace
+
+// Everything the formulation produces, for parity checks of intermediate stages.
+template <class T>
+struct Formulation {
+  int N = 0;
+  T q[10];
+  T R[9];
+  T rpy[3];
+  T Rb[9];
+  T x0[13];
+  T I_world[9];
+  T A_ct[169];
+  T B_ct[156];
+  T Rfoot[2][9];
+  T Acd[169];
+  T Bcd[156];
+  std::vector<T> A_qp;  // 13N x 13
+  std::vector<T> B_qp;  // 13N x 12N
+  T Fblk[192];          // F_control 16 x 12
+  std::vector<T> lb, ub;  // 16N
+  std::vector<T> H;       // 12N x 12N
+  std::vector<T> g;       // 12N
+};
+
+template <class T>
+static void formulate(const update_data_t* u, const problem_setup* setup, Formulation<T>& F)
+{
+  const int N = setup->horizon;
+  const int nx = 13 * N, nu = 12 * N, nc = 16 * N;
+  F.N = N;
+
+  // ---- SolverMPC.cpp:374-393 joint angles, offsets, fmod --------------------------------------
+  const double PI = 3.14159265359;
+  for (int i = 0; i < 10; i++) F.q[i] = (T)u->joint_angles[i];
+  F.q[2] = (T)((double)F.q[2] + 0.3 * PI);
+  F.q[3] = (T)((double)F.q[3] - 0.6 * PI);
+  F.q[4] = (T)((double)F.q[4] + 0.3 * PI);
+  F.q[7] = (T)((double)F.q[7] + 0.3 * PI);
+  F.q[8] = (T)((double)F.q[8] - 0.6 * PI);
+  F.q[9] = (T)((double)F.q[9] + 0.3 * PI);
+  const double PI2 = 2 * PI;
+  for (int i = 0; i < 10; i++) F.q[i] = (T)fmod((double)F.q[i], PI2);
+
+  // ---- RobotState.cpp:9-53 ---------------------------------------------------------------------
+  T quat[4] = {(T)u->q[0], (T)u->q[1], (T)u->q[2], (T)u->q[3]};
+  quat_to_R(quat, F.R);
+  T r_feet[3][2];
+  for (int rs = 0; rs < 3; rs++)
+    for (int c = 0; c < 2; c++) r_feet[rs][c] = (T)u->r[rs * 2 + c];
+  const T I_body[3] = {(T)0.5413, (T)0.5200, (T)0.0691};
+
+  // ---- SolverMPC.cpp:333-342 quat_to_rpy --------------------------------------------------------
+  {
+    T qw = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
+    double as_d = 2. * (double)(qw * qy - qx * qz);
+    if (!(as_d < .99999)) as_d = .99999;  // t_min(a,b): a<b ? a : b
+    T as = (T)as_d;
+    F.rpy[0] = (T)atan2((double)((T)2 * (qw * qx + qy * qz)), 1. - (double)((T)2 * (qx * qx + qy * qy)));
+    F.rpy[1] = (T)asin((double)as);
+    F.rpy[2] = (T)atan2((double)((T)2 * (qw * qz + qx * qy)), 1. - (double)((T)2 * (qy * qy + qz * qz)));
+  }
+  // ---- SolverMPC.cpp:65-89 euler_to_rotation (Rb = inverse of the rate map) --------------------
+  {
+    double p = (double)F.rpy[1], y = (double)F.rpy[2];
+    T Rbm[9] = {(T)(cos(y) * cos(p)), (T)(-sin(y)), (T)0,
+                (T)(sin(y) * cos(p)), (T)(cos(y)),  (T)0,
+                (T)(-sin(p)),         (T)0,         (T)1};
+    inverse3(Rbm, F.Rb);
+  }
+  // ---- SolverMPC.cpp:420-421 --------------------------------------------------------------------
+  for (int i = 0; i < 3; i++) {
+    F.x0[i] = F.rpy[i];
+    F.x0[3 + i] = (T)u->p[i];
+    F.x0[6 + i] = (T)u->w[i];
+    F.x0[9 + i] = (T)u->v[i];
+  }
+  F.x0[12] = (T)9.81f;
+  {
+    // I_world = (R * I_body) * R^T ; I_body diagonal so (R*I_body)(i,k) = R(i,k)*Id[k] exactly
+    T RI[9], Rt[9];
+    for (int i = 0; i < 3; i++)
+      for (int k = 0; k < 3; k++) {
+        RI[i * 3 + k] = F.R[i * 3 + k] * I_body[k];
+        Rt[i * 3 + k] = F.R[k * 3 + i];
+      }
+    matmul(RI, Rt, F.I_world, 3, 3, 3);
+  }
+  // ---- SolverMPC.cpp:312-331 ct_ss_mats, m = 9.0 (SolverMPC.cpp:423) ---------------------------
+  {
+    memset(F.A_ct, 0, sizeof(F.A_ct));
+    memset(F.B_ct, 0, sizeof(F.B_ct));
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) F.A_ct[i * 13 + 6 + j] = F.Rb[i * 3 + j];
+    for (int i = 0; i < 3; i++) F.A_ct[(3 + i) * 13 + 9 + i] = (T)1;
+    F.A_ct[11 * 13 + 12] = (T)-1;
+    T I_inv[9];
+    inverse3(F.I_world, I_inv);
+    const T m = (T)9.0;
+    for (int b = 0; b < 2; b++) {
+      T rx = r_feet[0][b], ry = r_feet[1][b], rz = r_feet[2][b];
+      T cm[9] = {(T)0, -rz, ry, rz, (T)0, -rx, -ry, rx, (T)0};
+      T blk[9];
+      matmul(I_inv, cm, blk, 3, 3, 3);
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) F.B_ct[(6 + i) * 12 + b * 3 + j] = blk[i * 3 + j];
+    }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        F.B_ct[(6 + i) * 12 + 6 + j] = I_inv[i * 3 + j];
+        F.B_ct[(6 + i) * 12 + 9 + j] = I_inv[i * 3 + j];
+      }
+    for (int i = 0; i < 3; i++) {
+      F.B_ct[(9 + i) * 12 + 0 + i] = (T)1 / m;
+      F.B_ct[(9 + i) * 12 + 3 + i] = (T)1 / m;
+    }
+  }
+  // ---- SolverMPC.cpp:426-433 foot rotations ----------------------------------------------------
+  foot_rotation(&F.q[0], F.Rfoot[0]);
+  foot_rotation(&F.q[5], F.Rfoot[1]);
+
+  // ---- SolverMPC.cpp:133-193 c2qp (forward Euler, re-powered blocks) ---------------------------
+  {
+    const T dt = (T)setup->dt;
+    for (int i = 0; i < 169; i++) F.Acd[i] = ((i / 13 == i % 13) ? (T)1 : (T)0) + dt * F.A_ct[i];
+    for (int i = 0; i < 156; i++) F.Bcd[i] = dt * F.B_ct[i];
+    F.A_qp.assign((size_t)nx * 13, (T)0);
+    F.B_qp.assign((size_t)nx * nu, (T)0);
+    // powers P_k = (((I*Acd)*Acd)*...)  (Acdm *= Acd, k times).  I*Acd == Acd exactly.
+    std::vector<T> P((size_t)(N + 1) * 169);
+    for (int i = 0; i < 169; i++) P[i] = (i / 13 == i % 13) ? (T)1 : (T)0;
+    for (int k = 1; k <= N; k++) matmul(&P[(size_t)(k - 1) * 169], F.Acd, &P[(size_t)k * 169], 13, 13, 13);
+    for (int i = 0; i < N; i++) memcpy(&F.A_qp[(size_t)i * 169], &P[(size_t)(i + 1) * 169], 169 * sizeof(T));
+    // B_qp(i,j) = P_{i-j} * Bcd for j <= i.  (P_0 * Bcd == Bcd exactly: 1*x + 0*y sums are exact.)
+    std::vector<T> M((size_t)N * 156);
+    for (int d = 0; d < N; d++) matmul(&P[(size_t)d * 169], F.Bcd, &M[(size_t)d * 156], 13, 13, 12);
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j <= i; j++)
+        for (int r = 0; r < 13; r++)
+          for (int c = 0; c < 12; c++)
+            F.B_qp[(size_t)(13 * i + r) * nu + 12 * j + c] = M[(size_t)(i - j) * 156 + r * 12 + c];
+  }
+
+  // ---- SolverMPC.cpp:466-482 bounds -------------------------------------------------------------
+  F.lb.assign(nc, (T)0);
+  F.ub.assign(nc, (T)0);
+  for (int leg = 0; leg < 2; leg++)
+    for (int i = 0; i < N; i++) {
+      for (int j = 0; j < 4; j++) {
+        F.ub[8 * leg + j + 16 * i] = (T)kBigNumber;
+        F.lb[8 * leg + j + 16 * i] = (T)0.0f;
+      }
+      F.ub[8 * leg + 4 + 16 * i] = (T)0.01f;
+      F.ub[8 * leg + 5 + 16 * i] = (T)0.0f;
+      F.ub[8 * leg + 6 + 16 * i] = (T)0.0f;
+      F.ub[8 * leg + 7 + 16 * i] = (T)setup->f_max * (T)u->gait[2 * i + leg];
+      F.lb[8 * leg + 4 + 16 * i] = (T)0.0f;
+      F.lb[8 * leg + 5 + 16 * i] = (T)(-kBigNumber);
+      F.lb[8 * leg + 6 + 16 * i] = (T)(-kBigNumber);
+      F.lb[8 * leg + 7 + 16 * i] = (T)0.0f;
+    }
+
+  // ---- SolverMPC.cpp:488-548 F_control ----------------------------------------------------------
+  {
+    const T mu = (T)2.0;  // local literal shadows setup->mu (quirk Q3)
+    const T lt = (T)0.09, lh = (T)0.06;
+    memset(F.Fblk, 0, sizeof(F.Fblk));
+    T* Fc = F.Fblk;
+    for (int leg = 0; leg < 2; leg++) {
+      const int r0 = 8 * leg, cF = 3 * leg, cM = 6 + 3 * leg;
+      const T* Rf = F.Rfoot[leg];
+      Fc[(r0 + 0) * 12 + cF + 0] = -mu; Fc[(r0 + 0) * 12 + cF + 2] = (T)1;
+      Fc[(r0 + 1) * 12 + cF + 0] = mu;  Fc[(r0 + 1) * 12 + cF + 2] = (T)1;
+      Fc[(r0 + 2) * 12 + cF + 1] = -mu; Fc[(r0 + 2) * 12 + cF + 2] = (T)1;
+      Fc[(r0 + 3) * 12 + cF + 1] = mu;  Fc[(r0 + 3) * 12 + cF + 2] = (T)1;
+      // v * R_foot^T * R^T evaluated left to right; the selector vectors have a single non-zero
+      // so the first product is exact: (e_k * s) * R_foot^T = s * R_foot(:,k)^T.
+      T xw[3], yw[3], zlt[3], zlh[3];
+      for (int j = 0; j < 3; j++) {
+        // second product: sum_k v1(k) * R(j,k), k = 0,1,2
+        T v1x[3] = {Rf[0], Rf[3], Rf[6]};                       // Moment_selection -> column 0
+        T v1y[3] = {Rf[1], Rf[4], Rf[7]};                       // M_vec -> column 1
+        T v1t[3] = {-lt * Rf[2], -lt * Rf[5], -lt * Rf[8]};     // -lt_vec -> column 2 scaled
+        T v1h[3] = {-lh * Rf[2], -lh * Rf[5], -lh * Rf[8]};     // -lh_vec
+        xw[j] = (v1x[0] * F.R[j * 3 + 0] + v1x[1] * F.R[j * 3 + 1]) + v1x[2] * F.R[j * 3 + 2];
+        yw[j] = (v1y[0] * F.R[j * 3 + 0] + v1y[1] * F.R[j * 3 + 1]) + v1y[2] * F.R[j * 3 + 2];
+        zlt[j] = (v1t[0] * F.R[j * 3 + 0] + v1t[1] * F.R[j * 3 + 1]) + v1t[2] * F.R[j * 3 + 2];
+        zlh[j] = (v1h[0] * F.R[j * 3 + 0] + v1h[1] * F.R[j * 3 + 1]) + v1h[2] * F.R[j * 3 + 2];
+      }
+      for (int j = 0; j < 3; j++) {
+        Fc[(r0 + 4) * 12 + cM + j] = xw[j];
+        Fc[(r0 + 5) * 12 + cF + j] = zlt[j];
+        Fc[(r0 + 5) * 12 + cM + j] = yw[j];
+        Fc[(r0 + 6) * 12 + cF + j] = zlh[j];
+        // left foot uses -M_vec, right foot +M_vec (quirk Q5, SolverMPC.cpp:525-526 vs 545-546)
+        Fc[(r0 + 6) * 12 + cM + j] = (leg == 0) ? -yw[j] : yw[j];
+      }
+      Fc[(r0 + 7) * 12 + cF + 2] = (T)2;
+    }
+  }
+
+  // ---- SolverMPC.cpp:450-461, 557-570 cost ------------------------------------------------------
+  {
+    std::vector<T> wdiag(nx), Xd(nx, (T)0);
+    for (int i = 0; i < N; i++) {
+      for (int j = 0; j < 12; j++) {
+        wdiag[13 * i + j] = (T)u->weights[j];
+        Xd[13 * i + j] = (T)u->traj[12 * i + j];
+      }
+      wdiag[13 * i + 12] = (T)0;
+    }
+    // T1 = B^T * S  (S diagonal stored dense: every other product is an exact zero)
+    std::vector<T> T1((size_t)nu * nx);
+    for (int i = 0; i < nu; i++)
+      for (int k = 0; k < nx; k++) T1[(size_t)i * nx + k] = F.B_qp[(size_t)k * nu + i] * wdiag[k];
+    F.H.assign((size_t)nu * nu, (T)0);
+    for (int i = 0; i < nu; i++)
+      for (int j = 0; j < nu; j++) {
+        T acc = T1[(size_t)i * nx] * F.B_qp[j];
+        for (int k = 1; k < nx; k++) acc = acc + T1[(size_t)i * nx + k] * F.B_qp[(size_t)k * nu + j];
+        T alpha = (i == j) ? (T)u->Alpha_K[i % 12] : (T)0;
+        F.H[(size_t)i * nu + j] = (T)2 * (acc + alpha);
+      }
+    // d = A_qp * x0 - X_d ; g = (2*B^T*S) * d
+    std::vector<T> d(nx);
+    for (int r = 0; r < nx; r++) {
+      T acc = F.A_qp[(size_t)r * 13] * F.x0[0];
+      for (int c = 1; c < 13; c++) acc = acc + F.A_qp[(size_t)r * 13 + c] * F.x0[c];
+      d[r] = acc - Xd[r];
+    }
+    F.g.assign(nu, (T)0);
+    for (int i = 0; i < nu; i++) {
+      T acc = (T1[(size_t)i * nx] * (T)2) * d[0];
+      for (int k = 1; k < nx; k++) acc = acc + (T1[(size_t)i * nx + k] * (T)2) * d[k];
+      F.g[i] = acc;
+    }
+  }
+}
+
+// ---- SolverMPC.cpp:589-637 swing-leg elimination -------------------------------------------------
+static inline bool near_zero_f(float a) { return (a < 0.0001 && a > -.0001); }
+static inline bool near_two_f(float a) { return near_zero_f(a - 2); }
+
+struct ReducedQP {
+  int nv = 0, nc = 0;
+  std::vector<int> var_ind, con_ind;
+  std::vector<double> H, g, A, lb, ub;
+};
+
+template <class T>
+static void eliminate(const Formulation<T>& F, ReducedQP& Q)
+{
+  const int N = F.N, nu = 12 * N, ncon = 16 * N;
+  std::vector<char> var_elim(nu + 16, 0), con_elim(ncon + 16, 0);
+  for (int i = 0; i < ncon; i++) {
+    if (!(near_zero_f((float)(double)F.lb[i]) && near_zero_f((float)(double)F.ub[i]))) continue;
+    // row i of the block-diagonal constraint matrix
+    const int step = i / 16, lr = i % 16;
+    for (int j = 0; j < nu; j++) {
+      double c = (j / 12 == step) ? (double)F.Fblk[lr * 12 + j % 12] : 0.0;
+      if (near_two_f((float)c)) {
+        int cs = (j % 2 == 0) ? (j + 4) / 6 * 8 - 1 : (j + 1) / 6 * 8 + 7;
+        var_elim[j + 6] = var_elim[j + 5] = var_elim[j + 4] = 1;
+        var_elim[j - 2] = var_elim[j - 1] = var_elim[j] = 1;
+        for (int k = 0; k < 8; k++) con_elim[cs - k] = 1;
+      }
+    }
+  }
+  Q.var_ind.clear();
+  Q.con_ind.clear();
+  for (int i = 0; i < nu; i++)
+    if (!var_elim[i]) Q.var_ind.push_back(i);
+  for (int i = 0; i < ncon; i++)
+    if (!con_elim[i]) Q.con_ind.push_back(i);
+  Q.nv = (int)Q.var_ind.size();
+  Q.nc = (int)Q.con_ind.size();
+  Q.H.resize((size_t)Q.nv * Q.nv);
+  Q.g.resize(Q.nv);
+  Q.A.resize((size_t)Q.nc * Q.nv);
+  Q.lb.resize(Q.nc);
+  Q.ub.resize(Q.nc);
+  for (int i = 0; i < Q.nv; i++) {
+    int oa = Q.var_ind[i];
+    Q.g[i] = (double)F.g[oa];
+    for (int j = 0; j < Q.nv; j++) Q.H[(size_t)i * Q.nv + j] = (double)F.H[(size_t)oa * nu + Q.var_ind[j]];
+  }
+  for (int c = 0; c < Q.nc; c++) {
+    int oc = Q.con_ind[c];
+    for (int s = 0; s < Q.nv; s++) {
+      int ov = Q.var_ind[s];
+      double v = (ov / 12 == oc / 16) ? (double)F.Fblk[(oc % 16) * 12 + ov % 12] : 0.0;
+      Q.A[(size_t)c * Q.nv + s] = (double)(float)v;  // `float cval = ...` SolverMPC.cpp:687
+    }
+    Q.lb[c] = (double)F.lb[oc];
+    Q.ub[c] = (double)F.ub[oc];
+  }
+}
+
+// ---- SolverMPC.cpp:702-712 : the reference's own solver, called the reference's way --------------
+static int solve_reduced(ReducedQP& Q, std::vector<double>& x, int* nwsr_out)
+{
+#ifdef ORACLE_WITH_QPOASES
+  x.assign(Q.nv > 0 ? Q.nv : 1, 0.0);
+  if (Q.nv == 0) { if (nwsr_out) *nwsr_out = 0; return 0; }
+  qpOASES::int_t nWSR = 500;
+  qpOASES::QProblem problem_red(Q.nv, Q.nc);
+  qpOASES::Options op;
+  op.setToMPC();
+  op.printLevel = qpOASES::PL_NONE;
+  problem_red.setOptions(op);
+  int rval = problem_red.init(Q.H.data(), Q.g.data(), Q.A.data(), NULL, NULL, Q.lb.data(), Q.ub.data(), nWSR);
+  int rval2 = problem_red.getPrimalSolution(x.data());
+  if (nwsr_out) *nwsr_out = (int)nWSR;
+  return (rval2 != qpOASES::SUCCESSFUL_RETURN) ? 1000 + rval2 : (rval != qpOASES::SUCCESSFUL_RETURN ? rval : 0);
+#else
+  (void)Q; (void)x; (void)nwsr_out;
+  return -1;
+#endif
+}
+
+template <class T>
+static int solve_one(const update_data_t* u, const problem_setup* s, double* q_soln, int* info)
+{
+  Formulation<T> F;
+  formulate<T>(u, s, F);
+  ReducedQP Q;
+  eliminate(F, Q);
+  std::vector<double> x;
+  int nwsr = 0;
+  int rc = solve_reduced(Q, x, &nwsr);
+  const int nu = 12 * s->horizon;
+  // SolverMPC.cpp:720-732 scatter, eliminated variables = 0
+  for (int i = 0; i < nu; i++) q_soln[i] = 0.0;
+  for (int i = 0; i < Q.nv; i++) q_soln[Q.var_ind[i]] = x[i];
+  if (info) { info[0] = rc; info[1] = nwsr; info[2] = Q.nv; info[3] = Q.nc; }
+  return rc;
+}
+
+// =================================================================================================
+// C entry points (ctypes-friendly)
+// =================================================================================================
+extern "C" {
+
+int oracle_has_qpoases(void)
+{
+#ifdef ORACLE_WITH_QPOASES
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+size_t oracle_sizeof_update_data(void) { return sizeof(update_data_t); }
+
+/* Solve `n` records.  assembly_fp64 = 0: the reference's arithmetic (fp32 formulation, fp64 solve);
+ * 1: the same formulation carried in double (sensitivity probe, not the reference).
+ * q_soln [n][12N]; info [n][4] = {return code, nWSR, reduced vars, reduced cons}. */
+int oracle_solve_batch(const update_data_t* u, int n, const problem_setup* s, int assembly_fp64,
+                       double* q_soln, int* info)
+{
+  int bad = 0;
+  const int nu = 12 * s->horizon;
+  for (int i = 0; i < n; i++) {
+    int rc = assembly_fp64 ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL)
+                           : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL);
+    if (rc) bad++;
+  }
+  return bad;
+}
+
+/* Timed variant for the CPU baseline: solves records [0,n) `reps` times round-robin on the calling
+ * thread and returns per-solve wall times (seconds) measured with clock_gettime(CLOCK_MONOTONIC)
+ * like the reference's Timer (include/common/Utilities/Timer.h:15-49).  The timed region is the
+ * equivalent of SolverMPC.cpp:374-732 plus the per-tick buffer (re)allocation the reference does in
+ * resize_qp_mats (all formulation buffers here are allocated per call, as there). */
+int oracle_time_solves(const update_data_t* u, int n, const problem_setup* s, int total,
+                       double* seconds_out)
+{
+  std::vector<double> q((size_t)12 * s->horizon);
+  int info[4];
+  int bad = 0;
+  for (int t = 0; t < total; t++) {
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    int rc = solve_one<float>(&u[t % n], s, q.data(), info);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    if (rc) bad++;
+    seconds_out[t] = (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+  }
+  return bad;
+}
+
+/* Formulation only (fp32, the reference's arithmetic): full un-reduced QP data of one record.
+ * H [n*n] row-major, g [n], Fblk [192], lb/ub [16N]; optional intermediates (may be NULL):
+ * x0 [13], Acd [169], Bcd [156], Rfoot [18], Rmat [9], A_qp [13N*13]. */
+int oracle_formulate_f32(const update_data_t* u, const problem_setup* s, float* H, float* g, float* Fblk,
+                         float* lb, float* ub, float* x0, float* Acd, float* Bcd, float* Rfoot,
+                         float* Rmat, float* A_qp)
+{
+  Formulation<float> F;
+  formulate<float>(u, s, F);
+  const int N = s->horizon, nu = 12 * N;
+  if (H) memcpy(H, F.H.data(), sizeof(float) * (size_t)nu * nu);
+  if (g) memcpy(g, F.g.data(), sizeof(float) * nu);
+  if (Fblk) memcpy(Fblk, F.Fblk, sizeof(F.Fblk));
+  if (lb) memcpy(lb, F.lb.data(), sizeof(float) * 16 * N);
+  if (ub) memcpy(ub, F.ub.data(), sizeof(float) * 16 * N);
+  if (x0) memcpy(x0, F.x0, sizeof(F.x0));
+  if (Acd) memcpy(Acd, F.Acd, sizeof(F.Acd));
+  if (Bcd) memcpy(Bcd, F.Bcd, sizeof(F.Bcd));
+  if (Rfoot) memcpy(Rfoot, F.Rfoot, sizeof(F.Rfoot));
+  if (Rmat) memcpy(Rmat, F.R, sizeof(F.R));
+  if (A_qp) memcpy(A_qp, F.A_qp.data(), sizeof(float) * (size_t)13 * N * 13);
+  return 0;
+}
+
+/* The reduced QP exactly as handed to qpOASES (doubles), for independent QP cross-checks.
+ * Buffers sized for the un-reduced problem.  Returns nv, writes nc. */
+int oracle_reduced_qp(const update_data_t* u, const problem_setup* s, int assembly_fp64, double* H,
+                      double* g, double* A, double* lb, double* ub, int* var_ind, int* con_ind, int* nc_out)
+{
+  ReducedQP Q;
+  if (assembly_fp64) { Formulation<double> F; formulate<double>(u, s, F); eliminate(F, Q); }
+  else { Formulation<float> F; formulate<float>(u, s, F); eliminate(F, Q); }
+  memcpy(H, Q.H.data(), sizeof(double) * Q.H.size());
+  memcpy(g, Q.g.data(), sizeof(double) * Q.g.size());
+  memcpy(A, Q.A.data(), sizeof(double) * Q.A.size());
+  memcpy(lb, Q.lb.data(), sizeof(double) * Q.lb.size());
+  memcpy(ub, Q.ub.data(), sizeof(double) * Q.ub.size());
+  memcpy(var_ind, Q.var_ind.data(), sizeof(int) * Q.nv);
+  memcpy(con_ind, Q.con_ind.data(), sizeof(int) * Q.nc);
+  *nc_out = Q.nc;
+  return Q.nv;
+}
+
+}  // extern "C"
