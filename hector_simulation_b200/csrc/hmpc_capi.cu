@@ -1,0 +1,401 @@
+// hmpc_capi.cu — host side of libhector_mpc_b200.so: the C-ABI declared in include/hector_mpc_b200.h.
+//
+// Part 1 re-exports the reference's boundary (convexMPC_interface.h:39-43) on top of a one-robot
+// context; part 2 is the batched interface.  There is no CPU solve path in this library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/hector_mpc_b200.h"
+#include "hmpc_device.cuh"
+
+static_assert(sizeof(update_data_t) == 3016, "update_data_t must match convexMPC_interface.h:19-37");
+static_assert(sizeof(problem_setup) == 16, "problem_setup must match convexMPC_interface.h:11-17");
+
+namespace {
+
+thread_local std::string g_err;
+
+bool cuda_fail(cudaError_t e, const char* what)
+{
+  if (e == cudaSuccess) return false;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return true;
+}
+#define CK(call)                          \
+  do {                                    \
+    if (cuda_fail((call), #call)) return HMPC_ERR_CUDA; \
+  } while (0)
+
+struct ClassCfg {
+  int nb_lo, nb_hi, nb_cap, qmax, threads, smem, grid_cap, maxt;
+};
+
+int round32(int x) { return (x + 31) / 32 * 32; }
+
+}  // namespace
+
+struct hmpc_ctx {
+  int device = 0, max_batch = 0, horizon = 0, rec_stride = 0, sm_count = 0;
+  problem_setup setup{};
+  ClassCfg cls[2];
+  int ncls = 0;
+  unsigned char* d_rec = nullptr;
+  float* d_wrench = nullptr;
+  int* d_status = nullptr;
+  unsigned char* h_rec = nullptr;  // pinned
+  float* h_wrench = nullptr;       // pinned
+  int* h_status = nullptr;         // pinned
+  cudaStream_t stream = nullptr;
+  int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
+};
+
+namespace {
+
+template <int MAXT, int MINB>
+cudaError_t prep_kernel(int smem, int threads, int* occ)
+{
+  auto k = hmpc::hmpc_solve_kernel<MAXT, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, threads, smem);
+}
+
+cudaError_t prep_class(ClassCfg& c, int* occ)
+{
+  if (c.threads <= 64) { c.maxt = 64; return prep_kernel<64, 8>(c.smem, c.threads, occ); }
+  if (c.threads <= 224) { c.maxt = 224; return prep_kernel<224, 2>(c.smem, c.threads, occ); }
+  c.maxt = 544;
+  return prep_kernel<544, 1>(c.smem, c.threads, occ);
+}
+
+cudaError_t launch_class(const ClassCfg& c, const hmpc::KernelArgs& ka, int grid, cudaStream_t st)
+{
+  if (c.maxt == 64) hmpc::hmpc_solve_kernel<64, 8><<<grid, c.threads, c.smem, st>>>(ka);
+  else if (c.maxt == 224) hmpc::hmpc_solve_kernel<224, 2><<<grid, c.threads, c.smem, st>>>(ka);
+  else hmpc::hmpc_solve_kernel<544, 1><<<grid, c.threads, c.smem, st>>>(ka);
+  return cudaGetLastError();
+}
+
+// largest working-set capacity whose solver view still fits under `limit` bytes of union
+int fit_qmax(int N, int nb_cap, int rec_stride, int want_min)
+{
+  int q = want_min;
+  const int base = hmpc::make_layout(N, nb_cap, want_min, rec_stride).total;
+  while (q < 6 * nb_cap && hmpc::make_layout(N, nb_cap, q + 1, rec_stride).total <= base) q++;
+  return q;
+}
+
+int build_classes(hmpc_ctx* c)
+{
+  const int N = c->horizon;
+  // class 0: at most N blocks of 6 variables (e.g. any single-support schedule); class 1: up to 2N.
+  const int caps[2] = {N, 2 * N};
+  c->ncls = 2;
+  int prev = -1;
+  for (int i = 0; i < 2; i++) {
+    ClassCfg& k = c->cls[i];
+    k.nb_lo = prev;
+    k.nb_hi = caps[i];
+    k.nb_cap = caps[i];
+    prev = caps[i];
+    const int n = 6 * k.nb_cap;
+    k.qmax = fit_qmax(N, k.nb_cap, c->rec_stride, n < 64 ? n : 64);
+    k.threads = round32(k.nb_cap * (k.nb_cap + 1) / 2);
+    if (k.threads < 64) k.threads = 64;
+    k.smem = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride).total;
+    int occ = 0;
+    if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (is this an sm_100a device?)")) return HMPC_ERR_CUDA;
+    if (occ < 1) { g_err = "kernel does not fit on this device"; return HMPC_ERR_CUDA; }
+    k.grid_cap = occ * c->sm_count;
+  }
+  return HMPC_OK;
+}
+
+hmpc::KernelArgs base_args(const hmpc_ctx* c, const void* d_records, int B, float* d_wrench, int* d_status)
+{
+  hmpc::KernelArgs ka{};
+  ka.records = static_cast<const unsigned char*>(d_records);
+  ka.rec_stride = c->rec_stride;
+  ka.batch = B;
+  ka.horizon = c->horizon;
+  ka.dt = c->setup.dt;
+  ka.f_max = c->setup.f_max;
+  ka.max_iter = c->max_iter;
+  ka.wrench = d_wrench;
+  ka.status = d_status;
+  return ka;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// records
+// ---------------------------------------------------------------------------------------------------
+HMPC_EXTERNC size_t hmpc_record_bytes(int horizon)
+{
+  if (horizon < 1 || horizon > 18) return 0;
+  size_t b = (size_t)(54 + 12 * horizon) * 4 + (size_t)2 * horizon;
+  return (b + 15) / 16 * 16;
+}
+
+HMPC_EXTERNC int hmpc_pack_records(const update_data_t* in, int n, int horizon, void* out)
+{
+  const size_t stride = hmpc_record_bytes(horizon);
+  if (!in || !out || n < 0 || stride == 0) { g_err = "hmpc_pack_records: bad argument"; return HMPC_ERR_ARG; }
+  unsigned char* o = static_cast<unsigned char*>(out);
+  for (int i = 0; i < n; i++, o += stride) {
+    const update_data_t& u = in[i];
+    float* f = reinterpret_cast<float*>(o);
+    memcpy(f + 0, u.p, 12);
+    memcpy(f + 3, u.v, 12);
+    memcpy(f + 6, u.q, 16);
+    memcpy(f + 10, u.w, 12);
+    memcpy(f + 13, u.r, 24);
+    memcpy(f + 19, u.joint_angles, 40);
+    f[29] = u.yaw;
+    memcpy(f + 30, u.weights, 48);
+    memcpy(f + 42, u.Alpha_K, 48);
+    memcpy(f + 54, u.traj, (size_t)48 * horizon);
+    unsigned char* g = o + (size_t)(54 + 12 * horizon) * 4;
+    memcpy(g, u.gait, (size_t)2 * horizon);
+    memset(g + 2 * horizon, 0, stride - ((size_t)(54 + 12 * horizon) * 4 + 2 * horizon));
+  }
+  return HMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+HMPC_EXTERNC const char* hmpc_last_error(void) { return g_err.c_str(); }
+
+HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->d_rec) cudaFree(c->d_rec);
+  if (c->d_wrench) cudaFree(c->d_wrench);
+  if (c->d_status) cudaFree(c->d_status);
+  if (c->h_rec) cudaFreeHost(c->h_rec);
+  if (c->h_wrench) cudaFreeHost(c->h_wrench);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
+{
+  if (max_batch < 1 || horizon < 1 || horizon > HMPC_MAX_HORIZON) {
+    g_err = "hmpc_create: need max_batch >= 1 and 1 <= horizon <= 16";
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0) {
+    g_err = "hmpc_create: no usable CUDA device (this library has no CPU path)";
+    return nullptr;
+  }
+  hmpc_ctx* c = new hmpc_ctx;
+  c->device = device;
+  c->max_batch = max_batch;
+  c->horizon = horizon;
+  c->rec_stride = (int)hmpc_record_bytes(horizon);
+  c->setup.dt = 0.04f;
+  c->setup.mu = 0.25f;
+  c->setup.f_max = 500.f;
+  c->setup.horizon = horizon;
+  cudaDeviceProp prop{};
+  bool bad = cuda_fail(cudaSetDevice(device), "cudaSetDevice") ||
+             cuda_fail(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  if (!bad && prop.major != 10) {
+    g_err = "hmpc_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+            std::to_string(prop.minor);
+    bad = true;
+  }
+  if (!bad) {
+    c->sm_count = prop.multiProcessorCount;
+    const size_t nw = (size_t)12 * horizon;
+    bad = cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+          cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
+          cuda_fail(cudaMalloc(&c->d_wrench, (size_t)max_batch * nw * 4), "cudaMalloc wrench") ||
+          cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
+          cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
+          cuda_fail(cudaMallocHost(&c->h_wrench, (size_t)max_batch * nw * 4), "cudaMallocHost wrench") ||
+          cuda_fail(cudaMallocHost(&c->h_status, (size_t)max_batch * 4), "cudaMallocHost status") ||
+          build_classes(c) != HMPC_OK;
+  }
+  if (bad) {
+    std::string keep = g_err;
+    hmpc_destroy(c);
+    g_err = keep;
+    return nullptr;
+  }
+  return c;
+}
+
+HMPC_EXTERNC int hmpc_set_problem(hmpc_ctx* c, const problem_setup* s)
+{
+  if (!c || !s) { g_err = "hmpc_set_problem: null argument"; return HMPC_ERR_ARG; }
+  if (s->horizon != c->horizon) { g_err = "hmpc_set_problem: horizon differs from the context's"; return HMPC_ERR_ARG; }
+  c->setup = *s;
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls : 0; }
+
+HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* c, const void* d_records, int B, float* d_wrench, int* d_status,
+                                   void* stream)
+{
+  if (!c || !d_records || !d_wrench || !d_status || B < 0) { g_err = "hmpc_solve_device: bad argument"; return HMPC_ERR_ARG; }
+  if (B == 0) return HMPC_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < c->ncls; i++) {
+    const ClassCfg& k = c->cls[i];
+    hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench, d_status);
+    ka.nb_lo = k.nb_lo;
+    ka.nb_hi = k.nb_hi;
+    ka.nb_cap = k.nb_cap;
+    ka.qmax = k.qmax;
+    const int grid = B < k.grid_cap ? B : k.grid_cap;
+    CK(launch_class(k, ka, grid, st));
+  }
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B, float* d_H, float* d_g,
+                                      float* d_Fblk, float* d_lb, float* d_ub, void* stream)
+{
+  if (!c || !d_records || !d_H || !d_g || !d_Fblk || !d_lb || !d_ub || B < 0) {
+    g_err = "hmpc_assemble_device: bad argument";
+    return HMPC_ERR_ARG;
+  }
+  if (B == 0) return HMPC_OK;
+  CK(cudaSetDevice(c->device));
+  const ClassCfg& k = c->cls[c->ncls - 1];
+  hmpc::KernelArgs ka = base_args(c, d_records, B, c->d_wrench, c->d_status);
+  ka.nb_lo = -1;
+  ka.nb_hi = 1 << 20;
+  ka.nb_cap = k.nb_cap;
+  ka.qmax = k.qmax;
+  ka.dbg_H = d_H;
+  ka.dbg_g = d_g;
+  ka.dbg_F = d_Fblk;
+  ka.dbg_lb = d_lb;
+  ka.dbg_ub = d_ub;
+  const int grid = B < k.grid_cap ? B : k.grid_cap;
+  CK(launch_class(k, ka, grid, static_cast<cudaStream_t>(stream)));
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, int* status)
+{
+  if (!c || !in || !wrench_out || B < 0 || B > c->max_batch) {
+    g_err = "hmpc_solve_batch: bad argument (null pointer or batch > capacity)";
+    return HMPC_ERR_ARG;
+  }
+  if (B == 0) return HMPC_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t nw = (size_t)12 * c->horizon;
+  int rc = hmpc_pack_records(in, B, c->horizon, c->h_rec);
+  if (rc != HMPC_OK) return rc;
+  CK(cudaMemcpyAsync(c->d_rec, c->h_rec, (size_t)B * c->rec_stride, cudaMemcpyHostToDevice, c->stream));
+  rc = hmpc_solve_device(c, c->d_rec, B, c->d_wrench, c->d_status, c->stream);
+  if (rc != HMPC_OK) return rc;
+  CK(cudaMemcpyAsync(c->h_wrench, c->d_wrench, (size_t)B * nw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_status, c->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  bool all_ok = true;
+  for (size_t i = 0; i < (size_t)B * nw; i++) wrench_out[i] = (double)c->h_wrench[i];
+  for (int i = 0; i < B; i++) {
+    if (status) status[i] = c->h_status[i];
+    if (HMPC_STATUS_CODE(c->h_status[i]) != 0) all_ok = false;
+  }
+  if (!all_ok) { g_err = "hmpc_solve_batch: at least one instance did not reach a KKT point (see status[])"; return HMPC_ERR_NOT_CONVERGED; }
+  return HMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Part 1: the reference's boundary on a one-robot context (process-global, single caller thread —
+// the same contract as the reference's globals, convexMPC_interface.cpp:13-20)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+hmpc_ctx* g_ctx = nullptr;
+update_data_t g_update;  // zero-initialised static storage, like the reference's `update`
+double* g_soln = nullptr;
+int g_soln_len = 0;
+int g_has_solved = 0;
+int g_last_status = 0;
+
+[[noreturn]] void die(const char* where)
+{
+  fprintf(stderr, "[hector_mpc_b200] %s: %s\n", where, hmpc_last_error());
+  abort();
+}
+}  // namespace
+
+HMPC_EXTERNC void setup_problem(double dt, int horizon, double mu, double f_max)
+{
+  if (horizon > 19) {  // SolverMPC.cpp:140-143 throws here; a C boundary must not leak exceptions
+    g_err = "horizon is too long!";
+    die("setup_problem");
+  }
+  if (!g_ctx || g_ctx->horizon != horizon) {
+    if (g_ctx) hmpc_destroy(g_ctx);
+    g_ctx = hmpc_create(1, horizon, 0);
+    if (!g_ctx) die("setup_problem");
+    free(g_soln);
+    g_soln = static_cast<double*>(calloc((size_t)12 * horizon, sizeof(double)));
+    g_soln_len = 12 * horizon;
+  }
+  problem_setup s;
+  s.dt = (float)dt;
+  s.mu = (float)mu;
+  s.f_max = (float)f_max;
+  s.horizon = horizon;
+  hmpc_set_problem(g_ctx, &s);
+}
+
+HMPC_EXTERNC void update_problem_data(double* p, double* v, double* q, double* w, double* r, double* joint_angles,
+                                      double yaw, double* weights, double* state_trajectory, double* Alpha_K,
+                                      int* gait)
+{
+  if (!g_ctx) { g_err = "update_problem_data called before setup_problem"; die("update_problem_data"); }
+  const int N = g_ctx->horizon;
+  // double -> float narrowing, convexMPC_interface.cpp:87-99
+  for (int i = 0; i < 3; i++) { g_update.p[i] = (float)p[i]; g_update.v[i] = (float)v[i]; g_update.w[i] = (float)w[i]; }
+  for (int i = 0; i < 4; i++) g_update.q[i] = (float)q[i];
+  for (int i = 0; i < 6; i++) g_update.r[i] = (float)r[i];
+  for (int i = 0; i < 10; i++) g_update.joint_angles[i] = (float)joint_angles[i];
+  g_update.yaw = (float)yaw;
+  for (int i = 0; i < 12; i++) { g_update.weights[i] = (float)weights[i]; g_update.Alpha_K[i] = (float)Alpha_K[i]; }
+  for (int i = 0; i < 12 * N; i++) g_update.traj[i] = (float)state_trajectory[i];
+  for (int i = 0; i < 2 * N; i++) g_update.gait[i] = (unsigned char)gait[i];
+  int rc = hmpc_solve_batch(g_ctx, &g_update, 1, g_soln, &g_last_status);
+  if (rc == HMPC_ERR_NOT_CONVERGED) printf("failed to solve!\n");  // SolverMPC.cpp:714-715 (status word kept in g_last_status)
+  else if (rc != HMPC_OK) die("update_problem_data");
+  g_has_solved = 1;
+}
+
+HMPC_EXTERNC double get_solution(int index)
+{
+  if (!g_has_solved) return 0.f;  // convexMPC_interface.cpp:107
+  if (index < 0 || index >= g_soln_len) return 0.0;
+  return g_soln[index];
+}
+
+HMPC_EXTERNC void update_solver_settings(int max_iter, double rho, double sigma, double solver_alpha, double terminate,
+                                         double use_jcqp)
+{
+  (void)use_jcqp;  // convexMPC_interface.cpp:112-118: stored, not used by the solve
+  g_update.max_iterations = max_iter;
+  g_update.rho = rho;
+  g_update.sigma = sigma;
+  g_update.solver_alpha = solver_alpha;
+  g_update.terminate = terminate;
+}
+
+// status word of the last update_problem_data (additive; not part of the reference boundary)
+HMPC_EXTERNC int hmpc_reference_last_status(void) { return g_last_status; }

@@ -1,0 +1,213 @@
+"""Python face of libhector_mpc_b200.so (ctypes over the C-ABI in include/hector_mpc_b200.h).
+
+Mirrors the reference's boundary, hector_control/ConvexMPC/convexMPC_interface.h:39-43 — same names,
+argument order and semantics — and adds the batched calls.  All numerical work happens in the CUDA
+library; this module only marshals pointers.  There is no CPU fallback: if the shared library or a
+B200 is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .scenarios import UPDATE_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhector_mpc_b200.so")
+
+HMPC_OK, HMPC_ERR_ARG, HMPC_ERR_CUDA, HMPC_ERR_NOT_CONVERGED = 0, 1, 2, 3
+ST_OK, ST_ITER_CAP, ST_WS_CAP, ST_INFEASIBLE, ST_NOT_SPD = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "setup_problem", "get_solution", "update_solver_settings", "update_problem_data",
+    "hmpc_record_bytes", "hmpc_pack_records", "hmpc_create", "hmpc_destroy", "hmpc_last_error",
+    "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
+    "hmpc_assemble_device",
+]
+
+SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
+
+_lib = None
+
+
+class HmpcError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HmpcError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = ctypes.CDLL(LIB_PATH)
+        L.setup_problem.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.setup_problem.restype = None
+        L.get_solution.argtypes = [ctypes.c_int]
+        L.get_solution.restype = ctypes.c_double
+        L.update_solver_settings.argtypes = [ctypes.c_int] + [ctypes.c_double] * 5
+        L.update_solver_settings.restype = None
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.update_problem_data.argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
+        L.update_problem_data.restype = None
+        L.hmpc_record_bytes.argtypes = [ctypes.c_int]
+        L.hmpc_record_bytes.restype = ctypes.c_size_t
+        L.hmpc_pack_records.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.hmpc_pack_records.restype = ctypes.c_int
+        L.hmpc_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.hmpc_create.restype = ctypes.c_void_p
+        L.hmpc_destroy.argtypes = [ctypes.c_void_p]
+        L.hmpc_destroy.restype = None
+        L.hmpc_last_error.restype = ctypes.c_char_p
+        L.hmpc_set_problem.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_set_problem.restype = ctypes.c_int
+        L.hmpc_solve_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_solve_batch.restype = ctypes.c_int
+        L.hmpc_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_solve_device.restype = ctypes.c_int
+        L.hmpc_launches_per_solve.argtypes = [ctypes.c_void_p]
+        L.hmpc_launches_per_solve.restype = ctypes.c_int
+        L.hmpc_assemble_device.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6
+        L.hmpc_assemble_device.restype = ctypes.c_int
+        L.hmpc_reference_last_status.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().hmpc_last_error().decode()
+
+
+def _check(rc: int, allow_not_converged: bool = False) -> int:
+    if rc == HMPC_OK or (allow_not_converged and rc == HMPC_ERR_NOT_CONVERGED):
+        return rc
+    raise HmpcError(f"libhector_mpc_b200 rc={rc}: {last_error()}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Part 1: the reference's own entry points (convexMPC_interface.h:39-43)
+# ---------------------------------------------------------------------------------------------------
+def setup_problem(dt: float, horizon: int, mu: float, f_max: float) -> None:
+    lib().setup_problem(dt, horizon, mu, f_max)
+
+
+def update_problem_data(p, v, q, w, r, joint_angles, yaw, weights, state_trajectory, Alpha_K, gait) -> None:
+    """Blocks until the solve is done (convexMPC_interface.cpp:83-103)."""
+    def d(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    keep = [d(a) for a in (p, v, q, w, r, joint_angles, weights, state_trajectory, Alpha_K)]
+    g = np.ascontiguousarray(gait, dtype=np.int32)
+    ptr = [k[1] for k in keep]
+    lib().update_problem_data(ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], ptr[5], float(yaw), ptr[6], ptr[7], ptr[8],
+                              g.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+
+
+def get_solution(index: int) -> float:
+    return lib().get_solution(index)
+
+
+def update_solver_settings(max_iter, rho, sigma, solver_alpha, terminate, use_jcqp) -> None:
+    lib().update_solver_settings(max_iter, rho, sigma, solver_alpha, terminate, use_jcqp)
+
+
+def reference_last_status() -> int:
+    return lib().hmpc_reference_last_status()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Part 2: batched interface
+# ---------------------------------------------------------------------------------------------------
+def record_bytes(horizon: int) -> int:
+    return int(lib().hmpc_record_bytes(horizon))
+
+
+def pack_records(records: np.ndarray, horizon: int) -> np.ndarray:
+    """reference records -> packed device layout (uint8 [B, stride]); pure byte shuffling in C."""
+    records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+    out = np.zeros((records.shape[0], record_bytes(horizon)), dtype=np.uint8)
+    _check(lib().hmpc_pack_records(records.ctypes.data, records.shape[0], horizon, out.ctypes.data))
+    return out
+
+
+def status_code(s):
+    return np.asarray(s) & 0xFF
+
+
+def status_iters(s):
+    return (np.asarray(s) >> 8) & 0xFFF
+
+
+def status_nactive(s):
+    return (np.asarray(s) >> 20) & 0xFF
+
+
+class BatchedMPC:
+    """Context for `max_batch` robots of `horizon` steps on one GPU (hmpc_create / hmpc_destroy)."""
+
+    def __init__(self, max_batch: int, horizon: int = 10, device: int = 0, dt: float = 0.04, mu: float = 0.25,
+                 f_max: float = 500.0):
+        self._h = lib().hmpc_create(max_batch, horizon, device)
+        if not self._h:
+            raise HmpcError(f"hmpc_create failed: {last_error()}")
+        self.max_batch, self.horizon, self.device = max_batch, horizon, device
+        self.set_problem(dt, mu, f_max)
+
+    def set_problem(self, dt: float, mu: float, f_max: float) -> None:
+        s = np.zeros(1, dtype=SETUP_DTYPE)
+        s["dt"], s["mu"], s["f_max"], s["horizon"] = dt, mu, f_max, self.horizon
+        _check(lib().hmpc_set_problem(self._h, s.ctypes.data))
+
+    @property
+    def launches_per_solve(self) -> int:
+        return lib().hmpc_launches_per_solve(self._h)
+
+    def solve_batch(self, records: np.ndarray, strict: bool = True):
+        """Host-buffer path: H2D + kernels + D2H inside.  -> (wrench [B,12N] f64, status [B] i32)."""
+        records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+        B = records.shape[0]
+        wrench = np.zeros((B, 12 * self.horizon), dtype=np.float64)
+        status = np.zeros(B, dtype=np.int32)
+        _check(lib().hmpc_solve_batch(self._h, records.ctypes.data, B, wrench.ctypes.data, status.ctypes.data),
+               allow_not_converged=not strict)
+        return wrench, status
+
+    def solve_device(self, d_records, B: int, d_wrench, d_status, stream=None) -> None:
+        """Device-resident path.  Arguments are torch CUDA tensors (uint8 [B,stride], f32 [B,12N], i32 [B])."""
+        import torch
+
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _check(lib().hmpc_solve_device(self._h, d_records.data_ptr(), B, d_wrench.data_ptr(), d_status.data_ptr(),
+                                       ctypes.c_void_p(st)))
+
+    def assemble_device(self, d_records, B: int, stream=None) -> dict:
+        """Parity hook: un-reduced fp32 QP data of B packed records (torch tensors on the GPU)."""
+        import torch
+
+        N = self.horizon
+        dev = torch.device("cuda", self.device)
+        out = dict(
+            H=torch.zeros((B, 12 * N, 12 * N), dtype=torch.float32, device=dev),
+            g=torch.zeros((B, 12 * N), dtype=torch.float32, device=dev),
+            Fblk=torch.zeros((B, 16, 12), dtype=torch.float32, device=dev),
+            lb=torch.zeros((B, 16 * N), dtype=torch.float32, device=dev),
+            ub=torch.zeros((B, 16 * N), dtype=torch.float32, device=dev),
+        )
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _check(lib().hmpc_assemble_device(self._h, d_records.data_ptr(), B, out["H"].data_ptr(), out["g"].data_ptr(),
+                                          out["Fblk"].data_ptr(), out["lb"].data_ptr(), out["ub"].data_ptr(),
+                                          ctypes.c_void_p(st)))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

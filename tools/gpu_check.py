@@ -1,0 +1,86 @@
+"""Development check run on the GPU box: parity of assembly and of the solve, plus rough timings."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from hector_simulation_b200 import interface, scenarios  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+
+
+def main():
+    N = int(os.environ.get("HMPC_N", "10"))
+    B = int(os.environ.get("HMPC_B", "512"))
+    cfg = int(os.environ.get("HMPC_CFG", "3"))
+    res = {}
+    recs, _ = scenarios.make_batch(cfg, B, horizon=N)
+    setup = O.make_setup(N)
+    mpc = interface.BatchedMPC(max(B, 4096), N)
+    t = time.time()
+    ref, info = O.solve_batch(recs, setup)
+    res["oracle_ms_per_solve"] = (time.time() - t) / B * 1e3
+    # ---- assembly parity (bitwise) ----
+    packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
+    nchk = min(B, 64)
+    asm = mpc.assemble_device(packed, nchk)
+    torch.cuda.synchronize()
+    Hd = asm["H"].cpu().numpy(); gd = asm["g"].cpu().numpy(); Fd = asm["Fblk"].cpu().numpy()
+    nbad_H = nbad_g = nbad_F = 0
+    maxrel = 0.0
+    for i in range(nchk):
+        f = O.formulate_f32(recs[i], setup)
+        iu = np.triu_indices(12 * N)
+        a, b = Hd[i][iu], f["H"][iu]
+        nbad_H += int((a.view(np.uint32) != b.view(np.uint32)).sum())
+        maxrel = max(maxrel, float(np.abs(a - b).max() / np.abs(b).max()))
+        nbad_g += int((gd[i].view(np.uint32) != f["g"].view(np.uint32)).sum())
+        nbad_F += int((Fd[i].view(np.uint32) != f["Fblk"].view(np.uint32)).sum())
+        assert np.array_equal(asm["lb"][i].cpu().numpy(), f["lb"]) and np.array_equal(asm["ub"][i].cpu().numpy(), f["ub"])
+    res.update(asm_instances=nchk, H_bits_differ=nbad_H, g_bits_differ=nbad_g, F_bits_differ=nbad_F, H_maxrel=maxrel)
+    # ---- solve parity ----
+    wrench, status = mpc.solve_batch(recs, strict=False)
+    code = interface.status_code(status)
+    rel0 = np.linalg.norm(wrench[:, :12] - ref[:, :12], axis=1) / np.maximum(np.linalg.norm(ref[:, :12], axis=1), 1e-9)
+    relf = np.linalg.norm(wrench - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-9)
+    res.update(codes=np.bincount(code, minlength=5).tolist(), rel_u0_max=float(rel0.max()), rel_u0_med=float(np.median(rel0)),
+               rel_full_max=float(relf.max()), iters_max=int(interface.status_iters(status).max()),
+               iters_med=float(np.median(interface.status_iters(status))), nact_max=int(interface.status_nactive(status).max()),
+               nwsr_max=int(info[:, 1].max()), nwsr_med=float(np.median(info[:, 1])),
+               swing_zero=bool((wrench[ref == 0] == 0).all()))
+    worst = int(np.argmax(rel0))
+    res["worst"] = dict(i=worst, rel=float(rel0[worst]), iters=int(interface.status_iters(status)[worst]), nwsr=int(info[worst, 1]),
+                        nv=int(info[worst, 2]))
+    # ---- timing ----
+    d_w = torch.zeros((B, 12 * N), dtype=torch.float32, device="cuda")
+    d_s = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        mpc.solve_device(packed, B, d_w, d_s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        mpc.solve_device(packed, B, d_w, d_s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    res.update(kernel_ms=ms, qp_per_s=B / ms * 1e3)
+    t = time.time()
+    for _ in range(5):
+        mpc.solve_batch(recs, strict=False)
+    res["e2e_ms"] = (time.time() - t) / 5 * 1e3
+    res["e2e_qp_per_s"] = B / res["e2e_ms"] * 1e3
+    print(json.dumps(res, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"gpu_check_cfg{cfg}_N{N}_B{B}.json"), "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
