@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — QP solves/sec of the batched force-and-moment MPC hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path over one batch: BASELINE.json configs[1] — batch = 1024 Hector
+walking-gait states per GPU, horizon 10 — i.e. 1024 complete `solve_mpc` equivalents per step per GPU.
+
+  value : whole-job QP solves/s with the packed records already resident in HBM (device-timed with CUDA
+          events on the launch stream, max over ranks).  Every step reads a different input buffer
+          out of a ring larger than L2, so no step finds its inputs cached.
+  e2e   : the same metric through the reference-facing C-ABI call hmpc_solve_batch with HOST buffers
+          (pack + H2D + kernels + D2H inside the timed region).
+Multi-GPU: robots are independent, the batch is sharded (weak scaling: 1024 per GPU), no data-path
+collective; one all_gather of the results per step is included in the e2e leg only when N > 1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HORIZON = 10
+BATCH_PER_GPU = 1024
+METRIC = "QP solves/sec (batched MPC ticks), horizon N=10"
+UNIT = "QP/s"
+
+
+def algorithmic_bytes_per_qp(N: int) -> int:
+    return 216 + 98 * N  # inputs that change per tick + the 12N-float result
+
+
+def algorithmic_flops_per_qp(N: int, nv: float, k_iter: float) -> float:
+    """SURVEY.md §8d formulas, with nv = reduced variable count (12N double support, 6N walking)."""
+    f_asm = 2 * nv * nv * 13 * N + 2 * nv * 13 * N + 2 * 13 * 13 * N + N * (2 * 13 ** 3 + 2 * 13 * 13 * 12)
+    f_it = nv ** 3 / 3 + 2 * 16 * 12 * 12 * N * (nv / (12.0 * N)) + 4 * nv * nv + 2 * nv * nv + 4 * 16 * 12 * N * (nv / (12.0 * N))
+    return f_asm + k_iter * f_it
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+def cpu_reference_leg(records, steps: int, warmup: int, sample_per_step: int):
+    """Times the reference's CPU implementation (oracle/_ref: restated solve_mpc + the reference's qpOASES)
+    with one independent solver per host core (the reference is single-threaded and non-reentrant, so
+    cores are used as independent processes).  Returns (QP/s, cores, per-solve seconds array)."""
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    chunks = np.array_split(np.arange(sample_per_step), cores)
+    ctx = mp.get_context("fork")
+    total_solves = 0
+    lat = []
+    t_total = 0.0
+    jobs = [(records[c % len(records)],) for c in chunks if len(c)]
+    with ctx.Pool(cores) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            outs = pool.map(_cpu_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                t_total += dt
+                total_solves += sum(len(o) for o in outs)
+                lat.extend(np.concatenate(outs).tolist())
+    return total_solves / t_total, cores, np.array(lat)
+
+
+def cpu_sample_size() -> int:
+    """Solves per step for the CPU leg: 64 per core (~0.1 s of work per core per step at ~1.5 ms/solve),
+    cycling through the 1024 records of the workload."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return 64 * cores
+
+
+def _cpu_worker(args):
+    from oracle import oracle_py as O
+
+    (recs,) = args
+    setup = O.make_setup(HORIZON)
+    return O.time_solves(recs, setup, len(recs))
+
+
+def run_reference(args):
+    from hector_simulation_b200 import scenarios
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    recs, _ = scenarios.make_batch(2, BATCH_PER_GPU, horizon=HORIZON)
+    from oracle import oracle_py as O
+
+    if not O.has_qpoases():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref built without qpOASES (no /root/reference, no prebuilt .so)"}))
+        return
+    sample = cpu_sample_size()
+    qps, cores, lat = cpu_reference_leg(recs, args.steps, max(args.warmup, 1), sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sample / qps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 assembly / f64 solve",
+        "data": "synthetic", "config": {"workload": "configs[1]: batch=1024 Hector walking-gait states, horizon=10 (bounded sample per step)",
+                                       "horizon": HORIZON, "sample_per_step": sample},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{sample} solves per step (64 per core, cycling through the 1024 records), one solver process per core",
+                         "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="robots per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from hector_simulation_b200 import interface, scenarios
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, N = args.batch, HORIZON
+    K, W = args.steps, args.warmup
+
+    # synthetic walking-gait states (configs[1]); each rank gets its own shard (different seed)
+    recs, _ = scenarios.make_batch(2, B, horizon=N, seed=scenarios.config_seed(2) + 1000 * rank)
+    mpc = interface.BatchedMPC(B, N, device=local_rank)
+    stride = interface.record_bytes(N)
+    packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
+    # ring of input/output buffers larger than L2 (126 MB): no step re-reads cached inputs
+    ring = max(8, int(np.ceil(192e6 / (B * (stride + 48 * N + 4)))))
+    d_in = packed.unsqueeze(0).repeat(ring, 1, 1).contiguous()
+    d_out = torch.zeros((ring, B, 12 * N), dtype=torch.float32, device="cuda")
+    d_st = torch.zeros((ring, B), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg ----------------
+    for i in range(W):
+        mpc.solve_device(d_in[i % ring], B, d_out[i % ring], d_st[i % ring])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_all0.record(stream)
+    for i in range(K):
+        j = (W + i) % ring
+        ev[i][0].record(stream)
+        mpc.solve_device(d_in[j], B, d_out[j], d_st[j])
+        ev[i][1].record(stream)
+    e_all1.record(stream)
+    barrier()
+    total_ms = e_all0.elapsed_time(e_all1)
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    # ---------------- end-to-end leg (host buffers through the C-ABI) ----------------
+    for _ in range(W):
+        mpc.solve_batch(recs)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_lat = []
+    for _ in range(K):
+        t1 = time.perf_counter()
+        wrench, status = mpc.solve_batch(recs)
+        if world > 1:  # results of all shards on every rank: the path's only exchange
+            g = [torch.empty((B, 12 * N), dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(wrench).cuda())
+            torch.cuda.synchronize()
+        e2e_lat.append(time.perf_counter() - t1)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, float(np.percentile(step_ms, 99))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, p99_step_ms = (float(x) for x in t.cpu())
+    st = d_st[(W + K - 1) % ring].cpu().numpy()
+    assert (interface.status_code(st) == 0).all(), "non-converged instances in the timed region"
+    iters = interface.status_iters(st)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    qps = world * B * K / (total_ms * 1e-3)
+    e2e_qps = world * B * K / (e2e_ms * 1e-3)
+    peaks = measured_peaks()
+    k_mean = float(iters.mean())
+    nv = 6.0 * N  # walking gait: one stance leg per step
+    flops = algorithmic_flops_per_qp(N, nv, k_mean) * B
+    byts = algorithmic_bytes_per_qp(N) * B
+    kern_ms = float(np.mean(step_ms))  # both launches of one step (the empty-class launch is ~2 us)
+    ach_tf = flops / (kern_ms * 1e-3) / 1e12
+    ach_gbs = byts / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 assembly (bit-exact to reference arithmetic) / f64 solve", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch=1024 Hector walking-gait states per GPU, horizon=10, cold start every tick",
+                   "horizon": N, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}",
+                   "l2": f"ring of {ring} input/output buffers ({ring * B * (stride + 48 * N + 4) / 1e6:.0f} MB > L2)"},
+        "latency_ms": {"batch_p50": float(np.percentile(step_ms, 50)), "batch_p99": p99_step_ms,
+                       "note": "device time for the whole 1024-robot batch; every robot's result is ready within it"},
+        "solver": {"mean_working_set_changes": k_mean, "max": int(iters.max())},
+        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int(B * (48 * N + 4)),
+                "ms_per_step": e2e_ms / K, "latency_ms_p99": float(np.percentile(e2e_lat, 99) * 1e3)},
+        "gpu_launches": int(K * mpc.launches_per_solve),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["bf16_tflops"],
+                     "traffic": None, "peak_source": peaks["_source"],
+                     "note": "algorithmic flops (SURVEY.md §8d: F_asm + k*F_it, nv=6N) / mean kernel time; the kernel's math is fp32 FMUL/FADD + fp64 DFMA on CUDA cores, see DESIGN.md §6",
+                     "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
+                             "bytes_per_qp": algorithmic_bytes_per_qp(N)}},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            from oracle import oracle_py as O
+
+            if O.has_qpoases():
+                sample = cpu_sample_size()
+                cq, cores, lat = cpu_reference_leg(recs, 3, 1, sample)
+                line["cpu_baseline"] = {"value": cq, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"3 steps of {sample} solves (64 per core, cycling through the {B} records), one solver process per core (restated solve_mpc + the reference's qpOASES 3.2)",
+                                        "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"unavailable": str(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

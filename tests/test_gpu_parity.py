@@ -1,0 +1,236 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C-ABI, with the oracle.
+
+Bars:  formulation stage (H, g, constraint rows, bounds) — BIT-EXACT against the oracle's fp32 restatement;
+       optimal wrenches — within 1e-4 relative of the reference's qpOASES output (BASELINE.json north_star),
+       asserted at 5e-5 to keep a margin; eliminated (swing) entries exactly 0.
+Nothing here reads /root/reference: the oracle is the prebuilt oracle/_ref/*.so or the committed fixtures.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+from hector_simulation_b200 import interface, scenarios
+
+pytestmark = pytest.mark.gpu
+
+TOL = 5e-5  # asserted; the contract is 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch
+
+
+def _solve(records, N, strict=True):
+    mpc = interface.BatchedMPC(max(len(records), 1), N)
+    try:
+        return mpc.solve_batch(records, strict=strict)
+    finally:
+        mpc.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1_h10", "cfg2_h10", "cfg3_h10", "cfg4_h5", "cfg4_h16"])
+def test_wrench_matches_golden_qpoases(torch_cuda, name):
+    g = load_golden(name)
+    N = g["horizon"]
+    w, st = _solve(g["records"], N)
+    assert (interface.status_code(st) == 0).all()
+    assert rel_err(w, g["q_soln"], 12).max() < TOL          # first-step wrench: what the caller uses
+    # whole horizon; the N=16 extension config (cond(H) ~ 1.5e7, outside the reference's N=10 regime) is
+    # held to the 1e-4 contract itself rather than to the tighter internal margin
+    assert rel_err(w, g["q_soln"]).max() < (TOL if N <= 10 else 1e-4)
+    assert (w[g["q_soln"] == 0.0] == 0.0).all()             # eliminated variables are exactly 0
+    # both solvers start from an empty working set and add one row per change: on non-degenerate
+    # problems the counts coincide (the symmetric stand sits exactly on the Mx >= 0 rows, where the
+    # two feasibility tolerances differ, so it is excluded)
+    if len(st) > 1:
+        assert np.median(np.abs(interface.status_iters(st).astype(int) - g["info"][:, 1])) == 0
+
+
+@pytest.mark.parametrize("name", ["cfg2_h10", "cfg3_h10", "cfg4_h5", "cfg4_h16"])
+def test_formulation_is_bit_exact(torch_cuda, name):
+    torch = torch_cuda
+    g = load_golden(name)
+    N = g["horizon"]
+    nf = g["H"].shape[0]
+    mpc = interface.BatchedMPC(nf, N)
+    packed = torch.from_numpy(interface.pack_records(g["records"][:nf], N)).cuda()
+    out = mpc.assemble_device(packed, nf)
+    torch.cuda.synchronize()
+    iu = np.triu_indices(12 * N)
+    for i in range(nf):
+        H = out["H"][i].cpu().numpy()
+        assert np.array_equal(H[iu].view(np.uint32), g["H"][i][iu].view(np.uint32))  # the triangle the solver uses
+        assert np.array_equal(H, H.T)
+        for k in ("g", "lb", "ub"):
+            assert np.array_equal(out[k][i].cpu().numpy().view(np.uint32), g[k][i].view(np.uint32)), k
+        assert np.array_equal(out["Fblk"][i].cpu().numpy().view(np.uint32), g["Fblk"][i].view(np.uint32))
+    mpc.close()
+
+
+def test_formulation_bit_exact_vs_live_oracle_many(torch_cuda, oracle):
+    """256 fresh random states (not in the fixtures): H upper triangle, g, rows all bit-identical."""
+    torch = torch_cuda
+    N = 10
+    recs, _ = scenarios.make_batch(3, 256, horizon=N, seed=777)
+    mpc = interface.BatchedMPC(256, N)
+    packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
+    out = mpc.assemble_device(packed, 256)
+    H, gg, F = out["H"].cpu().numpy(), out["g"].cpu().numpy(), out["Fblk"].cpu().numpy()
+    setup = oracle.make_setup(N)
+    iu = np.triu_indices(12 * N)
+    ndiff = 0
+    for i in range(256):
+        f = oracle.formulate_f32(recs[i], setup)
+        ndiff += int((H[i][iu].view(np.uint32) != f["H"][iu].view(np.uint32)).sum())
+        ndiff += int((gg[i].view(np.uint32) != f["g"].view(np.uint32)).sum())
+        ndiff += int((F[i].view(np.uint32) != f["Fblk"].view(np.uint32)).sum())
+    assert ndiff == 0
+    mpc.close()
+
+
+def test_reference_boundary_single_robot(torch_cuda):
+    """setup_problem / update_problem_data / get_solution exactly as ConvexMPCLocomotion.cpp:410-430 calls them."""
+    g = load_golden("cfg1_h10")
+    b = scenarios.stand_inputs(10)
+    interface.setup_problem(scenarios.DT_MPC, 10, scenarios.MU_PASSED, scenarios.F_MAX)
+    interface.update_solver_settings(500, 1e-7, 1e-8, 1.5, 1e-7, 0.0)
+    interface.update_problem_data(b["p"], b["v"], b["q"], b["w"], b["r"], b["joint_angles"], b["yaw"], b["weights"],
+                                  b["state_trajectory"], b["Alpha_K"], b["gait"])
+    sol = np.array([interface.get_solution(i) for i in range(120)])
+    assert rel_err(sol[None], g["q_soln"][:1], 12)[0] < TOL
+    assert interface.status_code(interface.reference_last_status()) == 0
+    # a second tick with a walking table re-solves in place (setup_problem is called every tick, :410)
+    g2 = load_golden("cfg2_h10")
+    recs2, inputs2 = scenarios.make_batch(2, 3, horizon=10)
+    b2 = inputs2[2]
+    interface.setup_problem(scenarios.DT_MPC, 10, scenarios.MU_PASSED, scenarios.F_MAX)
+    interface.update_problem_data(b2["p"], b2["v"], b2["q"], b2["w"], b2["r"], b2["joint_angles"], b2["yaw"], b2["weights"],
+                                  b2["state_trajectory"], b2["Alpha_K"], b2["gait"])
+    sol2 = np.array([interface.get_solution(i) for i in range(120)])
+    assert rel_err(sol2[None], g2["q_soln"][2:3])[0] < TOL
+    leg_swing = 1 if b2["gait"][0] == 1 else 0
+    assert all(sol2[3 * leg_swing + c] == 0.0 and sol2[6 + 3 * leg_swing + c] == 0.0 for c in range(3))
+
+
+def test_full_size_configs_vs_live_oracle(torch_cuda, oracle):
+    """BASELINE configs[1] (B=1024 walking) in full; configs[2] (B=8192 mixed) on a strided sample of the oracle."""
+    if not oracle.has_qpoases():
+        pytest.skip("oracle/_ref without qpOASES")
+    setup = oracle.make_setup(10)
+    recs, _ = scenarios.make_batch(2, 1024, horizon=10)
+    w, st = _solve(recs, 10)
+    ref, info = oracle.solve_batch(recs, setup)
+    assert (interface.status_code(st) == 0).all()
+    e = rel_err(w, ref, 12)
+    assert e.max() < TOL and np.median(e) < 1e-6
+    recs3, _ = scenarios.make_batch(3, 8192, horizon=10)
+    w3, st3 = _solve(recs3, 10)
+    assert (interface.status_code(st3) == 0).all()
+    idx = np.arange(0, 8192, 16)
+    ref3, _ = oracle.solve_batch(recs3[idx], setup)
+    assert rel_err(w3[idx], ref3, 12).max() < TOL
+    assert rel_err(w3[idx], ref3).max() < TOL
+
+
+def test_kkt_residuals_at_full_size(torch_cuda, oracle):
+    """Size-independent property: every returned point is a KKT point of its own QP (fp64 check on the
+    oracle's restated QP data): primal feasible, and the gradient lies in the cone of active rows."""
+    recs, _ = scenarios.make_batch(3, 2048, horizon=10, seed=4242)
+    w, st = _solve(recs, 10)
+    assert (interface.status_code(st) == 0).all()
+    setup = oracle.make_setup(10)
+    for i in range(0, 2048, 64):
+        Q = oracle.reduced_qp(recs[i], setup)
+        x = w[i][Q["var_ind"]]
+        Ax = Q["A"] @ x
+        scale = max(1.0, np.abs(x).max())
+        tol = 2e-5 * scale  # fp32 output rounding of ~100 N forces
+        assert (Ax >= Q["lb"] - tol).all() and (Ax <= Q["ub"] + tol).all()
+        Hs = np.triu(Q["H"]) + np.triu(Q["H"], 1).T
+        grad = Hs @ x + Q["g"]
+        lo = np.abs(Ax - Q["lb"]) < tol
+        hi = np.abs(Ax - Q["ub"]) < tol
+        rows = np.concatenate([Q["A"][lo], -Q["A"][hi]])
+        if len(rows):
+            from scipy.optimize import nnls
+
+            lam, rn = nnls(rows.T, grad)
+        else:
+            rn = np.linalg.norm(grad)
+        assert rn <= 2e-3 * max(1.0, np.linalg.norm(Q["g"]))
+
+
+def test_determinism_and_batch_permutation(torch_cuda):
+    recs, _ = scenarios.make_batch(3, 300, horizon=10, seed=99)
+    w1, s1 = _solve(recs, 10)
+    w2, s2 = _solve(recs, 10)
+    assert np.array_equal(w1, w2) and np.array_equal(s1, s2)
+    perm = np.random.default_rng(0).permutation(300)
+    w3, s3 = _solve(recs[perm], 10)
+    assert np.array_equal(w3, w1[perm]) and np.array_equal(s3, s1[perm])
+
+
+def test_edge_cases(torch_cuda):
+    N = 10
+    mpc = interface.BatchedMPC(64, N)
+    # empty batch
+    w, s = mpc.solve_batch(np.zeros(0, dtype=scenarios.UPDATE_DTYPE))
+    assert w.shape == (0, 120)
+    # a robot with no foot in contact over the whole horizon: everything eliminated -> all zeros
+    b = scenarios.stand_inputs(N)
+    b["gait"][:] = 0
+    rec = scenarios.to_record(b, N)
+    w, s = mpc.solve_batch(np.array([rec]))
+    assert (w == 0).all() and interface.status_code(s)[0] == 0
+    # flight for the first steps, then double support (ragged contact schedule)
+    b = scenarios.stand_inputs(N)
+    b["gait"][:8] = 0
+    rec = scenarios.to_record(b, N)
+    w, s = mpc.solve_batch(np.array([rec]))
+    assert interface.status_code(s)[0] == 0 and (w[0, :48] == 0).all() and np.abs(w[0, 48:]).max() > 1
+    # batch larger than the context's capacity is refused, not truncated
+    recs, _ = scenarios.make_batch(2, 65, horizon=N)
+    with pytest.raises(interface.HmpcError):
+        mpc.solve_batch(recs)
+    mpc.close()
+
+
+def test_edge_cases_vs_oracle(torch_cuda, oracle):
+    if not oracle.has_qpoases():
+        pytest.skip("oracle/_ref without qpOASES")
+    N = 10
+    rng = np.random.default_rng(5)
+    recs = []
+    for k in range(48):
+        table = (rng.random(2 * N) < 0.6).astype(np.int32)  # arbitrary ragged contact schedules
+        b = scenarios._random_state(rng, N, table, moving=True)
+        recs.append(scenarios.to_record(b, N))
+    recs = np.array(recs)
+    w, s = _solve(recs, N)
+    ref, info = oracle.solve_batch(recs, oracle.make_setup(N))
+    assert (interface.status_code(s) == 0).all() and (info[:, 0] == 0).all()
+    assert rel_err(w, ref).max() < TOL
+    assert (w[ref == 0.0] == 0.0).all()
+
+
+def test_device_resident_path_and_status_words(torch_cuda):
+    torch = torch_cuda
+    g = load_golden("cfg3_h10")
+    N = 10
+    B = len(g["records"])
+    mpc = interface.BatchedMPC(B, N)
+    assert mpc.launches_per_solve >= 1
+    packed = torch.from_numpy(interface.pack_records(g["records"], N)).cuda()
+    d_w = torch.full((B, 12 * N), float("nan"), dtype=torch.float32, device="cuda")
+    d_s = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    mpc.solve_device(packed, B, d_w, d_s)
+    torch.cuda.synchronize()
+    w, s = d_w.cpu().numpy().astype(np.float64), d_s.cpu().numpy()
+    assert np.isfinite(w).all() and (s >= 0).all()      # every slot written: never silently stale
+    assert rel_err(w, g["q_soln"]).max() < TOL
+    assert (interface.status_nactive(s) <= interface.status_iters(s)).all()
+    mpc.close()
