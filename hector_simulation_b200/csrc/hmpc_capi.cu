@@ -31,10 +31,9 @@ bool cuda_fail(cudaError_t e, const char* what)
   } while (0)
 
 struct ClassCfg {
-  int nb_lo, nb_hi, nb_cap, qmax, threads, smem, grid_cap, maxt;
+  int nb_hi, nb_cap, qmax, threads, smem, grid_cap, variant;
+  hmpc::Layout L;
 };
-
-int round32(int x) { return (x + 31) / 32 * 32; }
 
 }  // namespace
 
@@ -44,10 +43,12 @@ struct hmpc_ctx {
   ClassCfg cls[2];
   int ncls = 0;
   unsigned char* d_rec = nullptr;
-  float* d_wrench = nullptr;
+  double* d_wrench = nullptr;      // fp64 results of the host-buffer path
   int* d_status = nullptr;
+  int* d_counts = nullptr;         // [2] class list lengths
+  int* d_lists = nullptr;          // [2][max_batch] class lists
   unsigned char* h_rec = nullptr;  // pinned
-  float* h_wrench = nullptr;       // pinned
+  double* h_wrench = nullptr;      // pinned
   int* h_status = nullptr;         // pinned
   cudaStream_t stream = nullptr;
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
@@ -55,28 +56,39 @@ struct hmpc_ctx {
 
 namespace {
 
-template <int MAXT, int MINB>
-cudaError_t prep_kernel(int smem, int threads, int* occ)
+// kernel variants: <threads, min CTAs/SM, sweep strip width>
+//   0: <64,8,3>   1: <128,7,3>   2: <288,2,3>   3: <64,8,6>   4: <224,2,6>   5: <544,1,6>
+template <int NT, int MINB, int BW>
+cudaError_t prep_kernel(int smem, int* occ)
 {
-  auto k = hmpc::hmpc_solve_kernel<MAXT, MINB>;
+  auto k = hmpc::hmpc_solve_kernel<NT, MINB, BW>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, threads, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, NT, smem);
 }
 
 cudaError_t prep_class(ClassCfg& c, int* occ)
 {
-  if (c.threads <= 64) { c.maxt = 64; return prep_kernel<64, 8>(c.smem, c.threads, occ); }
-  if (c.threads <= 224) { c.maxt = 224; return prep_kernel<224, 2>(c.smem, c.threads, occ); }
-  c.maxt = 544;
-  return prep_kernel<544, 1>(c.smem, c.threads, occ);
+  switch (c.variant) {
+    case 0: return prep_kernel<64, 8, 3>(c.smem, occ);
+    case 1: return prep_kernel<128, 7, 3>(c.smem, occ);
+    case 2: return prep_kernel<288, 2, 3>(c.smem, occ);
+    case 3: return prep_kernel<64, 8, 6>(c.smem, occ);
+    case 4: return prep_kernel<224, 2, 6>(c.smem, occ);
+    default: return prep_kernel<544, 1, 6>(c.smem, occ);
+  }
 }
 
 cudaError_t launch_class(const ClassCfg& c, const hmpc::KernelArgs& ka, int grid, cudaStream_t st)
 {
-  if (c.maxt == 64) hmpc::hmpc_solve_kernel<64, 8><<<grid, c.threads, c.smem, st>>>(ka);
-  else if (c.maxt == 224) hmpc::hmpc_solve_kernel<224, 2><<<grid, c.threads, c.smem, st>>>(ka);
-  else hmpc::hmpc_solve_kernel<544, 1><<<grid, c.threads, c.smem, st>>>(ka);
+  switch (c.variant) {
+    case 0: hmpc::hmpc_solve_kernel<64, 8, 3><<<grid, 64, c.smem, st>>>(ka); break;
+    case 1: hmpc::hmpc_solve_kernel<128, 7, 3><<<grid, 128, c.smem, st>>>(ka); break;
+    case 2: hmpc::hmpc_solve_kernel<288, 2, 3><<<grid, 288, c.smem, st>>>(ka); break;
+    case 3: hmpc::hmpc_solve_kernel<64, 8, 6><<<grid, 64, c.smem, st>>>(ka); break;
+    case 4: hmpc::hmpc_solve_kernel<224, 2, 6><<<grid, 224, c.smem, st>>>(ka); break;
+    default: hmpc::hmpc_solve_kernel<544, 1, 6><<<grid, 544, c.smem, st>>>(ka); break;
+  }
   return cudaGetLastError();
 }
 
@@ -85,28 +97,36 @@ int fit_qmax(int N, int nb_cap, int rec_stride, int want_min)
 {
   int q = want_min;
   const int base = hmpc::make_layout(N, nb_cap, want_min, rec_stride).total;
-  while (q < 6 * nb_cap && hmpc::make_layout(N, nb_cap, q + 1, rec_stride).total <= base) q++;
+  while (q < 6 * nb_cap && q < 250 && hmpc::make_layout(N, nb_cap, q + 1, rec_stride).total <= base) q++;
   return q;
 }
 
 int build_classes(hmpc_ctx* c)
 {
   const int N = c->horizon;
-  // class 0: at most N blocks of 6 variables (e.g. any single-support schedule); class 1: up to 2N.
+  // class 0: at most N blocks of 6 variables (e.g. any single-support schedule), 6x3 register strips;
+  // class 1: up to 2N blocks, 6x6 register blocks.  Working-set overflow in class 0 escalates to class 1.
   const int caps[2] = {N, 2 * N};
   c->ncls = 2;
-  int prev = -1;
   for (int i = 0; i < 2; i++) {
     ClassCfg& k = c->cls[i];
-    k.nb_lo = prev;
     k.nb_hi = caps[i];
     k.nb_cap = caps[i];
-    prev = caps[i];
     const int n = 6 * k.nb_cap;
-    k.qmax = fit_qmax(N, k.nb_cap, c->rec_stride, n < 64 ? n : 64);
-    k.threads = round32(k.nb_cap * (k.nb_cap + 1) / 2);
-    if (k.threads < 64) k.threads = 64;
-    k.smem = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride).total;
+    const int nbt = k.nb_cap * (k.nb_cap + 1) / 2;
+    if (i == 0) {
+      const int need = 2 * nbt > n ? 2 * nbt : n;
+      k.variant = need <= 64 ? 0 : (need <= 128 ? 1 : 2);
+      k.threads = need <= 64 ? 64 : (need <= 128 ? 128 : 288);
+    } else {
+      const int need = nbt > n ? nbt : n;
+      k.variant = need <= 64 ? 3 : (need <= 224 ? 4 : 5);
+      k.threads = need <= 64 ? 64 : (need <= 224 ? 224 : 544);
+    }
+    k.qmax = fit_qmax(N, k.nb_cap, c->rec_stride, n < 40 ? n : 40);
+    if (i == 1 && k.qmax < (n < 96 ? n : 96)) k.qmax = n < 96 ? n : 96;
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
+    k.smem = k.L.total;
     int occ = 0;
     if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (is this an sm_100a device?)")) return HMPC_ERR_CUDA;
     if (occ < 1) { g_err = "kernel does not fit on this device"; return HMPC_ERR_CUDA; }
@@ -150,14 +170,7 @@ HMPC_EXTERNC int hmpc_pack_records(const update_data_t* in, int n, int horizon, 
   for (int i = 0; i < n; i++, o += stride) {
     const update_data_t& u = in[i];
     float* f = reinterpret_cast<float*>(o);
-    memcpy(f + 0, u.p, 12);
-    memcpy(f + 3, u.v, 12);
-    memcpy(f + 6, u.q, 16);
-    memcpy(f + 10, u.w, 12);
-    memcpy(f + 13, u.r, 24);
-    memcpy(f + 19, u.joint_angles, 40);
-    f[29] = u.yaw;
-    memcpy(f + 30, u.weights, 48);
+    memcpy(f, u.p, 42 * 4);  // p v q w r joint_angles yaw weights are contiguous in update_data_t
     memcpy(f + 42, u.Alpha_K, 48);
     memcpy(f + 54, u.traj, (size_t)48 * horizon);
     unsigned char* g = o + (size_t)(54 + 12 * horizon) * 4;
@@ -179,6 +192,8 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->d_rec) cudaFree(c->d_rec);
   if (c->d_wrench) cudaFree(c->d_wrench);
   if (c->d_status) cudaFree(c->d_status);
+  if (c->d_counts) cudaFree(c->d_counts);
+  if (c->d_lists) cudaFree(c->d_lists);
   if (c->h_rec) cudaFreeHost(c->h_rec);
   if (c->h_wrench) cudaFreeHost(c->h_wrench);
   if (c->h_status) cudaFreeHost(c->h_status);
@@ -219,10 +234,12 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
     const size_t nw = (size_t)12 * horizon;
     bad = cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
-          cuda_fail(cudaMalloc(&c->d_wrench, (size_t)max_batch * nw * 4), "cudaMalloc wrench") ||
+          cuda_fail(cudaMalloc(&c->d_wrench, (size_t)max_batch * nw * 8), "cudaMalloc wrench") ||
+          cuda_fail(cudaMalloc(&c->d_counts, 2 * sizeof(int)), "cudaMalloc counts") ||
+          cuda_fail(cudaMalloc(&c->d_lists, (size_t)2 * max_batch * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
-          cuda_fail(cudaMallocHost(&c->h_wrench, (size_t)max_batch * nw * 4), "cudaMallocHost wrench") ||
+          cuda_fail(cudaMallocHost(&c->h_wrench, (size_t)max_batch * nw * 8), "cudaMallocHost wrench") ||
           cuda_fail(cudaMallocHost(&c->h_status, (size_t)max_batch * 4), "cudaMallocHost status") ||
           build_classes(c) != HMPC_OK;
   }
@@ -243,26 +260,55 @@ HMPC_EXTERNC int hmpc_set_problem(hmpc_ctx* c, const problem_setup* s)
   return HMPC_OK;
 }
 
-HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls : 0; }
+namespace {
+// classification pre-pass + one launch per class, all enqueued on `st`
+int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, double* d_wrench64, int* d_status,
+                  cudaStream_t st)
+{
+  if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->d_counts, 0, 2 * sizeof(int), st));
+  hmpc::hmpc_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride, B,
+                                                             c->horizon, c->setup.f_max, c->cls[0].nb_hi, c->d_counts,
+                                                             c->d_lists, c->max_batch);
+  CK(cudaGetLastError());
+  for (int i = 0; i < c->ncls; i++) {
+    const ClassCfg& k = c->cls[i];
+    hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
+    ka.wrench64 = d_wrench64;
+    ka.list = c->d_lists + (size_t)i * c->max_batch;
+    ka.counts = c->d_counts;
+    ka.cls = i;
+    ka.esc_list = (i + 1 < c->ncls) ? c->d_lists + (size_t)(i + 1) * c->max_batch : nullptr;
+    ka.nb_cap = k.nb_cap;
+    ka.qmax = k.qmax;
+    ka.L = k.L;
+    const int grid = B < k.grid_cap ? B : k.grid_cap;
+    CK(launch_class(k, ka, grid, st));
+  }
+  return HMPC_OK;
+}
+}  // namespace
+
+HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls + 1 : 0; }
+
+// launch configuration of class `cls`: out[0..5] = threads, dynamic smem bytes, working-set capacity,
+// resident-grid cap (CTAs), max blocks of 6 variables, sweep strip width
+HMPC_EXTERNC int hmpc_class_config(const hmpc_ctx* c, int cls, int* out)
+{
+  if (!c || !out || cls < 0 || cls >= c->ncls) return HMPC_ERR_ARG;
+  const ClassCfg& k = c->cls[cls];
+  out[0] = k.threads; out[1] = k.smem; out[2] = k.qmax; out[3] = k.grid_cap; out[4] = k.nb_cap;
+  out[5] = (k.variant < 3) ? 3 : 6;
+  return HMPC_OK;
+}
 
 HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* c, const void* d_records, int B, float* d_wrench, int* d_status,
                                    void* stream)
 {
   if (!c || !d_records || !d_wrench || !d_status || B < 0) { g_err = "hmpc_solve_device: bad argument"; return HMPC_ERR_ARG; }
   if (B == 0) return HMPC_OK;
-  CK(cudaSetDevice(c->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int i = 0; i < c->ncls; i++) {
-    const ClassCfg& k = c->cls[i];
-    hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench, d_status);
-    ka.nb_lo = k.nb_lo;
-    ka.nb_hi = k.nb_hi;
-    ka.nb_cap = k.nb_cap;
-    ka.qmax = k.qmax;
-    const int grid = B < k.grid_cap ? B : k.grid_cap;
-    CK(launch_class(k, ka, grid, st));
-  }
-  return HMPC_OK;
+  return enqueue_solve(c, d_records, B, d_wrench, nullptr, d_status, static_cast<cudaStream_t>(stream));
 }
 
 HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B, float* d_H, float* d_g,
@@ -275,11 +321,14 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
   if (B == 0) return HMPC_OK;
   CK(cudaSetDevice(c->device));
   const ClassCfg& k = c->cls[c->ncls - 1];
-  hmpc::KernelArgs ka = base_args(c, d_records, B, c->d_wrench, c->d_status);
-  ka.nb_lo = -1;
-  ka.nb_hi = 1 << 20;
+  hmpc::KernelArgs ka = base_args(c, d_records, B, nullptr, c->d_status);
+  ka.list = nullptr;  // identity
+  ka.counts = c->d_counts;
+  ka.cls = c->ncls - 1;
+  ka.esc_list = nullptr;
   ka.nb_cap = k.nb_cap;
   ka.qmax = k.qmax;
+  ka.L = k.L;
   ka.dbg_H = d_H;
   ka.dbg_g = d_g;
   ka.dbg_F = d_Fblk;
@@ -302,13 +351,14 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
   int rc = hmpc_pack_records(in, B, c->horizon, c->h_rec);
   if (rc != HMPC_OK) return rc;
   CK(cudaMemcpyAsync(c->d_rec, c->h_rec, (size_t)B * c->rec_stride, cudaMemcpyHostToDevice, c->stream));
-  rc = hmpc_solve_device(c, c->d_rec, B, c->d_wrench, c->d_status, c->stream);
+  rc = enqueue_solve(c, c->d_rec, B, nullptr, c->d_wrench, c->d_status, c->stream);
   if (rc != HMPC_OK) return rc;
-  CK(cudaMemcpyAsync(c->h_wrench, c->d_wrench, (size_t)B * nw * 4, cudaMemcpyDeviceToHost, c->stream));
+  // results land directly in the caller's buffers when they are pinned-or-pageable host memory
+  CK(cudaMemcpyAsync(c->h_wrench, c->d_wrench, (size_t)B * nw * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(c->h_status, c->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  memcpy(wrench_out, c->h_wrench, (size_t)B * nw * 8);
   bool all_ok = true;
-  for (size_t i = 0; i < (size_t)B * nw; i++) wrench_out[i] = (double)c->h_wrench[i];
   for (int i = 0; i < B; i++) {
     if (status) status[i] = c->h_status[i];
     if (HMPC_STATUS_CODE(c->h_status[i]) != 0) all_ok = false;

@@ -5,7 +5,7 @@
 //   stage 1  SRBD linearisation + foot rotations + constraint rows      (SolverMPC.cpp:374-433, 463-548)
 //   stage 2  forward-Euler discretisation, powers, Toeplitz blocks       (SolverMPC.cpp:133-193)
 //   stage 3  Hessian / gradient of the condensed QP, swing-leg removal   (SolverMPC.cpp:450-461, 557-570, 589-697)
-//   stage 4  in-register symmetric sweep inversion of H (fp64, 6x6 block per thread)
+//   stage 4  in-register symmetric sweep inversion of H (fp64, one 6xBW block per thread)
 //   stage 5  dual active-set iterations on the explicit inverse           (replaces qpOASES, SolverMPC.cpp:702-712)
 //   stage 6  scatter of the optimal wrenches, eliminated entries = 0     (SolverMPC.cpp:720-732)
 //
@@ -30,42 +30,21 @@ namespace hmpc {
 // termination codes (low byte of the status word, include/hector_mpc_b200.h)
 enum : int { ST_OK = 0, ST_ITER_CAP = 1, ST_WS_CAP = 2, ST_INFEASIBLE = 3, ST_NOT_SPD = 4 };
 
-struct KernelArgs {
-  const unsigned char* records;  // packed device records
-  int rec_stride;                // bytes, multiple of 16
-  int batch;
-  int horizon;                   // N
-  float dt;
-  float f_max;
-  int nb_lo, nb_hi;              // this launch handles instances with nb_lo < NB <= nb_hi
-  int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
-  int qmax;                      // working-set capacity
-  int max_iter;
-  float* wrench;                 // [batch][12N]
-  int* status;                   // [batch]
-  // assembly dump (parity hook); all null in production launches
-  float* dbg_H;                  // [batch][12N*12N]
-  float* dbg_g;                  // [batch][12N]
-  float* dbg_F;                  // [batch][192]
-  float* dbg_lb;                 // [batch][16N]
-  float* dbg_ub;                 // [batch][16N]
-};
-
 // ------------------------------------------------------------------------------------------------
-// shared-memory carve-up (byte offsets), identical on host and device
+// shared-memory carve-up (byte offsets), computed once on the host and passed by value
 // ------------------------------------------------------------------------------------------------
 struct Layout {
-  int H, gq, x0, x, w, HA, nrm, rhs, blk, misc, uni;
+  int H, gq, x0, x, HA, nrm, rhs, blk, misc, uni;
   // solver view of the union
   int Li, lam, dv, yv, rv, Wc, act;
   // assembly view of the union
-  int rec, x0f, Acd, Bcd, P, M, T, dd, fbl, wts;
+  int rec, x0f, Acd, Bcd, P, M, dd, fbl;
   int total;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline Layout make_layout(int N, int nb_cap, int qmax, int rec_stride)
+inline Layout make_layout(int N, int nb_cap, int qmax, int rec_stride)
 {
   Layout L;
   const int nbt = nb_cap * (nb_cap + 1) / 2;
@@ -75,15 +54,13 @@ __host__ __device__ inline Layout make_layout(int N, int nb_cap, int qmax, int r
   L.gq = o;   o += n * 8;
   L.x0 = o;   o += n * 8;
   L.x = o;    o += n * 8;   // doubles as sweep pivot-column buffer 0
-  L.w = o;    o += n * 8;   // doubles as sweep pivot-column buffer 1
-  L.HA = o;   o += n * 8;
+  L.HA = o;   o += n * 8;   // doubles as sweep pivot-column buffer 1
   L.nrm = o;  o += 2 * 10 * 6 * 8;
   L.rhs = o;  o += m * 8;
-  L.blk = o;  o += align16(nb_cap * 4 + 2 * N * 4 * 2);  // block -> (step,leg) and (step,leg) -> block
+  L.blk = o;  o += align16((nb_cap + 2 * N) * 4);  // block -> (step,leg) and (step,leg) -> block
   L.misc = o; o += 512;
   L.uni = o;
-  // solver view
-  int s = L.uni;
+  int s = L.uni;  // solver view
   L.Li = s;   s += (qmax + 1) * (qmax + 2) / 2 * 8;
   L.lam = s;  s += (qmax + 2) * 8;
   L.dv = s;   s += (qmax + 2) * 8;
@@ -91,21 +68,44 @@ __host__ __device__ inline Layout make_layout(int N, int nb_cap, int qmax, int r
   L.rv = s;   s += (qmax + 2) * 8;
   L.Wc = s;   s += align16((qmax + 2) * 4);
   L.act = s;  s += align16(m);
-  // assembly view
-  int a = L.uni;
+  int a = L.uni;  // assembly view
   L.rec = a;  a += align16(rec_stride);
   L.x0f = a;  a += 16 * 4;
   L.Acd = a;  a += align16(169 * 4);
   L.Bcd = a;  a += align16(156 * 4);
-  L.P = a;    a += align16((N + 1) * 169 * 4);
-  L.M = a;    a += align16(N * 156 * 4);
-  L.T = a;    a += align16(N * 144 * 4);
-  L.dd = a;   a += align16(13 * N * 4);
+  L.P = a;    a += 2 * align16(169 * 4);
+  L.M = a;    a += align16(N * 144 * 4);
+  L.dd = a;   a += align16(12 * N * 4);
   L.fbl = a;  a += 192 * 4;
-  L.wts = a;  a += 16 * 4;
   L.total = align16(s > a ? s : a);
   return L;
 }
+
+struct KernelArgs {
+  const unsigned char* records;  // packed device records
+  int rec_stride;                // bytes, multiple of 16
+  int batch;
+  int horizon;                   // N
+  float dt;
+  float f_max;
+  const int* list;               // instances of this launch's class (nullptr: identity over [0,batch))
+  int* counts;                   // [ncls] list lengths (device); counts[cls] is this launch's
+  int cls;                       // class index of this launch
+  int* esc_list;                 // next class's list (working-set overflow escalation) or nullptr
+  int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
+  int qmax;                      // working-set capacity
+  int max_iter;
+  float* wrench;                 // [batch][12N] float results, or nullptr
+  double* wrench64;              // [batch][12N] double results, or nullptr
+  int* status;                   // [batch]
+  // assembly dump (parity hook); all null in production launches
+  float* dbg_H;                  // [batch][12N*12N]
+  float* dbg_g;                  // [batch][12N]
+  float* dbg_F;                  // [batch][192]
+  float* dbg_lb;                 // [batch][16N]
+  float* dbg_ub;                 // [batch][16N]
+  Layout L;
+};
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -143,11 +143,29 @@ __device__ __forceinline__ int leg_of(int c12) { return (c12 / 3) & 1; }        
 __device__ __forceinline__ int loc_of(int c12) { return (c12 % 3) + (c12 >= 6 ? 3 : 0); }  // -> slot in [F(3) M(3)]
 __device__ __forceinline__ int col12_of(int leg, int loc) { return (loc < 3) ? 3 * leg + loc : 6 + 3 * leg + (loc - 3); }
 
-// element (i,j) of the symmetric matrix stored as lower 6x6 blocks; i = 6*ib+r, j = 6*jb+c
+// symmetric matrix stored as lower 6x6 blocks: block (ib,jb), jb <= ib, at (ib(ib+1)/2+jb)*36, row-major inside
 __device__ __forceinline__ int blk_off(int ib, int jb) { return (ib * (ib + 1) / 2 + jb) * 36; }
-__device__ __forceinline__ double hsym(const double* H, int ib, int r, int jb, int c)
+
+// dot of row (6*ib + r) of the symmetric matrix, restricted to block column kb, with a 6-vector
+__device__ __forceinline__ double hrow6(const double* H, int ib, int r, int kb, const double* v)
 {
-  return (ib >= jb) ? H[blk_off(ib, jb) + r * 6 + c] : H[blk_off(jb, ib) + c * 6 + r];
+  double acc;
+  if (ib >= kb) {
+    const double2* p = reinterpret_cast<const double2*>(H + blk_off(ib, kb) + r * 6);
+    const double2 a = p[0], b = p[1], c = p[2];
+    acc = a.x * v[0];
+    acc = fma(a.y, v[1], acc);
+    acc = fma(b.x, v[2], acc);
+    acc = fma(b.y, v[3], acc);
+    acc = fma(c.x, v[4], acc);
+    acc = fma(c.y, v[5], acc);
+  } else {
+    const double* p = H + blk_off(kb, ib) + r;
+    acc = p[0] * v[0];
+#pragma unroll
+    for (int c = 1; c < 6; c++) acc = fma(p[6 * c], v[c], acc);
+  }
+  return acc;
 }
 
 // Eigen 3x3 inverse restated (oracle: inverse3)
@@ -182,6 +200,24 @@ __device__ inline void mul3(const float* A, const float* B, float* C)
       C[i * 3 + j] = acc;
     }
 }
+// RobotState::set — Quaternionf::toRotationMatrix (RobotState.cpp:17-30)
+__device__ inline void quat_to_R(const float* qq, float* R)
+{
+  float w = qq[0], x = qq[1], y = qq[2], z = qq[3];
+  float tx = FM(2.f, x), ty = FM(2.f, y), tz = FM(2.f, z);
+  float twx = FM(tx, w), twy = FM(ty, w), twz = FM(tz, w);
+  float txx = FM(tx, x), txy = FM(ty, x), txz = FM(tz, x);
+  float tyy = FM(ty, y), tyz = FM(tz, y), tzz = FM(tz, z);
+  R[0] = FS(1.f, FA(tyy, tzz));
+  R[1] = FS(txy, twz);
+  R[2] = FA(txz, twy);
+  R[3] = FA(txy, twz);
+  R[4] = FS(1.f, FA(txx, tzz));
+  R[5] = FS(tyz, twx);
+  R[6] = FS(txz, twy);
+  R[7] = FA(tyz, twx);
+  R[8] = FS(1.f, FA(txx, tyy));
+}
 
 // foot rotation from five offset-corrected joint angles (SolverMPC.cpp:428-433; oracle: foot_rotation)
 __device__ inline void foot_rotation(const float* q, float* Rf)
@@ -215,44 +251,48 @@ __device__ inline void foot_rotation(const float* q, float* Rf)
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 1: scalar prologue (one thread): fills x0f, Acd, Bcd, Fblk rows
+// stage 1, split into three independent roles that run on different warps (each recomputes the cheap R)
 // record floats: p[0..2] v[3..5] q[6..9] w[10..12] r[13..18] joint[19..28] yaw[29] weights[30..41]
-//                alpha[42..53] traj[54..54+12N)  then gait bytes
+//                alpha[42..53] traj[54..54+12N)  then gait bytes.   Acd/Bcd/Fblk are pre-zeroed.
 // ------------------------------------------------------------------------------------------------
-__device__ inline void prologue(const float* rf, float dt, float* x0f, float* Acd, float* Bcd, float* Fblk)
+// role "leg": joint offsets + fmod (SolverMPC.cpp:374-393), foot rotation, the leg's 8 constraint rows (:488-548)
+__device__ inline void role_leg(const float* rf, int leg, float* Fblk)
 {
-  // joint angles: SolverMPC.cpp:374-393
   const double PI = 3.14159265359;
-  float q[10];
-  for (int i = 0; i < 10; i++) q[i] = rf[19 + i];
+  float q[5];
+  for (int i = 0; i < 5; i++) q[i] = rf[19 + 5 * leg + i];
   q[2] = (float)DA((double)q[2], DM(0.3, PI));
   q[3] = (float)DS((double)q[3], DM(0.6, PI));
   q[4] = (float)DA((double)q[4], DM(0.3, PI));
-  q[7] = (float)DA((double)q[7], DM(0.3, PI));
-  q[8] = (float)DS((double)q[8], DM(0.6, PI));
-  q[9] = (float)DA((double)q[9], DM(0.3, PI));
   const double PI2 = DM(2.0, PI);
-  for (int i = 0; i < 10; i++) q[i] = (float)fmod((double)q[i], PI2);
-
-  // RobotState::set — Quaternionf::toRotationMatrix
-  float R[9];
-  {
-    float w = rf[6], x = rf[7], y = rf[8], z = rf[9];
-    float tx = FM(2.f, x), ty = FM(2.f, y), tz = FM(2.f, z);
-    float twx = FM(tx, w), twy = FM(ty, w), twz = FM(tz, w);
-    float txx = FM(tx, x), txy = FM(ty, x), txz = FM(tz, x);
-    float tyy = FM(ty, y), tyz = FM(tz, y), tzz = FM(tz, z);
-    R[0] = FS(1.f, FA(tyy, tzz));
-    R[1] = FS(txy, twz);
-    R[2] = FA(txz, twy);
-    R[3] = FA(txy, twz);
-    R[4] = FS(1.f, FA(txx, tzz));
-    R[5] = FS(tyz, twx);
-    R[6] = FS(txz, twy);
-    R[7] = FA(tyz, twx);
-    R[8] = FS(1.f, FA(txx, tyy));
+  for (int i = 0; i < 5; i++) q[i] = (float)fmod((double)q[i], PI2);
+  float R[9], Rf[9];
+  quat_to_R(rf + 6, R);
+  foot_rotation(q, Rf);
+  const float mu = 2.0f, lt = 0.09f, lh = 0.06f;
+  const int r0 = 8 * leg, cF = 3 * leg, cM = 6 + 3 * leg;
+  Fblk[(r0 + 0) * 12 + cF + 0] = -mu; Fblk[(r0 + 0) * 12 + cF + 2] = 1.f;
+  Fblk[(r0 + 1) * 12 + cF + 0] = mu;  Fblk[(r0 + 1) * 12 + cF + 2] = 1.f;
+  Fblk[(r0 + 2) * 12 + cF + 1] = -mu; Fblk[(r0 + 2) * 12 + cF + 2] = 1.f;
+  Fblk[(r0 + 3) * 12 + cF + 1] = mu;  Fblk[(r0 + 3) * 12 + cF + 2] = 1.f;
+  float v1t[3] = {FM(-lt, Rf[2]), FM(-lt, Rf[5]), FM(-lt, Rf[8])};
+  float v1h[3] = {FM(-lh, Rf[2]), FM(-lh, Rf[5]), FM(-lh, Rf[8])};
+  for (int j = 0; j < 3; j++) {
+    float xw = FA(FA(FM(Rf[0], R[j * 3]), FM(Rf[3], R[j * 3 + 1])), FM(Rf[6], R[j * 3 + 2]));
+    float yw = FA(FA(FM(Rf[1], R[j * 3]), FM(Rf[4], R[j * 3 + 1])), FM(Rf[7], R[j * 3 + 2]));
+    float zt = FA(FA(FM(v1t[0], R[j * 3]), FM(v1t[1], R[j * 3 + 1])), FM(v1t[2], R[j * 3 + 2]));
+    float zh = FA(FA(FM(v1h[0], R[j * 3]), FM(v1h[1], R[j * 3 + 1])), FM(v1h[2], R[j * 3 + 2]));
+    Fblk[(r0 + 4) * 12 + cM + j] = xw;
+    Fblk[(r0 + 5) * 12 + cF + j] = zt;
+    Fblk[(r0 + 5) * 12 + cM + j] = yw;
+    Fblk[(r0 + 6) * 12 + cF + j] = zh;
+    Fblk[(r0 + 6) * 12 + cM + j] = (leg == 0) ? -yw : yw;  // quirk Q5
   }
-  // quat_to_rpy: SolverMPC.cpp:333-342
+  Fblk[(r0 + 7) * 12 + cF + 2] = 2.f;
+}
+// role "state": rpy (SolverMPC.cpp:333-342), Rb (:65-89), x0 (:420), the non-trivial entries of Acd (:145,315-317)
+__device__ inline void role_state(const float* rf, float dt, float* x0f, float* Acd)
+{
   float rpy[3];
   {
     float qw = rf[6], qx = rf[7], qy = rf[8], qz = rf[9];
@@ -265,7 +305,6 @@ __device__ inline void prologue(const float* rf, float dt, float* x0f, float* Ac
     rpy[2] = (float)atan2((double)FM(2.f, FA(FM(qw, qz), FM(qx, qy))),
                           DS(1.0, (double)FM(2.f, FA(FM(qy, qy), FM(qz, qz)))));
   }
-  // euler_to_rotation: SolverMPC.cpp:65-89
   float Rb[9];
   {
     double sp, cp, sy, cy;
@@ -281,8 +320,17 @@ __device__ inline void prologue(const float* rf, float dt, float* x0f, float* Ac
     x0f[9 + i] = rf[3 + i];
   }
   x0f[12] = 9.81f;
-  // I_world, I_inv: SolverMPC.cpp:421, 320
-  float Iinv[9];
+  for (int i = 0; i < 13; i++) Acd[i * 13 + i] = 1.f;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Acd[i * 13 + 6 + j] = FA(0.f, FM(dt, Rb[i * 3 + j]));
+  for (int i = 0; i < 3; i++) Acd[(3 + i) * 13 + 9 + i] = FA(0.f, FM(dt, 1.f));
+  Acd[11 * 13 + 12] = FA(0.f, FM(dt, -1.f));
+}
+// role "inertia": I_world, its inverse (SolverMPC.cpp:421, 320) and Bcd = dt*B (:146, 323-330), m = 9.0 (:423)
+__device__ inline void role_inertia(const float* rf, float dt, float* Bcd)
+{
+  float R[9], Iinv[9];
+  quat_to_R(rf + 6, R);
   {
     const float Ib[3] = {0.5413f, 0.5200f, 0.0691f};
     float RI[9], Rt[9], Iw[9];
@@ -294,14 +342,6 @@ __device__ inline void prologue(const float* rf, float dt, float* x0f, float* Ac
     mul3(RI, Rt, Iw);
     inverse3(Iw, Iinv);
   }
-  // ct_ss_mats + c2qp's Acd/Bcd: SolverMPC.cpp:312-331, 145-146
-  for (int i = 0; i < 169; i++) Acd[i] = 0.f;
-  for (int i = 0; i < 156; i++) Bcd[i] = 0.f;
-  for (int i = 0; i < 13; i++) Acd[i * 13 + i] = 1.f;
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) Acd[i * 13 + 6 + j] = FA(0.f, FM(dt, Rb[i * 3 + j]));
-  for (int i = 0; i < 3; i++) Acd[(3 + i) * 13 + 9 + i] = FA(0.f, FM(dt, 1.f));
-  Acd[11 * 13 + 12] = FA(0.f, FM(dt, -1.f));
   for (int b = 0; b < 2; b++) {
     float rx = rf[13 + 0 + b], ry = rf[13 + 2 + b], rz = rf[13 + 4 + b];
     float cm[9] = {0.f, -rz, ry, rz, 0.f, -rx, -ry, rx, 0.f};
@@ -316,93 +356,89 @@ __device__ inline void prologue(const float* rf, float dt, float* x0f, float* Ac
       Bcd[(6 + i) * 12 + 6 + j] = v;
       Bcd[(6 + i) * 12 + 9 + j] = v;
     }
-  {
-    float v = FM(dt, FD(1.f, 9.0f));  // mass literal 9.0, SolverMPC.cpp:423
-    for (int i = 0; i < 3; i++) {
-      Bcd[(9 + i) * 12 + i] = v;
-      Bcd[(9 + i) * 12 + 3 + i] = v;
-    }
-  }
-  // F_control: SolverMPC.cpp:488-548
-  for (int i = 0; i < 192; i++) Fblk[i] = 0.f;
-  const float mu = 2.0f, lt = 0.09f, lh = 0.06f;
-  for (int leg = 0; leg < 2; leg++) {
-    float Rf[9];
-    foot_rotation(&q[5 * leg], Rf);
-    const int r0 = 8 * leg, cF = 3 * leg, cM = 6 + 3 * leg;
-    Fblk[(r0 + 0) * 12 + cF + 0] = -mu; Fblk[(r0 + 0) * 12 + cF + 2] = 1.f;
-    Fblk[(r0 + 1) * 12 + cF + 0] = mu;  Fblk[(r0 + 1) * 12 + cF + 2] = 1.f;
-    Fblk[(r0 + 2) * 12 + cF + 1] = -mu; Fblk[(r0 + 2) * 12 + cF + 2] = 1.f;
-    Fblk[(r0 + 3) * 12 + cF + 1] = mu;  Fblk[(r0 + 3) * 12 + cF + 2] = 1.f;
-    float v1t[3] = {FM(-lt, Rf[2]), FM(-lt, Rf[5]), FM(-lt, Rf[8])};
-    float v1h[3] = {FM(-lh, Rf[2]), FM(-lh, Rf[5]), FM(-lh, Rf[8])};
-    for (int j = 0; j < 3; j++) {
-      float xw = FA(FA(FM(Rf[0], R[j * 3]), FM(Rf[3], R[j * 3 + 1])), FM(Rf[6], R[j * 3 + 2]));
-      float yw = FA(FA(FM(Rf[1], R[j * 3]), FM(Rf[4], R[j * 3 + 1])), FM(Rf[7], R[j * 3 + 2]));
-      float zt = FA(FA(FM(v1t[0], R[j * 3]), FM(v1t[1], R[j * 3 + 1])), FM(v1t[2], R[j * 3 + 2]));
-      float zh = FA(FA(FM(v1h[0], R[j * 3]), FM(v1h[1], R[j * 3 + 1])), FM(v1h[2], R[j * 3 + 2]));
-      Fblk[(r0 + 4) * 12 + cM + j] = xw;
-      Fblk[(r0 + 5) * 12 + cF + j] = zt;
-      Fblk[(r0 + 5) * 12 + cM + j] = yw;
-      Fblk[(r0 + 6) * 12 + cF + j] = zh;
-      Fblk[(r0 + 6) * 12 + cM + j] = (leg == 0) ? -yw : yw;  // quirk Q5
-    }
-    Fblk[(r0 + 7) * 12 + cF + 2] = 2.f;
+  float v = FM(dt, FD(1.f, 9.0f));
+  for (int i = 0; i < 3; i++) {
+    Bcd[(9 + i) * 12 + i] = v;
+    Bcd[(9 + i) * 12 + 3 + i] = v;
   }
 }
 
-// block argmin over (value, index); result broadcast through `red` (32 doubles followed by 32 ints)
-__device__ inline void block_argmin(double v, int idx, double* red, double& vout, int& iout)
+// block argmin over (value, index) with ONE barrier: warp partials to smem, every thread folds them.
+// `red` = NW doubles followed (at +32 doubles) by NW ints.
+__device__ __forceinline__ void block_argmin(double v, int idx, double* red, int nwarps, double& vout, int& iout)
 {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_down_sync(0xffffffffu, v, o);
-    int oi = __shfl_down_sync(0xffffffffu, idx, o);
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
   int* redi = reinterpret_cast<int*>(red + 32);
   if (lane == 0) { red[wid] = v; redi[wid] = idx; }
   __syncthreads();
-  if (wid == 0) {
-    v = (lane < nw) ? red[lane] : 1e300;
-    idx = (lane < nw) ? redi[lane] : 0x7fffffff;
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_down_sync(0xffffffffu, v, o);
-      int oi = __shfl_down_sync(0xffffffffu, idx, o);
-      if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-    if (lane == 0) { red[31] = v; redi[31] = idx; }
+  v = red[0];
+  idx = redi[0];
+  for (int w = 1; w < nwarps; w++) {
+    const double ov = red[w];
+    const int oi = redi[w];
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
-  __syncthreads();
-  vout = red[31];
-  iout = redi[31];
+  vout = v;
+  iout = idx;
+}
+
+// working-set entry: block index in the high bits, normal index (leg*10+type) in the low byte
+__device__ __forceinline__ int ws_pack(int blk, int nidx) { return (blk << 8) | nidx; }
+
+// ------------------------------------------------------------------------------------------------
+// classification pre-pass: bucket instances by reduced size (number of stance (step,leg) blocks)
+// ------------------------------------------------------------------------------------------------
+__global__ void hmpc_classify_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,
+                                     int nb_hi0, int* counts, int* lists, int list_stride)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const unsigned char* g = records + (size_t)i * rec_stride + (54 + 12 * N) * 4;
+  int nb = 0;
+  for (int e = 0; e < 2 * N; e++) {
+    const float ub = FM(f_max, (float)g[e]);
+    nb += !(ub < 0.0001f && ub > -0.0001f);
+  }
+  const int c = (nb <= nb_hi0) ? 0 : 1;
+  const int slot = atomicAdd(&counts[c], 1);
+  lists[(size_t)c * list_stride + slot] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  NT threads, BW = columns of the 6xBW register block each thread sweeps (3 or 6)
 // ------------------------------------------------------------------------------------------------
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs ka)
+template <int NT, int MINB, int BW>
+__global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs ka)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = NT / 32;
+  constexpr int HPB = 6 / BW;  // threads per 6x6 block
   const int N = ka.horizon;
-  const Layout L = make_layout(N, ka.nb_cap, ka.qmax, ka.rec_stride);
+  const Layout& L = ka.L;
   const bool dump = (ka.dbg_H != nullptr);
 
   double* H = reinterpret_cast<double*>(smem + L.H);
   double* gq = reinterpret_cast<double*>(smem + L.gq);
   double* x0 = reinterpret_cast<double*>(smem + L.x0);
   double* xv = reinterpret_cast<double*>(smem + L.x);
-  double* wv = reinterpret_cast<double*>(smem + L.w);
   double* HA = reinterpret_cast<double*>(smem + L.HA);
-  double* nrm = reinterpret_cast<double*>(smem + L.nrm);  // [leg][type][6]
+  double* nrm = reinterpret_cast<double*>(smem + L.nrm);  // [leg*10+type][6]
   double* rhs = reinterpret_cast<double*>(smem + L.rhs);  // [block*10 + type]
   int* blk_sl = reinterpret_cast<int*>(smem + L.blk);     // block -> step*2+leg
   int* sl_blk = blk_sl + ka.nb_cap;                       // step*2+leg -> block or -1
-  double* red = reinterpret_cast<double*>(smem + L.misc);       // 32 doubles + 32 ints of reduction scratch
-  int* flags = reinterpret_cast<int*>(smem + L.misc + 384);     // [0]=NB [1]=stance0 [2]=stance1 [3]=code [4]=decision [5]=drop
+  double* red = reinterpret_cast<double*>(smem + L.misc);    // 32 doubles + 32 ints of reduction scratch
+  int* flags = reinterpret_cast<int*>(smem + L.misc + 384);  // [0]=NB [1]=stance0 [2]=stance1 [3]=code [4]=decision [5]=drop
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.misc + 448);
+  double* enext = reinterpret_cast<double*>(smem + L.misc + 464);  // [2] next-pivot diagonal, double-buffered
+  double* tstep = reinterpret_cast<double*>(smem + L.misc + 480);  // [1] step length of the current GI iteration
 
   double* Li = reinterpret_cast<double*>(smem + L.Li);
   double* lam = reinterpret_cast<double*>(smem + L.lam);
@@ -417,10 +453,9 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
   float* x0f = reinterpret_cast<float*>(smem + L.x0f);
   float* Acd = reinterpret_cast<float*>(smem + L.Acd);
   float* Bcd = reinterpret_cast<float*>(smem + L.Bcd);
-  float* P = reinterpret_cast<float*>(smem + L.P);
-  float* Mb = reinterpret_cast<float*>(smem + L.M);
-  float* Tb = reinterpret_cast<float*>(smem + L.T);
-  float* dd = reinterpret_cast<float*>(smem + L.dd);
+  float* Pbuf = reinterpret_cast<float*>(smem + L.P);  // two 13x13 buffers, 172 floats apart
+  float* Mb = reinterpret_cast<float*>(smem + L.M);    // [N][12][12] rows 0..11 of P_d * Bcd
+  float* dd = reinterpret_cast<float*>(smem + L.dd);   // [N][12]
   float* Fblk = reinterpret_cast<float*>(smem + L.fbl);
 
   if (tid == 0) {
@@ -429,116 +464,124 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
   }
   __syncthreads();
   uint32_t phase = 0;
+  const int count = ka.list ? ka.counts[ka.cls] : ka.batch;
 
-  for (int inst = blockIdx.x; inst < ka.batch; inst += gridDim.x) {
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int inst = ka.list ? ka.list[idx] : idx;
     // ---------------- stage 0: record -> shared memory (TMA bulk copy) ----------------
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the union
       mbar_expect_tx(bar, (uint32_t)ka.rec_stride);
       bulk_g2s(rec, ka.records + (size_t)inst * ka.rec_stride, (uint32_t)ka.rec_stride, bar);
     }
+    // meanwhile: zero the sparse fp32 operands, P_0 = I
+    for (int e = tid; e < 169; e += NT) { Acd[e] = 0.f; Pbuf[e] = (e / 13 == e % 13) ? 1.f : 0.f; }
+    for (int e = tid; e < 156; e += NT) Bcd[e] = 0.f;
+    for (int e = tid; e < 192; e += NT) Fblk[e] = 0.f;
     mbar_wait(bar, phase);
     phase ^= 1;
 
     // ---------------- contact table -> reduced block list (SolverMPC.cpp:589-637) ----------------
     const unsigned char* gait = rec + (54 + 12 * N) * 4;
-    if (tid == 0) {
-      int nb = 0;
-      unsigned st0 = 0, st1 = 0;
-      for (int s = 0; s < N; s++)
-        for (int l = 0; l < 2; l++) {
-          float ub = FM(ka.f_max, (float)gait[2 * s + l]);
-          bool swing = (ub < 0.0001f && ub > -0.0001f) && !dump;  // near_zero(lb) && near_zero(ub); lb == 0
-          if (swing) sl_blk[2 * s + l] = -1;
-          else {
-            sl_blk[2 * s + l] = (nb < ka.nb_cap) ? nb : -1;
-            if (nb < ka.nb_cap) blk_sl[nb] = 2 * s + l;
-            nb++;
-            if (l == 0) st0 |= 1u << s; else st1 |= 1u << s;
-          }
+    if (wid == 0) {
+      bool stance = false;
+      if (lane < 2 * N) {
+        const float ub = FM(ka.f_max, (float)gait[lane]);
+        stance = !(ub < 0.0001f && ub > -0.0001f) || dump;  // swing <=> near_zero(lb) && near_zero(ub); lb == 0
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, stance);
+      const int k = __popc(mask & ((1u << lane) - 1u));
+      if (lane < 2 * N) {
+        sl_blk[lane] = (stance && k < ka.nb_cap) ? k : -1;
+        if (stance && k < ka.nb_cap) blk_sl[k] = lane;
+      }
+      if (lane == 0) {
+        unsigned st0 = 0, st1 = 0;
+        for (int s = 0; s < N; s++) {
+          st0 |= ((mask >> (2 * s)) & 1u) << s;
+          st1 |= ((mask >> (2 * s + 1)) & 1u) << s;
         }
-      flags[0] = nb;
-      flags[1] = (int)st0;
-      flags[2] = (int)st1;
-      flags[3] = ST_OK;
+        flags[0] = __popc(mask);
+        flags[1] = (int)st0;
+        flags[2] = (int)st1;
+        flags[3] = ST_OK;
+      }
     }
     __syncthreads();
     const int NB = flags[0];
-    if (!(NB > ka.nb_lo && NB <= ka.nb_hi)) {  // another launch's instance
-      __syncthreads();
-      continue;
-    }
     const int n = 6 * NB, m = 10 * NB;
     const unsigned stmask[2] = {(unsigned)flags[1], (unsigned)flags[2]};
 
-    // ---------------- stage 1: prologue ----------------
-    if (tid == 0) prologue(rf, ka.dt, x0f, Acd, Bcd, Fblk);
-    if (tid == 32 || (nt <= 32 && tid == 0)) {
-      for (int i = 0; i < 169; i++) P[i] = (i / 13 == i % 13) ? 1.f : 0.f;
+    // ---------------- stage 1: prologue, three roles on different warps ----------------
+    {
+      constexpr int W1 = (NW > 1) ? 1 : 0, W2 = (NW > 2) ? 2 : 0;
+      if (wid == 0 && lane < 2) role_leg(rf, lane, Fblk);
+      if (wid == W1 && lane == 2) role_state(rf, ka.dt, x0f, Acd);
+      if (wid == W2 && lane == 3) role_inertia(rf, ka.dt, Bcd);
     }
     __syncthreads();
 
-    // constraint normals (fp64 copies of the fp32 rows) and right-hand sides, "c'x >= d" form
-    for (int e = tid; e < 2 * 10 * 6; e += nt) {
-      int leg = e / 60, t = (e / 6) % 10, c = e % 6;
-      int col = col12_of(leg, c);
-      // one-sided rows in "c'x >= d" form: t0-3 friction (lower), t4/t5 Mx lower/upper, t6/t7 line
-      // contact (upper), t8/t9 Fz lower/upper
+    // constraint normals (fp64 copies of the fp32 rows) and right-hand sides, "c'x >= d" form:
+    // t0-3 friction (lower), t4/t5 Mx lower/upper, t6/t7 line contact (upper), t8/t9 Fz lower/upper
+    for (int e = tid; e < 2 * 10 * 6; e += NT) {
+      const int leg = e / 60, t = (e / 6) % 10, c = e % 6;
+      const int col = col12_of(leg, c);
       const int row = (t < 5) ? t : (t == 5 ? 4 : (t < 8 ? t - 1 : 7));
       const bool neg = (t == 5 || t == 6 || t == 7 || t == 9);
-      float v = Fblk[(8 * leg + row) * 12 + col];
+      const float v = Fblk[(8 * leg + row) * 12 + col];
       nrm[e] = (double)(neg ? -v : v);
     }
-    for (int e = tid; e < m; e += nt) {
-      int k = e / 10, t = e % 10;
-      int sl = blk_sl[k];
-      double d = 0.0;
-      if (t == 5) d = -(double)0.01f;
-      if (t == 9) d = -(double)FM(ka.f_max, (float)gait[sl]);
-      rhs[e] = d;
+    if (!dump) {
+      for (int e = tid; e < m; e += NT) {
+        const int k = e / 10, t = e % 10;
+        double d = 0.0;
+        if (t == 5) d = -(double)0.01f;
+        if (t == 9) d = -(double)FM(ka.f_max, (float)gait[blk_sl[k]]);
+        rhs[e] = d;
+      }
     }
 
-    // ---------------- stage 2: powers of Acd, Toeplitz blocks ----------------
-    for (int k = 1; k <= N; k++) {
-      const float* Pp = P + (k - 1) * 169;
-      float* Pn = P + k * 169;
-      for (int e = tid; e < 169; e += nt) {
-        int i = e / 13, j = e % 13;
-        float acc = FM(Pp[i * 13], Acd[j]);
+    // ---------------- stage 2: powers of Acd, Toeplitz blocks, d = A_qp x0 - X_d ----------------
+    // pass k has P_k in Pc: writes P_{k+1}, M_k = P_k*Bcd (rows 0..11) and d_{k-1} = P_k x0 - traj_{k-1}
+    for (int k = 0; k <= N; k++) {
+      const float* Pc = Pbuf + (k & 1) * 172;
+      float* Pn = Pbuf + ((k + 1) & 1) * 172;
+      for (int e = tid; e < 169 + 144 + 12; e += NT) {
+        if (e < 169) {
+          if (k < N) {
+            const int i = e / 13, j = e % 13;
+            float acc = FM(Pc[i * 13], Acd[j]);
 #pragma unroll
-        for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pp[i * 13 + t], Acd[t * 13 + j]));
-        Pn[e] = acc;
+            for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pc[i * 13 + t], Acd[t * 13 + j]));
+            Pn[e] = acc;
+          }
+        } else if (e < 169 + 144) {
+          if (k < N) {
+            const int r = (e - 169) / 12, c = (e - 169) % 12;
+            float acc = FM(Pc[r * 13], Bcd[c]);
+#pragma unroll
+            for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pc[r * 13 + t], Bcd[t * 12 + c]));
+            Mb[k * 144 + r * 12 + c] = acc;
+          }
+        } else if (k >= 1) {
+          const int r = e - 169 - 144, s = k - 1;
+          float acc = FM(Pc[r * 13], x0f[0]);
+#pragma unroll
+          for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pc[r * 13 + t], x0f[t]));
+          dd[12 * s + r] = FS(acc, rf[54 + 12 * s + r]);
+        }
       }
       __syncthreads();
     }
-    // M_d = P_d * Bcd (rows 0..11 used), T_d = M_d .* w, dd = A_qp x0 - X_d
-    for (int e = tid; e < N * 144; e += nt) {
-      int d = e / 144, r = (e % 144) / 12, c = e % 12;
-      const float* Pd = P + d * 169 + r * 13;
-      float acc = FM(Pd[0], Bcd[c]);
-#pragma unroll
-      for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pd[t], Bcd[t * 12 + c]));
-      Mb[d * 156 + r * 12 + c] = acc;
-      Tb[d * 144 + r * 12 + c] = FM(acc, rf[30 + r]);
-    }
-    for (int e = tid; e < N * 12; e += nt) {
-      int s = e / 12, r = e % 12;
-      const float* Ps = P + (s + 1) * 169 + r * 13;
-      float acc = FM(Ps[0], x0f[0]);
-#pragma unroll
-      for (int t = 1; t < 13; t++) acc = FA(acc, FM(Ps[t], x0f[t]));
-      dd[13 * s + r] = FS(acc, rf[54 + 12 * s + r]);
-    }
-    __syncthreads();
 
-    // ---------------- stage 3: Hessian prefix chains + gradient ----------------
+    // ---------------- stage 3: Hessian prefix chains (4 columns per item) + gradient ----------------
     if (dump) {
       float* oF = ka.dbg_F + (size_t)inst * 192;
-      for (int e = tid; e < 192; e += nt) oF[e] = Fblk[e];
+      for (int e = tid; e < 192; e += NT) oF[e] = Fblk[e];
       float* olb = ka.dbg_lb + (size_t)inst * 16 * N;
       float* oub = ka.dbg_ub + (size_t)inst * 16 * N;
-      for (int e = tid; e < 16 * N; e += nt) {
-        int s = e / 16, r = e % 16, leg = r / 8, rr = r % 8;
+      for (int e = tid; e < 16 * N; e += NT) {
+        const int s = e / 16, r = e % 16, leg = r / 8, rr = r % 8;
         float lo = 0.f, hi = 0.f;
         if (rr < 4) hi = (float)5e10;
         else if (rr == 4) hi = 0.01f;
@@ -548,190 +591,232 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
         oub[e] = hi;
       }
     }
-    for (int id = tid; id < N * 144; id += nt) {
-      const int delta = id / 144, ii = (id % 144) / 12, jj = id % 12;
-      if (delta == 0 && ii > jj) continue;
-      const int li = leg_of(ii), lj = leg_of(jj);
-      const unsigned need = stmask[li] & (stmask[lj] >> delta);  // bit a: entry (a,ii)-(a+delta,jj) wanted
-      if (!need) continue;
-      const int amin = __ffs(need) - 1;
-      const int Kmax = N - 1 - delta - amin;
-      const int ci = loc_of(ii), cj = loc_of(jj);
-      const float alpha = (delta == 0 && ii == jj) ? rf[42 + ii] : 0.f;
-      float acc = 0.f;
-      for (int K = 0; K <= Kmax; K++) {
-        const float* Tk = Tb + (K + delta) * 144 + ii;
-        const float* Mk = Mb + K * 156 + jj;
+    {
+      float wr[12];
 #pragma unroll
-        for (int r = 0; r < 12; r++) acc = FA(acc, FM(Tk[r * 12], Mk[r * 12]));
-        const int a = N - 1 - K - delta, b = a + delta;
-        if ((need >> a) & 1u) {
-          const float hv = FM(2.f, FA(acc, alpha));  // qH = 2*(B'SB + Alpha_rep)
-          if (dump) {
-            float* oH = ka.dbg_H + (size_t)inst * (144 * N * N);
-            oH[(size_t)(12 * a + ii) * (12 * N) + 12 * b + jj] = hv;
-            oH[(size_t)(12 * b + jj) * (12 * N) + 12 * a + ii] = hv;
-          } else {
-            const int ka_ = sl_blk[2 * a + li], kb_ = sl_blk[2 * b + lj];
-            const double hd = (double)hv;
-            if (ka_ == kb_) {
-              H[blk_off(ka_, ka_) + ci * 6 + cj] = hd;
-              H[blk_off(ka_, ka_) + cj * 6 + ci] = hd;
-            } else if (kb_ > ka_) H[blk_off(kb_, ka_) + cj * 6 + ci] = hd;
-            else H[blk_off(ka_, kb_) + ci * 6 + cj] = hd;
+      for (int r = 0; r < 12; r++) wr[r] = rf[30 + r];
+      // item = (delta, ii, jq): running sums G_delta(K)[ii][4jq..4jq+3] = sum_{e<=K} T_{e+delta}^T M_e;
+      // block (a,b) of B'SB, b - a = delta, equals G_delta(N-1-b) — the oracle's own summation order.
+      for (int it = tid; it < N * 36; it += NT) {
+        const int delta = it / 36, ii = (it % 36) / 3, jq = it % 3;
+        const int li = leg_of(ii);
+        unsigned need[4];
+        unsigned any = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int jj = 4 * jq + c;
+          need[c] = (delta == 0 && ii > jj) ? 0u : (stmask[li] & (stmask[leg_of(jj)] >> delta));
+          any |= need[c];
+        }
+        if (!any) continue;
+        const int Kmax = N - 1 - delta - (__ffs(any) - 1);
+        const int ci = loc_of(ii);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int K = 0; K <= Kmax; K++) {
+          const float* Mi = Mb + (K + delta) * 144 + ii;
+          const float4* Mj = reinterpret_cast<const float4*>(Mb + K * 144 + 4 * jq);
+#pragma unroll
+          for (int r = 0; r < 12; r++) {
+            const float tv = FM(Mi[r * 12], wr[r]);  // (B'S)(i,k) = B(k,i)*w(k)
+            const float4 mj = Mj[r * 3];
+            acc[0] = FA(acc[0], FM(tv, mj.x));
+            acc[1] = FA(acc[1], FM(tv, mj.y));
+            acc[2] = FA(acc[2], FM(tv, mj.z));
+            acc[3] = FA(acc[3], FM(tv, mj.w));
+          }
+          const int a = N - 1 - K - delta, b = a + delta;
+          if ((any >> a) & 1u) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              if (!((need[c] >> a) & 1u)) continue;
+              const int jj = 4 * jq + c;
+              const float alpha = (delta == 0 && ii == jj) ? rf[42 + ii] : 0.f;
+              const float hv = FM(2.f, FA(acc[c], alpha));  // qH = 2*(B'SB + Alpha_rep)
+              if (dump) {
+                float* oH = ka.dbg_H + (size_t)inst * (144 * N * N);
+                oH[(size_t)(12 * a + ii) * (12 * N) + 12 * b + jj] = hv;
+                oH[(size_t)(12 * b + jj) * (12 * N) + 12 * a + ii] = hv;
+              } else {
+                const int ka_ = sl_blk[2 * a + li], kb_ = sl_blk[2 * b + leg_of(jj)], cj = loc_of(jj);
+                const double hd = (double)hv;
+                if (ka_ == kb_) {
+                  H[blk_off(ka_, ka_) + ci * 6 + cj] = hd;
+                  H[blk_off(ka_, ka_) + cj * 6 + ci] = hd;
+                } else if (kb_ > ka_) H[blk_off(kb_, ka_) + cj * 6 + ci] = hd;
+                else H[blk_off(ka_, kb_) + ci * 6 + cj] = hd;
+              }
+            }
           }
         }
       }
-    }
-    for (int e = tid; e < N * 12; e += nt) {
-      const int a = e / 12, ii = e % 12, li = leg_of(ii);
-      if (!((stmask[li] >> a) & 1u)) continue;
-      float acc = 0.f;
-      for (int s = a; s < N; s++) {
-        const float* Tk = Tb + (s - a) * 144 + ii;
-        const float* dk = dd + 13 * s;
+      // gradient: g(a,ii) = sum_{s>=a} sum_r (T_{s-a}[r][ii]*2) * d_s[r]
+      for (int e = tid; e < N * 12; e += NT) {
+        const int a = e / 12, ii = e % 12, li = leg_of(ii);
+        if (!((stmask[li] >> a) & 1u)) continue;
+        float acc = 0.f;
+        for (int s = a; s < N; s++) {
+          const float* Mi = Mb + (s - a) * 144 + ii;
+          const float* dk = dd + 12 * s;
 #pragma unroll
-        for (int r = 0; r < 12; r++) acc = FA(acc, FM(FM(Tk[r * 12], 2.f), dk[r]));
+          for (int r = 0; r < 12; r++) acc = FA(acc, FM(FM(FM(Mi[r * 12], wr[r]), 2.f), dk[r]));
+        }
+        if (dump) ka.dbg_g[(size_t)inst * 12 * N + e] = acc;
+        else gq[6 * sl_blk[2 * a + li] + loc_of(ii)] = (double)acc;
       }
-      if (dump) ka.dbg_g[(size_t)inst * 12 * N + e] = acc;
-      else gq[6 * sl_blk[2 * a + li] + loc_of(ii)] = (double)acc;
     }
     __syncthreads();
     if (dump) continue;
 
-    float* out = ka.wrench + (size_t)inst * 12 * N;
     if (NB == 0) {
-      for (int e = tid; e < 12 * N; e += nt) out[e] = 0.f;
+      for (int e = tid; e < 12 * N; e += NT) {
+        if (ka.wrench) ka.wrench[(size_t)inst * 12 * N + e] = 0.f;
+        if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = 0.0;
+      }
       if (tid == 0) ka.status[inst] = ST_OK;
       __syncthreads();
       continue;
     }
 
-    // ---------------- stage 4: sweep inversion, one 6x6 block per thread in registers ----------------
+    // ---------------- stage 4: sweep inversion, one 6xBW block per thread in registers ----------------
     // After sweeping every pivot the matrix holds -H^-1 (Goodnight's sweep operator on an SPD matrix).
+    // Per pivot: ONE barrier.  The pivot column k+1 and the current value of diagonal k+2 are published
+    // during step k, and every thread predicts pivot k+1's reciprocal while it applies step k.
     {
       const int nbt = NB * (NB + 1) / 2;
-      const bool own = tid < nbt;
+      const int bt = tid / HPB, hh = tid % HPB;  // block id, half
+      const bool own = bt < nbt;
       int ib = 0, jb = 0;
       if (own) {
-        ib = (int)((sqrtf(8.f * (float)tid + 1.f) - 1.f) * 0.5f);
-        while ((ib + 1) * (ib + 2) / 2 <= tid) ib++;
-        while (ib * (ib + 1) / 2 > tid) ib--;
-        jb = tid - ib * (ib + 1) / 2;
+        ib = (int)((sqrtf(8.f * (float)bt + 1.f) - 1.f) * 0.5f);
+        while ((ib + 1) * (ib + 2) / 2 <= bt) ib++;
+        while (ib * (ib + 1) / 2 > bt) ib--;
+        jb = bt - ib * (ib + 1) / 2;
       }
-      double a[36];
+      const int c0 = BW * hh;  // first column of this thread's strip inside the block
+      double a[6][BW];
       if (own) {
-        const double* src = H + blk_off(ib, jb);
+        const double* src = H + blk_off(ib, jb) + c0;
 #pragma unroll
-        for (int e = 0; e < 36; e++) a[e] = src[e];
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < BW; c++) a[r][c] = src[r * 6 + c];
       }
-      double* colbuf[2] = {xv, wv};
-      bool bad = false;
+      double* colbuf[2] = {xv, HA};
+      // publish pivot column 0 and diagonal 1
+      if (own) {
+        if (jb == 0 && hh == 0) {
+#pragma unroll
+          for (int r = 0; r < 6; r++) colbuf[0][6 * ib + r] = a[r][0];
+        }
+        if (ib == 0 && jb == 0 && hh == 1 / BW) enext[0] = a[1][1 % BW];
+      }
+      __syncthreads();
+      double inv = 1.0 / colbuf[0][0];
+      bool bad = !(colbuf[0][0] > 0.0);
       for (int kb = 0; kb < NB; kb++) {
 #pragma unroll
         for (int kk = 0; kk < 6; kk++) {
-          double* col = colbuf[kk & 1];
-          if (own) {
-            if (jb == kb) {
-#pragma unroll
-              for (int r = 0; r < 6; r++) col[6 * ib + r] = a[r * 6 + kk];
-            } else if (ib == kb) {
-#pragma unroll
-              for (int c = 0; c < 6; c++) col[6 * jb + c] = a[kk * 6 + c];
-            }
+          const int k = 6 * kb + kk;
+          const double* col = colbuf[kk & 1];
+          double* coln = colbuf[(kk + 1) & 1];
+          double invn = 0.0;
+          if (k + 1 < n) {  // reciprocal of the next pivot, overlapped with this step's updates
+            const double cn = col[k + 1];
+            const double dn = fma(-cn, cn * inv, enext[kk & 1]);
+            bad |= !(dn > 0.0);
+            invn = 1.0 / dn;
           }
-          __syncthreads();
           if (own) {
-            const double d = col[6 * kb + kk];
-            if (!(d > 0.0)) bad = true;
-            const double inv = 1.0 / d;
-            double ci[6], cj[6];
+            double ci[6], cj[BW];
 #pragma unroll
             for (int r = 0; r < 6; r++) ci[r] = col[6 * ib + r];
 #pragma unroll
-            for (int c = 0; c < 6; c++) cj[c] = col[6 * jb + c] * inv;
+            for (int c = 0; c < BW; c++) cj[c] = col[6 * jb + c0 + c] * inv;
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
-              for (int c = 0; c < 6; c++) a[r * 6 + c] = fma(-ci[r], cj[c], a[r * 6 + c]);
-            if (jb == kb) {
+              for (int c = 0; c < BW; c++) a[r][c] = fma(-ci[r], cj[c], a[r][c]);
+            if (jb == kb && hh == kk / BW) {
 #pragma unroll
-              for (int r = 0; r < 6; r++) a[r * 6 + kk] = ci[r] * inv;
+              for (int r = 0; r < 6; r++) a[r][kk % BW] = ci[r] * inv;
             }
             if (ib == kb) {
 #pragma unroll
-              for (int c = 0; c < 6; c++) a[kk * 6 + c] = cj[c];
-              if (jb == kb) a[kk * 6 + kk] = -inv;
+              for (int c = 0; c < BW; c++) a[kk][c] = cj[c];
+              if (jb == kb && hh == kk / BW) a[kk][kk % BW] = -inv;
+            }
+            // publish column k+1 (and diagonal k+2) for the next step
+            if (kk < 5) {
+              if (jb == kb && hh == (kk + 1) / BW) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) coln[6 * ib + r] = a[r][(kk + 1) % BW];
+              } else if (ib == kb && jb < kb) {
+#pragma unroll
+                for (int c = 0; c < BW; c++) coln[6 * jb + c0 + c] = a[kk + 1][c];
+              }
+              if (kk < 4) {
+                if (ib == kb && jb == kb && hh == (kk + 2) / BW) enext[(kk + 1) & 1] = a[kk + 2][(kk + 2) % BW];
+              } else {
+                if (ib == kb + 1 && jb == kb + 1 && hh == 0) enext[(kk + 1) & 1] = a[0][0];
+              }
+            } else {
+              if (jb == kb + 1 && hh == 0) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) coln[6 * ib + r] = a[r][0];
+              } else if (ib == kb + 1 && jb < kb + 1) {
+#pragma unroll
+                for (int c = 0; c < BW; c++) coln[6 * jb + c0 + c] = a[0][c];
+              }
+              if (ib == kb + 1 && jb == kb + 1 && hh == 1 / BW) enext[(kk + 1) & 1] = a[1][1 % BW];
             }
           }
+          __syncthreads();
+          inv = invn;
         }
       }
       if (own) {
-        double* dst = H + blk_off(ib, jb);
+        double* dst = H + blk_off(ib, jb) + c0;
 #pragma unroll
-        for (int e = 0; e < 36; e++) dst[e] = -a[e];
-        if (bad) atomicExch(&flags[3], ST_NOT_SPD);
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < BW; c++) dst[r * 6 + c] = -a[r][c];
       }
+      if (bad && tid == 0) flags[3] = ST_NOT_SPD;
       __syncthreads();
     }
 
     // ---------------- stage 5: dual active-set iterations ----------------
-    // x0 = -H^-1 g
-    for (int i = tid; i < n; i += nt) {
-      const int ibk = i / 6, r = i % 6;
+    // per-thread constants: one variable (row of H^-1) and up to CPT constraints
+    const bool isvar = tid < n;
+    const int vib = tid / 6, vr = tid % 6;
+    if (isvar) {  // x0 = -H^-1 g
       double acc = 0.0;
-      for (int jbk = 0; jbk < NB; jbk++) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) acc = fma(hsym(H, ibk, r, jbk, c), gq[6 * jbk + c], acc);
-      }
-      x0[i] = -acc;
+      for (int jbk = 0; jbk < NB; jbk++) acc += hrow6(H, vib, vr, jbk, gq + 6 * jbk);
+      x0[tid] = -acc;
+      xv[tid] = -acc;
     }
-    for (int e = tid; e < m; e += nt) act[e] = 0;
+    for (int e = tid; e < m; e += NT) act[e] = 0;
     __syncthreads();
 
     int q = 0, iters = 0;
     int code = flags[3];
-    double xscale = 1.0;
+    double tol;
     {
       double mx = 0.0;
-      for (int i = tid; i < n; i += nt) mx = fmax(mx, fabs(x0[i]));
+      for (int i = tid; i < n; i += NT) mx = fmax(mx, fabs(x0[i]));
       int dummy;
-      block_argmin(-mx, tid, red, mx, dummy);
-      xscale = fmax(1.0, -mx);
+      block_argmin(-mx, tid, red, NW, mx, dummy);
+      tol = 1e-9 * fmax(1.0, -mx);
+      __syncthreads();  // red is reused by the first argmin below
     }
-    const double tol = 1e-9 * xscale;
 
     while (code == ST_OK) {
-      // w = A_W' lam ; x = x0 + H^-1 w
-      for (int i = tid; i < n; i += nt) {
-        const int k = i / 6, c = i % 6, leg = blk_sl[k] & 1;
-        double acc = 0.0;
-        for (int j = 0; j < q; j++) {
-          const int cj = Wc[j];
-          if (cj / 10 == k) acc = fma(lam[j], nrm[(leg * 10 + cj % 10) * 6 + c], acc);
-        }
-        wv[i] = acc;
-      }
-      __syncthreads();
-      for (int i = tid; i < n; i += nt) {
-        const int ibk = i / 6, r = i % 6;
-        double acc = x0[i];
-        for (int jbk = 0; jbk < NB; jbk++) {
-          const double* wj = wv + 6 * jbk;
-          if (wj[0] != 0.0 || wj[1] != 0.0 || wj[2] != 0.0 || wj[3] != 0.0 || wj[4] != 0.0 || wj[5] != 0.0) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) acc = fma(hsym(H, ibk, r, jbk, c), wj[c], acc);
-          }
-        }
-        xv[i] = acc;
-      }
-      __syncthreads();
-      // most violated inactive constraint
+      // most violated inactive constraint (slacks straight from x)
       double sbest = 1e300;
       int pbest = 0x7fffffff;
-      for (int e = tid; e < m; e += nt) {
+      for (int e = tid; e < m; e += NT) {
         if (act[e]) continue;
-        const int k = e / 10, t = e % 10, leg = blk_sl[k] & 1;
+        const int k = e / 10, t = e - 10 * k, leg = blk_sl[k] & 1;
         const double* nn = nrm + (leg * 10 + t) * 6;
         const double* xb = xv + 6 * k;
         double s = -rhs[e];
@@ -741,37 +826,34 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
       }
       double sp;
       int p;
-      block_argmin(sbest, pbest, red, sp, p);
+      block_argmin(sbest, pbest, red, NW, sp, p);
       if (!(sp < -tol)) break;  // KKT point reached
 
       // ---- add constraint p (possibly after dropping blocking ones) ----
-      const int kp = p / 10, tp = p % 10, legp = blk_sl[kp] & 1;
-      const double* np_ = nrm + (legp * 10 + tp) * 6;
+      const int kp = p / 10, nip = (blk_sl[kp] & 1) * 10 + (p - 10 * kp);
+      const double* np_ = nrm + nip * 6;
       double lam_p = 0.0;
       while (true) {
         iters++;
         if (iters > ka.max_iter) { code = ST_ITER_CAP; break; }
-        // HA = H^-1 a_p
-        for (int i = tid; i < n; i += nt) {
-          const int ibk = i / 6, r = i % 6;
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < 6; c++) acc = fma(hsym(H, ibk, r, kp, c), np_[c], acc);
-          HA[i] = acc;
+        double ha = 0.0;
+        if (isvar) {  // HA = H^-1 a_p
+          ha = hrow6(H, vib, vr, kp, np_);
+          HA[tid] = ha;
         }
         __syncthreads();
         // warp 0: step direction in the dual space through the inverse Cholesky factor of the Schur complement
-        if (tid < 32) {
-          const int lane = tid;
+        if (wid == 0) {
           double cHc = 0.0;
 #pragma unroll
           for (int c = 0; c < 6; c++) cHc = fma(np_[c], HA[6 * kp + c], cHc);
           for (int j = lane; j < q; j += 32) {
-            const int cj = Wc[j], kj = cj / 10, lj = blk_sl[kj] & 1;
-            const double* nj = nrm + (lj * 10 + cj % 10) * 6;
+            const int w = Wc[j];
+            const double* nj = nrm + (w & 0xff) * 6;
+            const double* hj = HA + 6 * (w >> 8);
             double acc = 0.0;
 #pragma unroll
-            for (int c = 0; c < 6; c++) acc = fma(nj[c], HA[6 * kj + c], acc);
+            for (int c = 0; c < 6; c++) acc = fma(nj[c], hj[c], acc);
             dv[j] = acc;
           }
           __syncwarp();
@@ -783,6 +865,7 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
             yv[j] = acc;
             yy = fma(acc, acc, yy);
           }
+#pragma unroll
           for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
           __syncwarp();
           const double zn = cHc - yy;
@@ -798,12 +881,12 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
               if (ratio < t1 || (ratio == t1 && i < l1)) { t1 = ratio; l1 = i; }
             }
           }
+#pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            double ot = __shfl_xor_sync(0xffffffffu, t1, o);
-            int ol = __shfl_xor_sync(0xffffffffu, l1, o);
+            const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, l1, o);
             if (ot < t1 || (ot == t1 && ol < l1)) { t1 = ot; l1 = ol; }
           }
-          __syncwarp();
           const double t2 = dependent ? 1e300 : fmax(0.0, -sp / zn);
           const double t = fmin(t1, t2);
           int decision;  // 0 = full step (p joins W), 1 = partial step (drop l1, retry), 2 = infeasible, 3 = W full
@@ -813,59 +896,70 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
           if (decision < 2) {
             for (int i = lane; i < q; i += 32) lam[i] = fmax(0.0, lam[i] - t * rv[i]);
           }
-          __syncwarp();
           if (decision == 0) {
             // new row of the inverse factor: [-r'/rho, 1/rho], rho = sqrt(zn)
-            const double rho = sqrt(zn), irho = 1.0 / rho;
+            const double irho = rsqrt(zn);
             double* row = Li + q * (q + 1) / 2;
             for (int i = lane; i < q; i += 32) row[i] = -rv[i] * irho;
             if (lane == 0) {
               row[q] = irho;
-              Wc[q] = p;
+              Wc[q] = ws_pack(kp, nip);
               lam[q] = lam_p + t;
               act[p] = 1;
             }
           } else if (decision == 1 && lane == 0) {
             lam[q] = lam_p + t;  // pending multiplier of p, parked behind the working set
-            Wc[q] = p;
+            Wc[q] = ws_pack(kp, nip);
             flags[5] = l1;
           }
-          if (lane == 0) flags[4] = decision;
+          if (lane == 0) {
+            flags[4] = decision;
+            tstep[0] = dependent ? 0.0 : t;
+          }
         }
         __syncthreads();
         const int decision = flags[4];
-        if (decision == 0) { q++; break; }
-        if (decision == 2) { code = ST_INFEASIBLE; break; }
-        if (decision == 3) { code = ST_WS_CAP; break; }
+        if (decision >= 2) { code = (decision == 2) ? ST_INFEASIBLE : ST_WS_CAP; break; }
+        // primal step: x += t * (HA - H^-1 A_W' r)
+        {
+          const double t = tstep[0];
+          if (isvar && t != 0.0) {
+            double z = ha;
+            for (int j = 0; j < q; j++) {
+              const int w = Wc[j];
+              z = fma(-rv[j], hrow6(H, vib, vr, w >> 8, nrm + (w & 0xff) * 6), z);
+            }
+            xv[tid] = fma(t, z, xv[tid]);
+          }
+        }
+        if (decision == 0) {
+          q++;
+          __syncthreads();
+          break;
+        }
         // ---- partial step: drop working-set entry l, rebuild the inverse factor, refresh s_p ----
         {
           const int l = flags[5];
           lam_p = lam[q];
           __syncthreads();
           if (tid == 0) {
-            act[Wc[l]] = 0;
+            const int w = Wc[l];
+            act[(w >> 8) * 10 + ((w & 0xff) % 10)] = 0;
             for (int j = l; j < q; j++) { Wc[j] = Wc[j + 1]; lam[j] = lam[j + 1]; }  // includes the parked p at q
           }
           q--;
           __syncthreads();
           // rebuild Li by appending the q remaining constraints one at a time (warp 0)
-          if (tid < 32) {
-            const int lane = tid;
+          if (wid == 0) {
             for (int jn = 0; jn < q; jn++) {
-              const int cn = Wc[jn], kn = cn / 10, ln = blk_sl[kn] & 1;
-              const double* nn = nrm + (ln * 10 + cn % 10) * 6;
-              // S[jn][i] = a_n' H^-1 a_i, i <= jn
-              for (int i = lane; i <= jn; i += 32) {
-                const int ci_ = Wc[i], ki = ci_ / 10, li_ = blk_sl[ki] & 1;
-                const double* ni = nrm + (li_ * 10 + ci_ % 10) * 6;
+              const int wn = Wc[jn], kn = wn >> 8;
+              const double* nn = nrm + (wn & 0xff) * 6;
+              for (int i = lane; i <= jn; i += 32) {  // S[jn][i] = a_n' H^-1 a_i
+                const int wi = Wc[i];
+                const double* ni = nrm + (wi & 0xff) * 6;
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < 6; r++) {
-                  double hr = 0.0;
-#pragma unroll
-                  for (int c = 0; c < 6; c++) hr = fma(hsym(H, kn, r, ki, c), ni[c], hr);
-                  acc = fma(nn[r], hr, acc);
-                }
+                for (int r = 0; r < 6; r++) acc = fma(nn[r], hrow6(H, kn, r, wi >> 8, ni), acc);
                 dv[i] = acc;
               }
               __syncwarp();
@@ -877,10 +971,10 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
                 yv[j] = acc;
                 yy = fma(acc, acc, yy);
               }
+#pragma unroll
               for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
               __syncwarp();
-              const double znn = dv[jn] - yy;
-              const double irho = 1.0 / sqrt(fmax(znn, 1e-300));
+              const double irho = rsqrt(fmax(dv[jn] - yy, 1e-300));
               double* row = Li + jn * (jn + 1) / 2;
               for (int i = lane; i < jn; i += 32) {
                 double acc = 0.0;
@@ -892,28 +986,6 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
             }
           }
           __syncthreads();
-          // x with the parked multiplier of p included -> refreshed slack of p
-          for (int i = tid; i < n; i += nt) {
-            const int k = i / 6, c = i % 6, leg = blk_sl[k] & 1;
-            double acc = 0.0;
-            for (int j = 0; j <= q; j++) {
-              const int cj = Wc[j];
-              if (cj / 10 == k) acc = fma(lam[j], nrm[(leg * 10 + cj % 10) * 6 + c], acc);
-            }
-            wv[i] = acc;
-          }
-          __syncthreads();
-          for (int i = tid; i < n; i += nt) {
-            const int ibk = i / 6, r = i % 6;
-            double acc = x0[i];
-            for (int jbk = 0; jbk < NB; jbk++) {
-              const double* wj = wv + 6 * jbk;
-#pragma unroll
-              for (int c = 0; c < 6; c++) acc = fma(hsym(H, ibk, r, jbk, c), wj[c], acc);
-            }
-            xv[i] = acc;
-          }
-          __syncthreads();
           sp = -rhs[p];
 #pragma unroll
           for (int c = 0; c < 6; c++) sp = fma(np_[c], xv[6 * kp + c], sp);
@@ -921,13 +993,32 @@ __global__ void __launch_bounds__(MAXT, MINB) hmpc_solve_kernel(const KernelArgs
       }
     }
 
+    // polish: x from scratch with the final multipliers, x = x0 + sum_j lam_j H^-1 a_j
+    if (code == ST_OK && isvar) {
+      double acc = x0[tid];
+      for (int j = 0; j < q; j++) {
+        const int w = Wc[j];
+        acc = fma(lam[j], hrow6(H, vib, vr, w >> 8, nrm + (w & 0xff) * 6), acc);
+      }
+      HA[tid] = acc;
+    } else if (isvar) HA[tid] = xv[tid];
+    __syncthreads();
+
     // ---------------- stage 6: scatter (eliminated variables are exactly 0) ----------------
-    for (int e = tid; e < 12 * N; e += nt) {
+    for (int e = tid; e < 12 * N; e += NT) {
       const int s = e / 12, c12 = e % 12, leg = leg_of(c12);
       const int k = sl_blk[2 * s + leg];
-      out[e] = (k >= 0) ? (float)xv[6 * k + loc_of(c12)] : 0.f;
+      const double v = (k >= 0) ? HA[6 * k + loc_of(c12)] : 0.0;
+      if (ka.wrench) ka.wrench[(size_t)inst * 12 * N + e] = (float)v;
+      if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = (double)(float)v;
     }
-    if (tid == 0) ka.status[inst] = (code & 0xff) | ((iters & 0xfff) << 8) | ((q & 0xff) << 20);
+    if (tid == 0) {
+      if (code == ST_WS_CAP && ka.esc_list) {  // hand over to the next class (larger working-set capacity)
+        const int slot = atomicAdd(&ka.counts[ka.cls + 1], 1);
+        ka.esc_list[slot] = inst;
+      }
+      ka.status[inst] = (code & 0xff) | ((iters & 0xfff) << 8) | ((q & 0xff) << 20);
+    }
     __syncthreads();
   }
 }

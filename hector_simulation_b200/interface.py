@@ -24,7 +24,7 @@ EXPORTS = [
     "setup_problem", "get_solution", "update_solver_settings", "update_problem_data",
     "hmpc_record_bytes", "hmpc_pack_records", "hmpc_create", "hmpc_destroy", "hmpc_last_error",
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
-    "hmpc_assemble_device",
+    "hmpc_assemble_device", "hmpc_class_config",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -72,6 +72,8 @@ def lib() -> ctypes.CDLL:
         L.hmpc_assemble_device.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6
         L.hmpc_assemble_device.restype = ctypes.c_int
         L.hmpc_reference_last_status.restype = ctypes.c_int
+        L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.hmpc_class_config.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -163,6 +165,11 @@ class BatchedMPC:
     @property
     def launches_per_solve(self) -> int:
         return lib().hmpc_launches_per_solve(self._h)
+
+    def class_config(self, cls: int) -> dict:
+        out = np.zeros(6, dtype=np.int32)
+        _check(lib().hmpc_class_config(self._h, cls, out.ctypes.data))
+        return dict(zip(("threads", "smem_bytes", "qmax", "grid_cap", "nb_cap", "strip"), (int(v) for v in out)))
 
     def solve_batch(self, records: np.ndarray, strict: bool = True):
         """Host-buffer path: H2D + kernels + D2H inside.  -> (wrench [B,12N] f64, status [B] i32)."""

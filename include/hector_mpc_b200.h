@@ -144,8 +144,11 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* ctx, const struct update_data_t* in,
 HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench,
                                    int* d_status, void* stream);
 
-/* number of kernel launches hmpc_solve_device enqueues per call */
+/* number of kernel launches hmpc_solve_device enqueues per call (classification pre-pass + one per size class) */
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
+/* launch configuration of size class `cls` (0 or 1): out[0..5] = threads per CTA, dynamic shared memory bytes,
+ * working-set capacity, resident-grid cap (CTAs), max blocks of 6 variables, sweep strip width */
+HMPC_EXTERNC int hmpc_class_config(const hmpc_ctx* ctx, int cls, int* out);
 
 /* Debug/parity hook: run only the assembly stage for B packed device records and write the
  * full (un-reduced) fp32 QP data per instance: H [n*n] row-major (upper triangle valid,

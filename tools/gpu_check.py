@@ -22,6 +22,7 @@ def main():
     recs, _ = scenarios.make_batch(cfg, B, horizon=N)
     setup = O.make_setup(N)
     mpc = interface.BatchedMPC(max(B, 4096), N)
+    res["classes"] = [mpc.class_config(0), mpc.class_config(1)]
     t = time.time()
     ref, info = O.solve_batch(recs, setup)
     res["oracle_ms_per_solve"] = (time.time() - t) / B * 1e3
