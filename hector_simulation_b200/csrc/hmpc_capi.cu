@@ -56,76 +56,70 @@ struct hmpc_ctx {
 
 namespace {
 
-// kernel variants: <threads, min CTAs/SM, sweep strip width>
-//   0: <64,8,3>   1: <128,7,3>   2: <288,2,3>   3: <64,8,6>   4: <224,2,6>   5: <544,1,6>
-template <int NT, int MINB, int BW>
-cudaError_t prep_kernel(int smem, int* occ)
-{
-  auto k = hmpc::hmpc_solve_kernel<NT, MINB, BW>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, NT, smem);
-}
+// kernel variants <threads, min CTAs/SM, sweep strip width, fixed horizon (0 = runtime), size class>
+//   0/1: horizon 10 fixed at compile time (class 0 / class 1)      2: horizon-10 class 0 with 6x3 strips (experiment)
+//   3..8: runtime horizon, 64 / 224 / 544 threads for class 0 and class 1
+#define HMPC_FOR_VARIANT(V, X)                      \
+  switch (V) {                                      \
+    case 0: X(64, 8, 6, 10, 0); break;              \
+    case 1: X(224, 2, 6, 10, 1); break;             \
+    case 2: X(128, 7, 3, 10, 0); break;             \
+    case 3: X(64, 8, 6, 0, 0); break;               \
+    case 4: X(224, 2, 6, 0, 0); break;              \
+    case 5: X(544, 1, 6, 0, 0); break;              \
+    case 6: X(64, 8, 6, 0, 1); break;               \
+    case 7: X(224, 2, 6, 0, 1); break;              \
+    default: X(544, 1, 6, 0, 1); break;             \
+  }
 
 cudaError_t prep_class(ClassCfg& c, int* occ)
 {
-  switch (c.variant) {
-    case 0: return prep_kernel<64, 8, 3>(c.smem, occ);
-    case 1: return prep_kernel<128, 7, 3>(c.smem, occ);
-    case 2: return prep_kernel<288, 2, 3>(c.smem, occ);
-    case 3: return prep_kernel<64, 8, 6>(c.smem, occ);
-    case 4: return prep_kernel<224, 2, 6>(c.smem, occ);
-    default: return prep_kernel<544, 1, 6>(c.smem, occ);
+  cudaError_t e = cudaSuccess;
+#define HMPC_PREP(NT, MB, BW, NF, CL)                                                                  \
+  {                                                                                                    \
+    auto k = hmpc::hmpc_solve_kernel<NT, MB, BW, NF, CL>;                                              \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);                  \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, NT, c.smem);       \
   }
+  HMPC_FOR_VARIANT(c.variant, HMPC_PREP)
+#undef HMPC_PREP
+  return e;
 }
 
 cudaError_t launch_class(const ClassCfg& c, const hmpc::KernelArgs& ka, int grid, cudaStream_t st)
 {
-  switch (c.variant) {
-    case 0: hmpc::hmpc_solve_kernel<64, 8, 3><<<grid, 64, c.smem, st>>>(ka); break;
-    case 1: hmpc::hmpc_solve_kernel<128, 7, 3><<<grid, 128, c.smem, st>>>(ka); break;
-    case 2: hmpc::hmpc_solve_kernel<288, 2, 3><<<grid, 288, c.smem, st>>>(ka); break;
-    case 3: hmpc::hmpc_solve_kernel<64, 8, 6><<<grid, 64, c.smem, st>>>(ka); break;
-    case 4: hmpc::hmpc_solve_kernel<224, 2, 6><<<grid, 224, c.smem, st>>>(ka); break;
-    default: hmpc::hmpc_solve_kernel<544, 1, 6><<<grid, 544, c.smem, st>>>(ka); break;
-  }
+#define HMPC_LAUNCH(NT, MB, BW, NF, CL) hmpc::hmpc_solve_kernel<NT, MB, BW, NF, CL><<<grid, NT, c.smem, st>>>(ka);
+  HMPC_FOR_VARIANT(c.variant, HMPC_LAUNCH)
+#undef HMPC_LAUNCH
   return cudaGetLastError();
-}
-
-// largest working-set capacity whose solver view still fits under `limit` bytes of union
-int fit_qmax(int N, int nb_cap, int rec_stride, int want_min)
-{
-  int q = want_min;
-  const int base = hmpc::make_layout(N, nb_cap, want_min, rec_stride).total;
-  while (q < 6 * nb_cap && q < 250 && hmpc::make_layout(N, nb_cap, q + 1, rec_stride).total <= base) q++;
-  return q;
 }
 
 int build_classes(hmpc_ctx* c)
 {
   const int N = c->horizon;
-  // class 0: at most N blocks of 6 variables (e.g. any single-support schedule), 6x3 register strips;
-  // class 1: up to 2N blocks, 6x6 register blocks.  Working-set overflow in class 0 escalates to class 1.
-  const int caps[2] = {N, 2 * N};
+  // class 0: at most N blocks of 6 variables (e.g. any single-support schedule); class 1: up to 2N.
+  // Working-set overflow in class 0 escalates to class 1.
   c->ncls = 2;
+  const char* exp = getenv("HMPC_CLS0_STRIPS");  // experiment switch: 6x3 strips on 128 threads for class 0
   for (int i = 0; i < 2; i++) {
     ClassCfg& k = c->cls[i];
-    k.nb_hi = caps[i];
-    k.nb_cap = caps[i];
+    k.nb_cap = hmpc::class_nb_cap(N, i);
+    k.nb_hi = k.nb_cap;
     const int n = 6 * k.nb_cap;
     const int nbt = k.nb_cap * (k.nb_cap + 1) / 2;
-    if (i == 0) {
-      const int need = 2 * nbt > n ? 2 * nbt : n;
-      k.variant = need <= 64 ? 0 : (need <= 128 ? 1 : 2);
-      k.threads = need <= 64 ? 64 : (need <= 128 ? 128 : 288);
+    const int need = nbt > n ? nbt : n;
+    const int bucket = need <= 64 ? 0 : (need <= 224 ? 1 : 2);
+    static const int bucket_threads[3] = {64, 224, 544};
+    if (N == 10) {
+      k.variant = i;
+      k.threads = (i == 0) ? 64 : 224;
+      if (i == 0 && exp && exp[0] == '1') { k.variant = 2; k.threads = 128; }
     } else {
-      const int need = nbt > n ? nbt : n;
-      k.variant = need <= 64 ? 3 : (need <= 224 ? 4 : 5);
-      k.threads = need <= 64 ? 64 : (need <= 224 ? 224 : 544);
+      k.variant = 3 + 3 * i + bucket;
+      k.threads = bucket_threads[bucket];
     }
-    k.qmax = fit_qmax(N, k.nb_cap, c->rec_stride, n < 40 ? n : 40);
-    if (i == 1 && k.qmax < (n < 96 ? n : 96)) k.qmax = n < 96 ? n : 96;
-    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
+    k.qmax = hmpc::class_qmax(N, i);
+    k.L = hmpc::class_layout(N, i);
     k.smem = k.L.total;
     int occ = 0;
     if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (is this an sm_100a device?)")) return HMPC_ERR_CUDA;
@@ -299,7 +293,7 @@ HMPC_EXTERNC int hmpc_class_config(const hmpc_ctx* c, int cls, int* out)
   if (!c || !out || cls < 0 || cls >= c->ncls) return HMPC_ERR_ARG;
   const ClassCfg& k = c->cls[cls];
   out[0] = k.threads; out[1] = k.smem; out[2] = k.qmax; out[3] = k.grid_cap; out[4] = k.nb_cap;
-  out[5] = (k.variant < 3) ? 3 : 6;
+  out[5] = (k.variant == 2) ? 3 : 6;
   return HMPC_OK;
 }
 

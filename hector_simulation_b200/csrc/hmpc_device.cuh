@@ -42,11 +42,11 @@ struct Layout {
   int total;
 };
 
-__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+__host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
-inline Layout make_layout(int N, int nb_cap, int qmax, int rec_stride)
+__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride)
 {
-  Layout L;
+  Layout L{};
   const int nbt = nb_cap * (nb_cap + 1) / 2;
   const int n = 6 * nb_cap, m = 10 * nb_cap;
   int o = 0;
@@ -79,6 +79,27 @@ inline Layout make_layout(int N, int nb_cap, int qmax, int rec_stride)
   L.fbl = a;  a += 192 * 4;
   L.total = align16(s > a ? s : a);
   return L;
+}
+
+// packed record stride (include/hector_mpc_b200.h: hmpc_record_bytes)
+__host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12 * N) * 4 + 2 * N); }
+
+// size classes: class 0 holds at most N blocks of 6 variables, class 1 up to 2N.  The working-set capacity is
+// the largest that still fits under the assembly staging area (class 1: at least min(n, 96)).
+__host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
+__host__ __device__ constexpr int class_qmax(int N, int cls)
+{
+  const int nb = class_nb_cap(N, cls), n = 6 * nb, rs = record_stride(N);
+  int q = n < 24 ? n : 24;
+  const int base = make_layout(N, nb, q, rs).total;
+  while (q < n && q < 250 && make_layout(N, nb, q + 1, rs).total <= base) q++;
+  const int floor1 = n < 96 ? n : 96;
+  if (cls == 1 && q < floor1) q = floor1;
+  return q;
+}
+__host__ __device__ constexpr Layout class_layout(int N, int cls)
+{
+  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N));
 }
 
 struct KernelArgs {
@@ -363,29 +384,46 @@ __device__ inline void role_inertia(const float* rf, float dt, float* Bcd)
   }
 }
 
-// block argmin over (value, index) with ONE barrier: warp partials to smem, every thread folds them.
-// `red` = NW doubles followed (at +32 doubles) by NW ints.
-__device__ __forceinline__ void block_argmin(double v, int idx, double* red, int nwarps, double& vout, int& iout)
+// fast fp64 reciprocal: MUFU.RCP64H seed + Newton steps (<= 2 ulp; the sweep and ratio tests do not need
+// correctly rounded division, and the IEEE division sequence is ~6x the instructions)
+__device__ __forceinline__ double fast_rcp(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(e, r, r);
+  e = fma(-x, r, 1.0);
+  r = fma(e, r, r);
+  e = fma(-x, r, 1.0);
+  r = fma(e, r, r);
+  return r;
+}
+
+// order-preserving map float -> uint (for REDUX.MIN)
+__device__ __forceinline__ unsigned fkey(float f)
+{
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// block argmin of a float key with ONE barrier: REDUX per warp, partials to smem, every thread folds them.
+// Ties go to the smaller index.  `redk`/`redi` hold one entry per warp.
+__device__ __forceinline__ int block_argmin32(float v, int idx, unsigned* redk, int* redi, int nwarps)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, v, o);
-    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-  int* redi = reinterpret_cast<int*>(red + 32);
-  if (lane == 0) { red[wid] = v; redi[wid] = idx; }
+  const unsigned key = fkey(v);
+  const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+  const int imin = __reduce_min_sync(0xffffffffu, key == kmin ? idx : 0x7fffffff);
+  if (lane == 0) { redk[wid] = kmin; redi[wid] = imin; }
   __syncthreads();
-  v = red[0];
-  idx = redi[0];
+  unsigned k = redk[0];
+  int i = redi[0];
   for (int w = 1; w < nwarps; w++) {
-    const double ov = red[w];
+    const unsigned ok = redk[w];
     const int oi = redi[w];
-    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    if (ok < k || (ok == k && oi < i)) { k = ok; i = oi; }
   }
-  vout = v;
-  iout = idx;
+  return i;
 }
 
 // working-set entry: block index in the high bits, normal index (leg*10+type) in the low byte
@@ -411,9 +449,11 @@ __global__ void hmpc_classify_kernel(const unsigned char* records, int rec_strid
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel.  NT threads, BW = columns of the 6xBW register block each thread sweeps (3 or 6)
+// the kernel.  NT threads; BW = columns of the 6xBW register block each thread sweeps (3 or 6);
+// NF > 0 fixes the horizon at compile time (layout offsets and loop bounds fold), NF == 0 reads it from
+// the arguments; CLS = size class (capacity N or 2N blocks of 6 variables).
 // ------------------------------------------------------------------------------------------------
-template <int NT, int MINB, int BW>
+template <int NT, int MINB, int BW, int NF, int CLS>
 __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs ka)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -421,8 +461,18 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   const int lane = tid & 31, wid = tid >> 5;
   constexpr int NW = NT / 32;
   constexpr int HPB = 6 / BW;  // threads per 6x6 block
-  const int N = ka.horizon;
-  const Layout& L = ka.L;
+  constexpr bool FIX = NF > 0;
+  const int N = FIX ? NF : ka.horizon;
+  const int nb_cap = FIX ? class_nb_cap(NF, CLS) : ka.nb_cap;
+  const int qmax = FIX ? class_qmax(NF > 0 ? NF : 1, CLS) : ka.qmax;
+  const int rec_stride = FIX ? record_stride(NF) : ka.rec_stride;
+  Layout L;
+  if constexpr (FIX) {
+    constexpr Layout LC = class_layout(NF, CLS);
+    L = LC;
+  } else {
+    L = ka.L;
+  }
   const bool dump = (ka.dbg_H != nullptr);
 
   double* H = reinterpret_cast<double*>(smem + L.H);
@@ -433,9 +483,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   double* nrm = reinterpret_cast<double*>(smem + L.nrm);  // [leg*10+type][6]
   double* rhs = reinterpret_cast<double*>(smem + L.rhs);  // [block*10 + type]
   int* blk_sl = reinterpret_cast<int*>(smem + L.blk);     // block -> step*2+leg
-  int* sl_blk = blk_sl + ka.nb_cap;                       // step*2+leg -> block or -1
-  double* red = reinterpret_cast<double*>(smem + L.misc);    // 32 doubles + 32 ints of reduction scratch
-  int* flags = reinterpret_cast<int*>(smem + L.misc + 384);  // [0]=NB [1]=stance0 [2]=stance1 [3]=code [4]=decision [5]=drop
+  int* sl_blk = blk_sl + nb_cap;                          // step*2+leg -> block or -1
+  unsigned* redk = reinterpret_cast<unsigned*>(smem + L.misc);   // [32] warp partial keys
+  int* redi = reinterpret_cast<int*>(smem + L.misc + 128);       // [32] warp partial indices
+  int* flags = reinterpret_cast<int*>(smem + L.misc + 384);  // [0]=NB [1]=stance0 [2]=stance1 [3]=code [4]=decision [5]=drop [6]=ncomb
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.misc + 448);
   double* enext = reinterpret_cast<double*>(smem + L.misc + 464);  // [2] next-pivot diagonal, double-buffered
   double* tstep = reinterpret_cast<double*>(smem + L.misc + 480);  // [1] step length of the current GI iteration
@@ -454,9 +505,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   float* Acd = reinterpret_cast<float*>(smem + L.Acd);
   float* Bcd = reinterpret_cast<float*>(smem + L.Bcd);
   float* Pbuf = reinterpret_cast<float*>(smem + L.P);  // two 13x13 buffers, 172 floats apart
-  float* Mb = reinterpret_cast<float*>(smem + L.M);    // [N][12][12] rows 0..11 of P_d * Bcd
+  float* Mb = reinterpret_cast<float*>(smem + L.M);    // [N][12][12]: rows 0..11 of P_d*Bcd, columns grouped by leg
   float* dd = reinterpret_cast<float*>(smem + L.dd);   // [N][12]
   float* Fblk = reinterpret_cast<float*>(smem + L.fbl);
+  int* comb = reinterpret_cast<int*>(smem + L.HA);     // stage-3 work list (HA is free until the sweep)
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -471,8 +523,8 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // ---------------- stage 0: record -> shared memory (TMA bulk copy) ----------------
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the union
-      mbar_expect_tx(bar, (uint32_t)ka.rec_stride);
-      bulk_g2s(rec, ka.records + (size_t)inst * ka.rec_stride, (uint32_t)ka.rec_stride, bar);
+      mbar_expect_tx(bar, (uint32_t)rec_stride);
+      bulk_g2s(rec, ka.records + (size_t)inst * rec_stride, (uint32_t)rec_stride, bar);
     }
     // meanwhile: zero the sparse fp32 operands, P_0 = I
     for (int e = tid; e < 169; e += NT) { Acd[e] = 0.f; Pbuf[e] = (e / 13 == e % 13) ? 1.f : 0.f; }
@@ -492,19 +544,34 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const unsigned mask = __ballot_sync(0xffffffffu, stance);
       const int k = __popc(mask & ((1u << lane) - 1u));
       if (lane < 2 * N) {
-        sl_blk[lane] = (stance && k < ka.nb_cap) ? k : -1;
-        if (stance && k < ka.nb_cap) blk_sl[k] = lane;
+        sl_blk[lane] = (stance && k < nb_cap) ? k : -1;
+        if (stance && k < nb_cap) blk_sl[k] = lane;
+      }
+      unsigned st0 = 0, st1 = 0;
+      for (int s = 0; s < N; s++) {
+        st0 |= ((mask >> (2 * s)) & 1u) << s;
+        st1 |= ((mask >> (2 * s + 1)) & 1u) << s;
+      }
+      // stage-3 work list: (li, lj, delta) combinations that own at least one wanted H block
+      int ncomb = 0;
+      for (int base = 0; base < 4 * N; base += 32) {
+        const int c = base + lane;
+        const int li = (c / N) >> 1, lj = (c / N) & 1, delta = c % N;
+        unsigned need = 0;
+        if (c < 4 * N) need = (li ? st1 : st0) & ((lj ? st1 : st0) >> delta);
+        const unsigned has = __ballot_sync(0xffffffffu, need != 0);
+        if (need) {
+          const int kmax = N - 1 - delta - (__ffs(need) - 1);
+          comb[ncomb + __popc(has & ((1u << lane) - 1u))] = li | (lj << 1) | (delta << 2) | (kmax << 8);
+        }
+        ncomb += __popc(has);
       }
       if (lane == 0) {
-        unsigned st0 = 0, st1 = 0;
-        for (int s = 0; s < N; s++) {
-          st0 |= ((mask >> (2 * s)) & 1u) << s;
-          st1 |= ((mask >> (2 * s + 1)) & 1u) << s;
-        }
         flags[0] = __popc(mask);
         flags[1] = (int)st0;
         flags[2] = (int)st1;
         flags[3] = ST_OK;
+        flags[6] = ncomb;
       }
     }
     __syncthreads();
@@ -542,7 +609,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
 
     // ---------------- stage 2: powers of Acd, Toeplitz blocks, d = A_qp x0 - X_d ----------------
-    // pass k has P_k in Pc: writes P_{k+1}, M_k = P_k*Bcd (rows 0..11) and d_{k-1} = P_k x0 - traj_{k-1}
+    // pass k has P_k in Pc: writes P_{k+1}, M_k = P_k*Bcd (rows 0..11) and d_{k-1} = P_k x0 - traj_{k-1}.
+    // Structural zeros of Acd = I + dt*A and of Bcd (rows 0..5, 12) are skipped: every skipped term is an exact
+    // zero product added to the running sum, so the values equal the reference's dense sequential sums.
     for (int k = 0; k <= N; k++) {
       const float* Pc = Pbuf + (k & 1) * 172;
       float* Pn = Pbuf + ((k + 1) & 1) * 172;
@@ -550,18 +619,24 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (e < 169) {
           if (k < N) {
             const int i = e / 13, j = e % 13;
-            float acc = FM(Pc[i * 13], Acd[j]);
-#pragma unroll
-            for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pc[i * 13 + t], Acd[t * 13 + j]));
+            float acc;
+            if (j < 6) acc = Pc[e];
+            else if (j < 9) {
+              acc = FM(Pc[i * 13], Acd[j]);
+              acc = FA(acc, FM(Pc[i * 13 + 1], Acd[13 + j]));
+              acc = FA(acc, FM(Pc[i * 13 + 2], Acd[26 + j]));
+              acc = FA(acc, Pc[e]);
+            } else if (j < 12) acc = FA(FM(Pc[i * 13 + j - 6], Acd[(j - 6) * 13 + j]), Pc[e]);
+            else acc = FA(FM(Pc[i * 13 + 11], Acd[11 * 13 + 12]), Pc[e]);
             Pn[e] = acc;
           }
         } else if (e < 169 + 144) {
           if (k < N) {
             const int r = (e - 169) / 12, c = (e - 169) % 12;
-            float acc = FM(Pc[r * 13], Bcd[c]);
+            float acc = FM(Pc[r * 13 + 6], Bcd[6 * 12 + c]);
 #pragma unroll
-            for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pc[r * 13 + t], Bcd[t * 12 + c]));
-            Mb[k * 144 + r * 12 + c] = acc;
+            for (int t = 7; t < 12; t++) acc = FA(acc, FM(Pc[r * 13 + t], Bcd[t * 12 + c]));
+            Mb[k * 144 + r * 12 + leg_of(c) * 6 + loc_of(c)] = acc;
           }
         } else if (k >= 1) {
           const int r = e - 169 - 144, s = k - 1;
@@ -574,7 +649,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       __syncthreads();
     }
 
-    // ---------------- stage 3: Hessian prefix chains (4 columns per item) + gradient ----------------
+    // ---------------- stage 3: Hessian prefix chains (one 1x6 leg tile per item) + gradient ----------------
     if (dump) {
       float* oF = ka.dbg_F + (size_t)inst * 192;
       for (int e = tid; e < 192; e += NT) oF[e] = Fblk[e];
@@ -595,49 +670,45 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       float wr[12];
 #pragma unroll
       for (int r = 0; r < 12; r++) wr[r] = rf[30 + r];
-      // item = (delta, ii, jq): running sums G_delta(K)[ii][4jq..4jq+3] = sum_{e<=K} T_{e+delta}^T M_e;
+      // item = (li, lj, delta, i): running sums G_delta(K)[i][leg lj's six columns] = sum_{e<=K} T_{e+delta}^T M_e;
       // block (a,b) of B'SB, b - a = delta, equals G_delta(N-1-b) — the oracle's own summation order.
-      for (int it = tid; it < N * 36; it += NT) {
-        const int delta = it / 36, ii = (it % 36) / 3, jq = it % 3;
-        const int li = leg_of(ii);
-        unsigned need[4];
-        unsigned any = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int jj = 4 * jq + c;
-          need[c] = (delta == 0 && ii > jj) ? 0u : (stmask[li] & (stmask[leg_of(jj)] >> delta));
-          any |= need[c];
-        }
-        if (!any) continue;
-        const int Kmax = N - 1 - delta - (__ffs(any) - 1);
-        const int ci = loc_of(ii);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int nitems = flags[6] * 6;
+      for (int rd = 0; rd * NT < nitems; rd++) {
+        const int it = rd * NT + ((rd & 1) ? (NT - 1 - tid) : tid);  // serpentine: long and short chains pair up
+        if (it >= nitems) continue;
+        const int cm = comb[it / 6], ci = it % 6;
+        const int li = cm & 1, lj = (cm >> 1) & 1, delta = (cm >> 2) & 63, Kmax = cm >> 8;
+        const unsigned need = stmask[li] & (stmask[lj] >> delta);  // bit a: block (a, a+delta) wanted
+        const int ii = col12_of(li, ci);
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int K = 0; K <= Kmax; K++) {
-          const float* Mi = Mb + (K + delta) * 144 + ii;
-          const float4* Mj = reinterpret_cast<const float4*>(Mb + K * 144 + 4 * jq);
+          const float* Mi = Mb + (K + delta) * 144 + 6 * li + ci;
+          const float2* Mj = reinterpret_cast<const float2*>(Mb + K * 144 + 6 * lj);
 #pragma unroll
           for (int r = 0; r < 12; r++) {
             const float tv = FM(Mi[r * 12], wr[r]);  // (B'S)(i,k) = B(k,i)*w(k)
-            const float4 mj = Mj[r * 3];
-            acc[0] = FA(acc[0], FM(tv, mj.x));
-            acc[1] = FA(acc[1], FM(tv, mj.y));
-            acc[2] = FA(acc[2], FM(tv, mj.z));
-            acc[3] = FA(acc[3], FM(tv, mj.w));
+            const float2 m0 = Mj[r * 6], m1 = Mj[r * 6 + 1], m2 = Mj[r * 6 + 2];
+            acc[0] = FA(acc[0], FM(tv, m0.x));
+            acc[1] = FA(acc[1], FM(tv, m0.y));
+            acc[2] = FA(acc[2], FM(tv, m1.x));
+            acc[3] = FA(acc[3], FM(tv, m1.y));
+            acc[4] = FA(acc[4], FM(tv, m2.x));
+            acc[5] = FA(acc[5], FM(tv, m2.y));
           }
           const int a = N - 1 - K - delta, b = a + delta;
-          if ((any >> a) & 1u) {
+          if ((need >> a) & 1u) {
+            const int ka_ = dump ? 0 : sl_blk[2 * a + li], kb_ = dump ? 0 : sl_blk[2 * b + lj];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-              if (!((need[c] >> a) & 1u)) continue;
-              const int jj = 4 * jq + c;
+            for (int cj = 0; cj < 6; cj++) {
+              const int jj = col12_of(lj, cj);
+              if (delta == 0 && ii > jj) continue;  // the reference's solver reads the upper triangle only
               const float alpha = (delta == 0 && ii == jj) ? rf[42 + ii] : 0.f;
-              const float hv = FM(2.f, FA(acc[c], alpha));  // qH = 2*(B'SB + Alpha_rep)
+              const float hv = FM(2.f, FA(acc[cj], alpha));  // qH = 2*(B'SB + Alpha_rep)
               if (dump) {
                 float* oH = ka.dbg_H + (size_t)inst * (144 * N * N);
                 oH[(size_t)(12 * a + ii) * (12 * N) + 12 * b + jj] = hv;
                 oH[(size_t)(12 * b + jj) * (12 * N) + 12 * a + ii] = hv;
               } else {
-                const int ka_ = sl_blk[2 * a + li], kb_ = sl_blk[2 * b + leg_of(jj)], cj = loc_of(jj);
                 const double hd = (double)hv;
                 if (ka_ == kb_) {
                   H[blk_off(ka_, ka_) + ci * 6 + cj] = hd;
@@ -655,7 +726,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (!((stmask[li] >> a) & 1u)) continue;
         float acc = 0.f;
         for (int s = a; s < N; s++) {
-          const float* Mi = Mb + (s - a) * 144 + ii;
+          const float* Mi = Mb + (s - a) * 144 + 6 * li + loc_of(ii);
           const float* dk = dd + 12 * s;
 #pragma unroll
           for (int r = 0; r < 12; r++) acc = FA(acc, FM(FM(FM(Mi[r * 12], wr[r]), 2.f), dk[r]));
@@ -681,9 +752,11 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // After sweeping every pivot the matrix holds -H^-1 (Goodnight's sweep operator on an SPD matrix).
     // Per pivot: ONE barrier.  The pivot column k+1 and the current value of diagonal k+2 are published
     // during step k, and every thread predicts pivot k+1's reciprocal while it applies step k.
+    // The pivot row/column come out of the generic rank-1 update by biasing the column entries at k:
+    //   row factor d-1 instead of d, column factor 1-1/d instead of 1, and (k,k) corrected by -2.
     {
       const int nbt = NB * (NB + 1) / 2;
-      const int bt = tid / HPB, hh = tid % HPB;  // block id, half
+      const int bt = tid / HPB, hh = tid % HPB;  // block id, strip
       const bool own = bt < nbt;
       int ib = 0, jb = 0;
       if (own) {
@@ -711,51 +784,49 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (ib == 0 && jb == 0 && hh == 1 / BW) enext[0] = a[1][1 % BW];
       }
       __syncthreads();
-      double inv = 1.0 / colbuf[0][0];
+      double inv = fast_rcp(colbuf[0][0]);
       bool bad = !(colbuf[0][0] > 0.0);
+      const double* rowp = colbuf[0] + 6 * ib;        // this thread's six row entries of the pivot column
+      const double* colp = colbuf[0] + 6 * jb + c0;   // and its BW column entries
+      const int boff = (int)(colbuf[1] - colbuf[0]);
       for (int kb = 0; kb < NB; kb++) {
+        const bool rowk = own && (ib == kb), colk = own && (jb == kb);
 #pragma unroll
         for (int kk = 0; kk < 6; kk++) {
           const int k = 6 * kb + kk;
-          const double* col = colbuf[kk & 1];
-          double* coln = colbuf[(kk + 1) & 1];
+          const int cur = (kk & 1) ? boff : 0, nxt = (kk & 1) ? 0 : boff;
           double invn = 0.0;
           if (k + 1 < n) {  // reciprocal of the next pivot, overlapped with this step's updates
-            const double cn = col[k + 1];
+            const double cn = colbuf[0][cur + k + 1];
             const double dn = fma(-cn, cn * inv, enext[kk & 1]);
             bad |= !(dn > 0.0);
-            invn = 1.0 / dn;
+            invn = fast_rcp(dn);
           }
           if (own) {
             double ci[6], cj[BW];
 #pragma unroll
-            for (int r = 0; r < 6; r++) ci[r] = col[6 * ib + r];
+            for (int r = 0; r < 6; r++) ci[r] = rowp[cur + r];
 #pragma unroll
-            for (int c = 0; c < BW; c++) cj[c] = col[6 * jb + c0 + c] * inv;
+            for (int c = 0; c < BW; c++) cj[c] = colp[cur + c] * inv;
+            if (rowk) ci[kk] -= 1.0;
+            if (colk && hh == kk / BW) cj[kk % BW] = 1.0 - inv;
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
               for (int c = 0; c < BW; c++) a[r][c] = fma(-ci[r], cj[c], a[r][c]);
-            if (jb == kb && hh == kk / BW) {
-#pragma unroll
-              for (int r = 0; r < 6; r++) a[r][kk % BW] = ci[r] * inv;
-            }
-            if (ib == kb) {
-#pragma unroll
-              for (int c = 0; c < BW; c++) a[kk][c] = cj[c];
-              if (jb == kb && hh == kk / BW) a[kk][kk % BW] = -inv;
-            }
+            if (rowk && colk && hh == kk / BW) a[kk][kk % BW] -= 2.0;
             // publish column k+1 (and diagonal k+2) for the next step
+            double* coln = colbuf[0] + nxt;
             if (kk < 5) {
-              if (jb == kb && hh == (kk + 1) / BW) {
+              if (colk && hh == (kk + 1) / BW) {
 #pragma unroll
                 for (int r = 0; r < 6; r++) coln[6 * ib + r] = a[r][(kk + 1) % BW];
-              } else if (ib == kb && jb < kb) {
+              } else if (rowk && jb < kb) {
 #pragma unroll
                 for (int c = 0; c < BW; c++) coln[6 * jb + c0 + c] = a[kk + 1][c];
               }
               if (kk < 4) {
-                if (ib == kb && jb == kb && hh == (kk + 2) / BW) enext[(kk + 1) & 1] = a[kk + 2][(kk + 2) % BW];
+                if (rowk && colk && hh == (kk + 2) / BW) enext[(kk + 1) & 1] = a[kk + 2][(kk + 2) % BW];
               } else {
                 if (ib == kb + 1 && jb == kb + 1 && hh == 0) enext[(kk + 1) & 1] = a[0][0];
               }
@@ -786,33 +857,29 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
 
     // ---------------- stage 5: dual active-set iterations ----------------
-    // per-thread constants: one variable (row of H^-1) and up to CPT constraints
+    // per-thread constants: one variable (row of H^-1)
     const bool isvar = tid < n;
     const int vib = tid / 6, vr = tid % 6;
+    double mx = 0.0;
     if (isvar) {  // x0 = -H^-1 g
       double acc = 0.0;
       for (int jbk = 0; jbk < NB; jbk++) acc += hrow6(H, vib, vr, jbk, gq + 6 * jbk);
       x0[tid] = -acc;
       xv[tid] = -acc;
+      mx = fabs(acc);
     }
     for (int e = tid; e < m; e += NT) act[e] = 0;
-    __syncthreads();
+    // tolerance scale: max |x0| (float ordering is enough)
+    const int imx = block_argmin32(-(float)mx, tid, redk, redi, NW);
+    const double tol = 1e-9 * fmax(1.0, fabs(x0[imx < n ? imx : 0]));
+    __syncthreads();  // x0/xv/act visible; redk/redi reusable
 
     int q = 0, iters = 0;
     int code = flags[3];
-    double tol;
-    {
-      double mx = 0.0;
-      for (int i = tid; i < n; i += NT) mx = fmax(mx, fabs(x0[i]));
-      int dummy;
-      block_argmin(-mx, tid, red, NW, mx, dummy);
-      tol = 1e-9 * fmax(1.0, -mx);
-      __syncthreads();  // red is reused by the first argmin below
-    }
 
     while (code == ST_OK) {
-      // most violated inactive constraint (slacks straight from x)
-      double sbest = 1e300;
+      // most violated inactive constraint (slacks straight from x; selection in float, value in double)
+      float sbest = 3.0e38f;
       int pbest = 0x7fffffff;
       for (int e = tid; e < m; e += NT) {
         if (act[e]) continue;
@@ -822,16 +889,19 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         double s = -rhs[e];
 #pragma unroll
         for (int c = 0; c < 6; c++) s = fma(nn[c], xb[c], s);
-        if (s < sbest) { sbest = s; pbest = e; }
+        const float sf = (float)s;
+        if (sf < sbest) { sbest = sf; pbest = e; }
       }
-      double sp;
-      int p;
-      block_argmin(sbest, pbest, red, NW, sp, p);
+      const int p = block_argmin32(sbest, pbest, redk, redi, NW);
+      if (p == 0x7fffffff) break;  // every row is in the working set
+      const int kp = p / 10, nip = (blk_sl[kp] & 1) * 10 + (p - 10 * kp);
+      const double* np_ = nrm + nip * 6;
+      double sp = -rhs[p];
+#pragma unroll
+      for (int c = 0; c < 6; c++) sp = fma(np_[c], xv[6 * kp + c], sp);
       if (!(sp < -tol)) break;  // KKT point reached
 
       // ---- add constraint p (possibly after dropping blocking ones) ----
-      const int kp = p / 10, nip = (blk_sl[kp] & 1) * 10 + (p - 10 * kp);
-      const double* np_ = nrm + nip * 6;
       double lam_p = 0.0;
       while (true) {
         iters++;
@@ -877,7 +947,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             for (int j = i; j < q; j++) acc = fma(Li[j * (j + 1) / 2 + i], yv[j], acc);
             rv[i] = acc;
             if (acc > 0.0) {
-              const double ratio = lam[i] / acc;
+              const double ratio = lam[i] * fast_rcp(acc);
               if (ratio < t1 || (ratio == t1 && i < l1)) { t1 = ratio; l1 = i; }
             }
           }
@@ -887,11 +957,11 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             const int ol = __shfl_xor_sync(0xffffffffu, l1, o);
             if (ot < t1 || (ot == t1 && ol < l1)) { t1 = ot; l1 = ol; }
           }
-          const double t2 = dependent ? 1e300 : fmax(0.0, -sp / zn);
+          const double t2 = dependent ? 1e300 : fmax(0.0, -sp * fast_rcp(zn));
           const double t = fmin(t1, t2);
           int decision;  // 0 = full step (p joins W), 1 = partial step (drop l1, retry), 2 = infeasible, 3 = W full
           if (!(t < 1e299)) decision = 2;
-          else if (t2 <= t1) decision = (q >= ka.qmax) ? 3 : 0;
+          else if (t2 <= t1) decision = (q >= qmax) ? 3 : 0;
           else decision = 1;
           if (decision < 2) {
             for (int i = lane; i < q; i += 32) lam[i] = fmax(0.0, lam[i] - t * rv[i]);

@@ -1,6 +1,6 @@
 """Correlate an .ncu-rep's per-SASS-instruction samples with CUDA source lines.
 
-    python tools/ncu_lines.py gpurun_out/prof.ncu-rep 'hmpc_solve_kernel<(int)64' [top_n]
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep 'hmpc_solve_kernel<(int)128' [top_n] [mangled-substring e.g. ILi128E]
 
 ncu's CLI source page carries no line column, so the kernel's cubin is disassembled with
 `nvdisasm --print-line-info` and zipped with the SASS rows by instruction order.
@@ -59,8 +59,7 @@ def line_table(lib, mangled_substr):
 def main():
     rep, ksub = sys.argv[1], sys.argv[2]
     topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    mang = {"64": "ILi64E", "224": "ILi224E", "544": "ILi544E"}
-    msub = next((v for k, v in mang.items() if f"(int){k}" in ksub or f"<{k}" in ksub), "hmpc_solve_kernel")
+    msub = sys.argv[4] if len(sys.argv) > 4 else "hmpc_solve_kernel"  # substring of the mangled name, e.g. ILi128ELi7ELi3E
     rows = sass_rows(rep, ksub)
     lt = line_table(os.path.join(ROOT, "hector_simulation_b200", "libhector_mpc_b200.so"), msub)
     if len(rows) == 2 * len(lt):  # ncu prints the listing twice
