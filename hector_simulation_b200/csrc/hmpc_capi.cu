@@ -255,6 +255,7 @@ HMPC_EXTERNC int hmpc_set_problem(hmpc_ctx* c, const problem_setup* s)
 }
 
 namespace {
+long long* g_dbg_clk = nullptr;  // profiling hook (hmpc_debug_set_clock_buffer)
 // classification pre-pass + one launch per class, all enqueued on `st`
 int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, double* d_wrench64, int* d_status,
                   cudaStream_t st)
@@ -277,12 +278,16 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     ka.nb_cap = k.nb_cap;
     ka.qmax = k.qmax;
     ka.L = k.L;
+    ka.dbg_clk = g_dbg_clk;
     const int grid = B < k.grid_cap ? B : k.grid_cap;
     CK(launch_class(k, ka, grid, st));
   }
   return HMPC_OK;
 }
 }  // namespace
+
+// profiling hook: device buffer [batch][8] of clock64() stage timestamps, or NULL to switch off
+HMPC_EXTERNC void hmpc_debug_set_clock_buffer(long long* d_buf) { g_dbg_clk = d_buf; }
 
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls + 1 : 0; }
 

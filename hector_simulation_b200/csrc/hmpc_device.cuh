@@ -125,6 +125,7 @@ struct KernelArgs {
   float* dbg_F;                  // [batch][192]
   float* dbg_lb;                 // [batch][16N]
   float* dbg_ub;                 // [batch][16N]
+  long long* dbg_clk;            // [batch][8] stage timestamps (clock64), profiling hook; null in production
   Layout L;
 };
 
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
 
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int inst = ka.list ? ka.list[idx] : idx;
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 0] = clock64();
     // ---------------- stage 0: record -> shared memory (TMA bulk copy) ----------------
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the union
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       bulk_g2s(rec, ka.records + (size_t)inst * rec_stride, (uint32_t)rec_stride, bar);
     }
     // meanwhile: zero the sparse fp32 operands, P_0 = I
-    for (int e = tid; e < 169; e += NT) { Acd[e] = 0.f; Pbuf[e] = (e / 13 == e % 13) ? 1.f : 0.f; }
+    for (int e = tid; e < 169; e += NT) Acd[e] = 0.f;
     for (int e = tid; e < 156; e += NT) Bcd[e] = 0.f;
     for (int e = tid; e < 192; e += NT) Fblk[e] = 0.f;
     mbar_wait(bar, phase);
@@ -608,47 +610,59 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       }
     }
 
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 1] = clock64();
     // ---------------- stage 2: powers of Acd, Toeplitz blocks, d = A_qp x0 - X_d ----------------
-    // pass k has P_k in Pc: writes P_{k+1}, M_k = P_k*Bcd (rows 0..11) and d_{k-1} = P_k x0 - traj_{k-1}.
-    // Structural zeros of Acd = I + dt*A and of Bcd (rows 0..5, 12) are skipped: every skipped term is an exact
-    // zero product added to the running sum, so the values equal the reference's dense sequential sums.
-    for (int k = 0; k <= N; k++) {
-      const float* Pc = Pbuf + (k & 1) * 172;
-      float* Pn = Pbuf + ((k + 1) & 1) * 172;
-      for (int e = tid; e < 169 + 144 + 12; e += NT) {
-        if (e < 169) {
-          if (k < N) {
-            const int i = e / 13, j = e % 13;
-            float acc;
-            if (j < 6) acc = Pc[e];
-            else if (j < 9) {
-              acc = FM(Pc[i * 13], Acd[j]);
-              acc = FA(acc, FM(Pc[i * 13 + 1], Acd[13 + j]));
-              acc = FA(acc, FM(Pc[i * 13 + 2], Acd[26 + j]));
-              acc = FA(acc, Pc[e]);
-            } else if (j < 12) acc = FA(FM(Pc[i * 13 + j - 6], Acd[(j - 6) * 13 + j]), Pc[e]);
-            else acc = FA(FM(Pc[i * 13 + 11], Acd[11 * 13 + 12]), Pc[e]);
-            Pn[e] = acc;
-          }
-        } else if (e < 169 + 144) {
-          if (k < N) {
-            const int r = (e - 169) / 12, c = (e - 169) % 12;
-            float acc = FM(Pc[r * 13 + 6], Bcd[6 * 12 + c]);
-#pragma unroll
-            for (int t = 7; t < 12; t++) acc = FA(acc, FM(Pc[r * 13 + t], Bcd[t * 12 + c]));
-            Mb[k * 144 + r * 12 + leg_of(c) * 6 + loc_of(c)] = acc;
-          }
-        } else if (k >= 1) {
-          const int r = e - 169 - 144, s = k - 1;
-          float acc = FM(Pc[r * 13], x0f[0]);
-#pragma unroll
-          for (int t = 1; t < 13; t++) acc = FA(acc, FM(Pc[r * 13 + t], x0f[t]));
-          dd[12 * s + r] = FS(acc, rf[54 + 12 * s + r]);
-        }
+    // Acd = I + dt*A has the SRBD pattern (SolverMPC.cpp:312-318): Rb block (rows 0-2, cols 6-8), dt on
+    // (3+c, 9+c) and -dt on (11,12).  Its powers P_k therefore differ from the identity in 14 entries only,
+    //   P_k[0:3][6:9]  (k-fold rounded accumulation of dt*Rb),  P_k[3+c][9+c],  P_k[5][12],  P_k[11][12],
+    // and the reference's dense sequential products reduce to the few terms below — every dropped term is an
+    // exact zero product, so the values are those of the dense sums (SolverMPC.cpp:148-177).
+    // Pk[k][0..8] = P_k[0:3][6:9], [9..11] = P_k[3+c][9+c], [12] = P_k[5][12], [13] = P_k[11][12]
+    float* Pk = Pbuf;  // (N+1) x 16 floats fit in the two 13x13 buffers
+    if (wid == 0) {
+      float v = 0.f;
+      if (lane < 16) Pk[lane] = 0.f;
+      for (int k = 0; k < N; k++) {
+        // lane 12 needs P_k[5][11] = Pk[k][11] before it is advanced: every lane reads its inputs first
+        const float pd2 = __shfl_sync(0xffffffffu, v, 11);
+        if (lane < 9) v = FA(Acd[(lane / 3) * 13 + 6 + lane % 3], v);
+        else if (lane < 12) v = FA(Acd[(lane - 6) * 13 + lane], v);
+        else if (lane == 12) v = FA(FM(pd2, Acd[11 * 13 + 12]), v);
+        else if (lane == 13) v = FA(Acd[11 * 13 + 12], v);
+        if (lane < 14) Pk[(k + 1) * 16 + lane] = v;
       }
-      __syncthreads();
     }
+    __syncthreads();
+    // M_k = P_k*Bcd rows 0..11 (columns regrouped by leg), d_s = P_{s+1} x0 - traj_s
+    for (int e = tid; e < N * 144; e += NT) {
+      const int k = e / 144, r = (e % 144) / 12, c = e % 12;
+      const float* pk = Pk + k * 16;
+      float acc;
+      if (r < 3) {
+        acc = FM(pk[r * 3], Bcd[6 * 12 + c]);
+        acc = FA(acc, FM(pk[r * 3 + 1], Bcd[7 * 12 + c]));
+        acc = FA(acc, FM(pk[r * 3 + 2], Bcd[8 * 12 + c]));
+      } else if (r < 6) acc = FM(pk[9 + r - 3], Bcd[(r + 6) * 12 + c]);
+      else acc = Bcd[r * 12 + c];
+      Mb[k * 144 + r * 12 + leg_of(c) * 6 + loc_of(c)] = acc;
+    }
+    for (int e = tid; e < N * 12; e += NT) {
+      const int s = e / 12, r = e % 12;
+      const float* pk = Pk + (s + 1) * 16;
+      float acc = x0f[r];
+      if (r < 3) {
+        acc = FA(acc, FM(pk[r * 3], x0f[6]));
+        acc = FA(acc, FM(pk[r * 3 + 1], x0f[7]));
+        acc = FA(acc, FM(pk[r * 3 + 2], x0f[8]));
+      } else if (r < 6) {
+        acc = FA(acc, FM(pk[9 + r - 3], x0f[r + 6]));
+        if (r == 5) acc = FA(acc, FM(pk[12], x0f[12]));
+      } else if (r == 11) acc = FA(acc, FM(pk[13], x0f[12]));
+      dd[e] = FS(acc, rf[54 + e]);
+    }
+    __syncthreads();
 
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 2] = clock64();
     // ---------------- stage 3: Hessian prefix chains (one 1x6 leg tile per item) + gradient ----------------
     if (dump) {
       float* oF = ka.dbg_F + (size_t)inst * 192;
@@ -681,11 +695,24 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const unsigned need = stmask[li] & (stmask[lj] >> delta);  // bit a: block (a, a+delta) wanted
         const int ii = col12_of(li, ci);
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // rows 6..8 of every M_e equal Bcd's (k-independent): their products are loop invariants.
+        // rows 3..5 / 9..11 hold one force axis each: they only couple force variables of the same axis.
+        float prod[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const float tv = FM(Bcd[(6 + r) * 12 + ii], wr[6 + r]);
+#pragma unroll
+          for (int c = 0; c < 6; c++) prod[r][c] = FM(tv, Bcd[(6 + r) * 12 + col12_of(lj, c)]);
+        }
+        const bool fax = ci < 3;
+        const int rax = fax ? ci : 0;
+        const float w3 = rf[30 + 3 + rax];
+        const float prod9 = FM(FM(Bcd[(9 + rax) * 12 + ii], rf[30 + 9 + rax]), Bcd[(9 + rax) * 12 + col12_of(lj, rax)]);
         for (int K = 0; K <= Kmax; K++) {
           const float* Mi = Mb + (K + delta) * 144 + 6 * li + ci;
           const float2* Mj = reinterpret_cast<const float2*>(Mb + K * 144 + 6 * lj);
 #pragma unroll
-          for (int r = 0; r < 12; r++) {
+          for (int r = 0; r < 3; r++) {
             const float tv = FM(Mi[r * 12], wr[r]);  // (B'S)(i,k) = B(k,i)*w(k)
             const float2 m0 = Mj[r * 6], m1 = Mj[r * 6 + 1], m2 = Mj[r * 6 + 2];
             acc[0] = FA(acc[0], FM(tv, m0.x));
@@ -694,6 +721,19 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             acc[3] = FA(acc[3], FM(tv, m1.y));
             acc[4] = FA(acc[4], FM(tv, m2.x));
             acc[5] = FA(acc[5], FM(tv, m2.y));
+          }
+          if (fax) {  // row 3+axis
+            const float t3 = FM(FM(Mi[(3 + rax) * 12], w3), Mb[K * 144 + (3 + rax) * 12 + 6 * lj + rax]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] = (c == rax) ? FA(acc[c], t3) : acc[c];
+          }
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[c] = FA(acc[c], prod[r][c]);
+          if (fax) {  // row 9+axis
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] = (c == rax) ? FA(acc[c], prod9) : acc[c];
           }
           const int a = N - 1 - K - delta, b = a + delta;
           if ((need >> a) & 1u) {
@@ -748,6 +788,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       continue;
     }
 
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 3] = clock64();
     // ---------------- stage 4: sweep inversion, one 6xBW block per thread in registers ----------------
     // After sweeping every pivot the matrix holds -H^-1 (Goodnight's sweep operator on an SPD matrix).
     // Per pivot: ONE barrier.  The pivot column k+1 and the current value of diagonal k+2 are published
@@ -856,6 +897,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       __syncthreads();
     }
 
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 4] = clock64();
     // ---------------- stage 5: dual active-set iterations ----------------
     // per-thread constants: one variable (row of H^-1)
     const bool isvar = tid < n;
@@ -1063,6 +1105,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       }
     }
 
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 5] = clock64();
     // polish: x from scratch with the final multipliers, x = x0 + sum_j lam_j H^-1 a_j
     if (code == ST_OK && isvar) {
       double acc = x0[tid];
@@ -1082,6 +1125,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       if (ka.wrench) ka.wrench[(size_t)inst * 12 * N + e] = (float)v;
       if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = (double)(float)v;
     }
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 6] = clock64();
     if (tid == 0) {
       if (code == ST_WS_CAP && ka.esc_list) {  // hand over to the next class (larger working-set capacity)
         const int slot = atomicAdd(&ka.counts[ka.cls + 1], 1);

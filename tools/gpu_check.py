@@ -72,6 +72,21 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     res.update(kernel_ms=ms, qp_per_s=B / ms * 1e3)
+    # ---- per-stage latency (clock64 stamps of thread 0 of each CTA) ----
+    import ctypes
+    clk = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+    interface.lib().hmpc_debug_set_clock_buffer(ctypes.c_void_p(clk.data_ptr()))
+    mpc.solve_device(packed, B, d_w, d_s)
+    torch.cuda.synchronize()
+    interface.lib().hmpc_debug_set_clock_buffer(None)
+    c = clk.cpu().numpy()
+    dur = np.diff(c[:, :7], axis=1).astype(np.float64)
+    names = ["load+prologue", "powers/M/d", "H,g chains", "sweep", "dual active set", "polish+scatter"]
+    res["stage_cycles"] = {n: dict(med=float(np.median(dur[:, i])), p99=float(np.percentile(dur[:, i], 99))) for i, n in enumerate(names)}
+    res["cta_total_cycles"] = dict(med=float(np.median(c[:, 6] - c[:, 0])), max=float((c[:, 6] - c[:, 0]).max()))
+    it = interface.status_iters(d_s.cpu().numpy())
+    gi = dur[:, 4]
+    res["gi_cycles_per_iter_med"] = float(np.median(gi[it > 0] / it[it > 0]))
     t = time.time()
     for _ in range(5):
         mpc.solve_batch(recs, strict=False)
