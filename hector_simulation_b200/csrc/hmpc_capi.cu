@@ -4,9 +4,11 @@
 // context; part 2 is the batched interface.  There is no CPU solve path in this library.
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 
 #include "../../include/hector_mpc_b200.h"
@@ -30,6 +32,8 @@ bool cuda_fail(cudaError_t e, const char* what)
     if (cuda_fail((call), #call)) return HMPC_ERR_CUDA; \
   } while (0)
 
+constexpr int NCHUNK = 4;  // the host-buffer path pipelines pack / H2D / solve / D2H over this many chunks
+
 struct ClassCfg {
   int nb_hi, nb_cap, qmax, threads, smem, grid_cap, variant;
   hmpc::Layout L;
@@ -43,14 +47,15 @@ struct hmpc_ctx {
   ClassCfg cls[2];
   int ncls = 0;
   unsigned char* d_rec = nullptr;
-  double* d_wrench = nullptr;      // fp64 results of the host-buffer path
+  float* d_wrench = nullptr;       // results of the host-buffer path
   int* d_status = nullptr;
-  int* d_counts = nullptr;         // [2] class list lengths
-  int* d_lists = nullptr;          // [2][max_batch] class lists
+  int* d_counts = nullptr;         // [NCHUNK][2] class list lengths
+  int* d_lists = nullptr;          // [NCHUNK][2][max_batch] class lists
   unsigned char* h_rec = nullptr;  // pinned
-  double* h_wrench = nullptr;      // pinned
+  float* h_wrench = nullptr;       // pinned
   int* h_status = nullptr;         // pinned
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // chunk 0 / single-robot stream
+  cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
 };
 
@@ -163,6 +168,12 @@ HMPC_EXTERNC int hmpc_pack_records(const update_data_t* in, int n, int horizon, 
   unsigned char* o = static_cast<unsigned char*>(out);
   for (int i = 0; i < n; i++, o += stride) {
     const update_data_t& u = in[i];
+    if (i + 2 < n) {  // the live bytes of a record are ~11 scattered cache lines of 47: fetch ahead
+      const char* nx = reinterpret_cast<const char*>(&in[i + 2]);
+      for (int off = 0; off < (42 + 12 * horizon) * 4; off += 64) __builtin_prefetch(nx + off);
+      __builtin_prefetch(nx + offsetof(update_data_t, Alpha_K));
+      __builtin_prefetch(nx + offsetof(update_data_t, gait));
+    }
     float* f = reinterpret_cast<float*>(o);
     memcpy(f, u.p, 42 * 4);  // p v q w r joint_angles yaw weights are contiguous in update_data_t
     memcpy(f + 42, u.Alpha_K, 48);
@@ -192,6 +203,8 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->h_wrench) cudaFreeHost(c->h_wrench);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->stream) cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 3; i++)
+    if (c->xstream[i]) cudaStreamDestroy(c->xstream[i]);
   delete c;
 }
 
@@ -227,13 +240,16 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
     c->sm_count = prop.multiProcessorCount;
     const size_t nw = (size_t)12 * horizon;
     bad = cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+          cuda_fail(cudaStreamCreateWithFlags(&c->xstream[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
+          cuda_fail(cudaStreamCreateWithFlags(&c->xstream[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
+          cuda_fail(cudaStreamCreateWithFlags(&c->xstream[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
-          cuda_fail(cudaMalloc(&c->d_wrench, (size_t)max_batch * nw * 8), "cudaMalloc wrench") ||
-          cuda_fail(cudaMalloc(&c->d_counts, 2 * sizeof(int)), "cudaMalloc counts") ||
-          cuda_fail(cudaMalloc(&c->d_lists, (size_t)2 * max_batch * sizeof(int)), "cudaMalloc lists") ||
+          cuda_fail(cudaMalloc(&c->d_wrench, (size_t)max_batch * nw * 4), "cudaMalloc wrench") ||
+          cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 2 * sizeof(int)), "cudaMalloc counts") ||
+          cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * 2 * max_batch * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
-          cuda_fail(cudaMallocHost(&c->h_wrench, (size_t)max_batch * nw * 8), "cudaMallocHost wrench") ||
+          cuda_fail(cudaMallocHost(&c->h_wrench, (size_t)max_batch * nw * 4), "cudaMallocHost wrench") ||
           cuda_fail(cudaMallocHost(&c->h_status, (size_t)max_batch * 4), "cudaMallocHost status") ||
           build_classes(c) != HMPC_OK;
   }
@@ -258,23 +274,25 @@ namespace {
 long long* g_dbg_clk = nullptr;  // profiling hook (hmpc_debug_set_clock_buffer)
 // classification pre-pass + one launch per class, all enqueued on `st`
 int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, double* d_wrench64, int* d_status,
-                  cudaStream_t st)
+                  cudaStream_t st, int slot = 0)
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
-  CK(cudaMemsetAsync(c->d_counts, 0, 2 * sizeof(int), st));
+  int* counts = c->d_counts + 2 * slot;
+  int* lists = c->d_lists + (size_t)slot * 2 * c->max_batch;
+  CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
   hmpc::hmpc_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride, B,
-                                                             c->horizon, c->setup.f_max, c->cls[0].nb_hi, c->d_counts,
-                                                             c->d_lists, c->max_batch);
+                                                             c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts, lists,
+                                                             c->max_batch);
   CK(cudaGetLastError());
   for (int i = 0; i < c->ncls; i++) {
     const ClassCfg& k = c->cls[i];
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
-    ka.list = c->d_lists + (size_t)i * c->max_batch;
-    ka.counts = c->d_counts;
+    ka.list = lists + (size_t)i * c->max_batch;
+    ka.counts = counts;
     ka.cls = i;
-    ka.esc_list = (i + 1 < c->ncls) ? c->d_lists + (size_t)(i + 1) * c->max_batch : nullptr;
+    ka.esc_list = (i + 1 < c->ncls) ? lists + (size_t)(i + 1) * c->max_batch : nullptr;
     ka.nb_cap = k.nb_cap;
     ka.qmax = k.qmax;
     ka.L = k.L;
@@ -347,20 +365,52 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
   if (B == 0) return HMPC_OK;
   CK(cudaSetDevice(c->device));
   const size_t nw = (size_t)12 * c->horizon;
-  int rc = hmpc_pack_records(in, B, c->horizon, c->h_rec);
-  if (rc != HMPC_OK) return rc;
-  CK(cudaMemcpyAsync(c->d_rec, c->h_rec, (size_t)B * c->rec_stride, cudaMemcpyHostToDevice, c->stream));
-  rc = enqueue_solve(c, c->d_rec, B, nullptr, c->d_wrench, c->d_status, c->stream);
-  if (rc != HMPC_OK) return rc;
-  // results land directly in the caller's buffers when they are pinned-or-pageable host memory
-  CK(cudaMemcpyAsync(c->h_wrench, c->d_wrench, (size_t)B * nw * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->h_status, c->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  memcpy(wrench_out, c->h_wrench, (size_t)B * nw * 8);
+  // pipeline over chunks: the host packs chunk k+1 while the GPU copies/solves chunk k, and converts the
+  // results of chunk k while later chunks are still in flight
+  const int nch = B >= 512 ? NCHUNK : (B >= 128 ? 2 : 1);
+  static const bool trace = getenv("HMPC_TRACE") != nullptr;
+  double tr[4 * NCHUNK + 2];
+  int ntr = 0;
+  auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+  if (trace) tr[ntr++] = now();
+  int lo[NCHUNK + 1];
+  for (int k = 0; k <= nch; k++) lo[k] = (int)((long long)B * k / nch);
+  cudaStream_t sts[NCHUNK] = {c->stream, c->xstream[0], c->xstream[1], c->xstream[2]};
+  for (int k = 0; k < nch; k++) {
+    const int b0 = lo[k], nb = lo[k + 1] - lo[k];
+    if (nb == 0) continue;
+    int rc = hmpc_pack_records(in + b0, nb, c->horizon, c->h_rec + (size_t)b0 * c->rec_stride);
+    if (rc != HMPC_OK) return rc;
+    if (trace) tr[ntr++] = now();
+    CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
+                       (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
+    rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, c->d_wrench + (size_t)b0 * nw, nullptr,
+                       c->d_status + b0, sts[k], k);
+    if (rc != HMPC_OK) return rc;
+    CK(cudaMemcpyAsync(c->h_wrench + (size_t)b0 * nw, c->d_wrench + (size_t)b0 * nw, (size_t)nb * nw * 4,
+                       cudaMemcpyDeviceToHost, sts[k]));
+    CK(cudaMemcpyAsync(c->h_status + b0, c->d_status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, sts[k]));
+    if (trace) tr[ntr++] = now();
+  }
   bool all_ok = true;
-  for (int i = 0; i < B; i++) {
-    if (status) status[i] = c->h_status[i];
-    if (HMPC_STATUS_CODE(c->h_status[i]) != 0) all_ok = false;
+  for (int k = 0; k < nch; k++) {
+    const int b0 = lo[k], nb = lo[k + 1] - lo[k];
+    if (nb == 0) continue;
+    CK(cudaStreamSynchronize(sts[k]));
+    if (trace) tr[ntr++] = now();
+    const float* src = c->h_wrench + (size_t)b0 * nw;
+    double* dst = wrench_out + (size_t)b0 * nw;
+    for (size_t i = 0; i < (size_t)nb * nw; i++) dst[i] = (double)src[i];
+    for (int i = b0; i < b0 + nb; i++) {
+      if (status) status[i] = c->h_status[i];
+      if (HMPC_STATUS_CODE(c->h_status[i]) != 0) all_ok = false;
+    }
+  }
+  if (trace) {
+    tr[ntr++] = now();
+    fprintf(stderr, "[hmpc trace] B=%d us since entry:", B);
+    for (int i = 1; i < ntr; i++) fprintf(stderr, " %.0f", tr[i] - tr[0]);
+    fprintf(stderr, "  (per chunk: packed, enqueued; then per chunk: synced; end)\n");
   }
   if (!all_ok) { g_err = "hmpc_solve_batch: at least one instance did not reach a KKT point (see status[])"; return HMPC_ERR_NOT_CONVERGED; }
   return HMPC_OK;
