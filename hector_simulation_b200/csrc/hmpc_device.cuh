@@ -74,7 +74,7 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.Acd = a;  a += align16(169 * 4);
   L.Bcd = a;  a += align16(156 * 4);
   L.P = a;    a += 2 * align16(169 * 4);
-  L.M = a;    a += align16(N * 144 * 4);
+  L.M = a;    a += align16(N * 72 * 4);
   L.dd = a;   a += align16(12 * N * 4);
   L.fbl = a;  a += 192 * 4;
   L.total = align16(s > a ? s : a);
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   float* Acd = reinterpret_cast<float*>(smem + L.Acd);
   float* Bcd = reinterpret_cast<float*>(smem + L.Bcd);
   float* Pbuf = reinterpret_cast<float*>(smem + L.P);  // two 13x13 buffers, 172 floats apart
-  float* Mb = reinterpret_cast<float*>(smem + L.M);    // [N][12][12]: rows 0..11 of P_d*Bcd, columns grouped by leg
+  float* Mb = reinterpret_cast<float*>(smem + L.M);    // [N][6][12]: rows 0..5 of P_d*Bcd (6..11 equal Bcd's), columns grouped by leg
   float* dd = reinterpret_cast<float*>(smem + L.dd);   // [N][12]
   float* Fblk = reinterpret_cast<float*>(smem + L.fbl);
   int* comb = reinterpret_cast<int*>(smem + L.HA);     // stage-3 work list (HA is free until the sweep)
@@ -618,47 +618,58 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // and the reference's dense sequential products reduce to the few terms below — every dropped term is an
     // exact zero product, so the values are those of the dense sums (SolverMPC.cpp:148-177).
     // Pk[k][0..8] = P_k[0:3][6:9], [9..11] = P_k[3+c][9+c], [12] = P_k[5][12], [13] = P_k[11][12]
-    float* Pk = Pbuf;  // (N+1) x 16 floats fit in the two 13x13 buffers
-    if (wid == 0) {
-      float v = 0.f;
-      if (lane < 16) Pk[lane] = 0.f;
-      for (int k = 0; k < N; k++) {
-        // lane 12 needs P_k[5][11] = Pk[k][11] before it is advanced: every lane reads its inputs first
-        const float pd2 = __shfl_sync(0xffffffffu, v, 11);
-        if (lane < 9) v = FA(Acd[(lane / 3) * 13 + 6 + lane % 3], v);
-        else if (lane < 12) v = FA(Acd[(lane - 6) * 13 + lane], v);
-        else if (lane == 12) v = FA(FM(pd2, Acd[11 * 13 + 12]), v);
-        else if (lane == 13) v = FA(Acd[11 * 13 + 12], v);
-        if (lane < 14) Pk[(k + 1) * 16 + lane] = v;
+    // Each item runs its own copy of the (one-FADD-per-step) recurrences, so the stage needs no exchange:
+    //   items 0..35  : column c of rows r and 3+r of every M_k (r = item/12)   -> Mb[k][r][.], Mb[k][3+r][.]
+    //   items 36..47 : row r of every d_s = P_{s+1} x0 - traj_s
+    // Rows 6..11 of M_k equal Bcd's rows for every k and are read from Bcd directly by stage 3.
+    for (int it = tid; it < 48; it += NT) {
+      if (it < 36) {
+        const int r = it / 12, c = it % 12;
+        const float a0 = Acd[r * 13 + 6], a1 = Acd[r * 13 + 7], a2 = Acd[r * 13 + 8], ad = Acd[(3 + r) * 13 + 9 + r];
+        const float b6 = Bcd[6 * 12 + c], b7 = Bcd[7 * 12 + c], b8 = Bcd[8 * 12 + c], b9 = Bcd[(9 + r) * 12 + c];
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, pd = 0.f;  // P_k[r][6..8], P_k[3+r][9+r]
+        float* dst = Mb + r * 12 + leg_of(c) * 6 + loc_of(c);
+        for (int k = 0; k < N; k++) {
+          dst[k * 72] = FA(FA(FM(p0, b6), FM(p1, b7)), FM(p2, b8));
+          dst[k * 72 + 36] = FM(pd, b9);
+          p0 = FA(a0, p0);
+          p1 = FA(a1, p1);
+          p2 = FA(a2, p2);
+          pd = FA(ad, pd);
+        }
+      } else {
+        const int r = it - 36;
+        const float xr_ = x0f[r];
+        if (r < 3) {
+          const float a0 = Acd[r * 13 + 6], a1 = Acd[r * 13 + 7], a2 = Acd[r * 13 + 8];
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+          for (int s = 0; s < N; s++) {
+            p0 = FA(a0, p0);
+            p1 = FA(a1, p1);
+            p2 = FA(a2, p2);
+            const float acc = FA(FA(FA(xr_, FM(p0, x0f[6])), FM(p1, x0f[7])), FM(p2, x0f[8]));
+            dd[12 * s + r] = FS(acc, rf[54 + 12 * s + r]);
+          }
+        } else if (r < 6) {
+          const float ad = Acd[r * 13 + r + 6], ag = Acd[11 * 13 + 12];
+          float pd = 0.f, p5 = 0.f;  // P_k[r][r+6], P_k[5][12]
+          for (int s = 0; s < N; s++) {
+            p5 = FA(FM(pd, ag), p5);  // uses P_k[5][11] before it advances (only meaningful for r == 5)
+            pd = FA(ad, pd);
+            float acc = FA(xr_, FM(pd, x0f[r + 6]));
+            if (r == 5) acc = FA(acc, FM(p5, x0f[12]));
+            dd[12 * s + r] = FS(acc, rf[54 + 12 * s + r]);
+          }
+        } else {
+          const float ag = Acd[11 * 13 + 12];
+          float p11 = 0.f;
+          for (int s = 0; s < N; s++) {
+            p11 = FA(ag, p11);
+            const float acc = (r == 11) ? FA(xr_, FM(p11, x0f[12])) : xr_;
+            dd[12 * s + r] = FS(acc, rf[54 + 12 * s + r]);
+          }
+        }
       }
-    }
-    __syncthreads();
-    // M_k = P_k*Bcd rows 0..11 (columns regrouped by leg), d_s = P_{s+1} x0 - traj_s
-    for (int e = tid; e < N * 144; e += NT) {
-      const int k = e / 144, r = (e % 144) / 12, c = e % 12;
-      const float* pk = Pk + k * 16;
-      float acc;
-      if (r < 3) {
-        acc = FM(pk[r * 3], Bcd[6 * 12 + c]);
-        acc = FA(acc, FM(pk[r * 3 + 1], Bcd[7 * 12 + c]));
-        acc = FA(acc, FM(pk[r * 3 + 2], Bcd[8 * 12 + c]));
-      } else if (r < 6) acc = FM(pk[9 + r - 3], Bcd[(r + 6) * 12 + c]);
-      else acc = Bcd[r * 12 + c];
-      Mb[k * 144 + r * 12 + leg_of(c) * 6 + loc_of(c)] = acc;
-    }
-    for (int e = tid; e < N * 12; e += NT) {
-      const int s = e / 12, r = e % 12;
-      const float* pk = Pk + (s + 1) * 16;
-      float acc = x0f[r];
-      if (r < 3) {
-        acc = FA(acc, FM(pk[r * 3], x0f[6]));
-        acc = FA(acc, FM(pk[r * 3 + 1], x0f[7]));
-        acc = FA(acc, FM(pk[r * 3 + 2], x0f[8]));
-      } else if (r < 6) {
-        acc = FA(acc, FM(pk[9 + r - 3], x0f[r + 6]));
-        if (r == 5) acc = FA(acc, FM(pk[12], x0f[12]));
-      } else if (r == 11) acc = FA(acc, FM(pk[13], x0f[12]));
-      dd[e] = FS(acc, rf[54 + e]);
     }
     __syncthreads();
 
@@ -709,8 +720,8 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const float w3 = rf[30 + 3 + rax];
         const float prod9 = FM(FM(Bcd[(9 + rax) * 12 + ii], rf[30 + 9 + rax]), Bcd[(9 + rax) * 12 + col12_of(lj, rax)]);
         for (int K = 0; K <= Kmax; K++) {
-          const float* Mi = Mb + (K + delta) * 144 + 6 * li + ci;
-          const float2* Mj = reinterpret_cast<const float2*>(Mb + K * 144 + 6 * lj);
+          const float* Mi = Mb + (K + delta) * 72 + 6 * li + ci;
+          const float2* Mj = reinterpret_cast<const float2*>(Mb + K * 72 + 6 * lj);
 #pragma unroll
           for (int r = 0; r < 3; r++) {
             const float tv = FM(Mi[r * 12], wr[r]);  // (B'S)(i,k) = B(k,i)*w(k)
@@ -723,7 +734,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             acc[5] = FA(acc[5], FM(tv, m2.y));
           }
           if (fax) {  // row 3+axis
-            const float t3 = FM(FM(Mi[(3 + rax) * 12], w3), Mb[K * 144 + (3 + rax) * 12 + 6 * lj + rax]);
+            const float t3 = FM(FM(Mi[(3 + rax) * 12], w3), Mb[K * 72 + (3 + rax) * 12 + 6 * lj + rax]);
 #pragma unroll
             for (int c = 0; c < 3; c++) acc[c] = (c == rax) ? FA(acc[c], t3) : acc[c];
           }
@@ -737,24 +748,30 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           }
           const int a = N - 1 - K - delta, b = a + delta;
           if ((need >> a) & 1u) {
-            const int ka_ = dump ? 0 : sl_blk[2 * a + li], kb_ = dump ? 0 : sl_blk[2 * b + lj];
+            if (!dump && delta > 0) {  // block (b,a) strictly below the diagonal: element (cj, ci), no alpha
+              double* dst = H + blk_off(sl_blk[2 * b + lj], sl_blk[2 * a + li]) + ci;
 #pragma unroll
-            for (int cj = 0; cj < 6; cj++) {
-              const int jj = col12_of(lj, cj);
-              if (delta == 0 && ii > jj) continue;  // the reference's solver reads the upper triangle only
-              const float alpha = (delta == 0 && ii == jj) ? rf[42 + ii] : 0.f;
-              const float hv = FM(2.f, FA(acc[cj], alpha));  // qH = 2*(B'SB + Alpha_rep)
-              if (dump) {
-                float* oH = ka.dbg_H + (size_t)inst * (144 * N * N);
-                oH[(size_t)(12 * a + ii) * (12 * N) + 12 * b + jj] = hv;
-                oH[(size_t)(12 * b + jj) * (12 * N) + 12 * a + ii] = hv;
-              } else {
-                const double hd = (double)hv;
-                if (ka_ == kb_) {
-                  H[blk_off(ka_, ka_) + ci * 6 + cj] = hd;
-                  H[blk_off(ka_, ka_) + cj * 6 + ci] = hd;
-                } else if (kb_ > ka_) H[blk_off(kb_, ka_) + cj * 6 + ci] = hd;
-                else H[blk_off(ka_, kb_) + ci * 6 + cj] = hd;
+              for (int cj = 0; cj < 6; cj++) dst[cj * 6] = (double)FM(2.f, FA(acc[cj], 0.f));
+            } else {
+              const int ka_ = dump ? 0 : sl_blk[2 * a + li], kb_ = dump ? 0 : sl_blk[2 * b + lj];
+#pragma unroll
+              for (int cj = 0; cj < 6; cj++) {
+                const int jj = col12_of(lj, cj);
+                if (delta == 0 && ii > jj) continue;  // the reference's solver reads the upper triangle only
+                const float alpha = (delta == 0 && ii == jj) ? rf[42 + ii] : 0.f;
+                const float hv = FM(2.f, FA(acc[cj], alpha));  // qH = 2*(B'SB + Alpha_rep)
+                if (dump) {
+                  float* oH = ka.dbg_H + (size_t)inst * (144 * N * N);
+                  oH[(size_t)(12 * a + ii) * (12 * N) + 12 * b + jj] = hv;
+                  oH[(size_t)(12 * b + jj) * (12 * N) + 12 * a + ii] = hv;
+                } else {
+                  const double hd = (double)hv;
+                  if (ka_ == kb_) {
+                    H[blk_off(ka_, ka_) + ci * 6 + cj] = hd;
+                    H[blk_off(ka_, ka_) + cj * 6 + ci] = hd;
+                  } else if (kb_ > ka_) H[blk_off(kb_, ka_) + cj * 6 + ci] = hd;
+                  else H[blk_off(ka_, kb_) + ci * 6 + cj] = hd;
+                }
               }
             }
           }
@@ -765,11 +782,16 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const int a = e / 12, ii = e % 12, li = leg_of(ii);
         if (!((stmask[li] >> a) & 1u)) continue;
         float acc = 0.f;
+        float t6[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) t6[r] = FM(FM(Bcd[(6 + r) * 12 + ii], wr[6 + r]), 2.f);
         for (int s = a; s < N; s++) {
-          const float* Mi = Mb + (s - a) * 144 + 6 * li + loc_of(ii);
+          const float* Mi = Mb + (s - a) * 72 + 6 * li + loc_of(ii);
           const float* dk = dd + 12 * s;
 #pragma unroll
-          for (int r = 0; r < 12; r++) acc = FA(acc, FM(FM(FM(Mi[r * 12], wr[r]), 2.f), dk[r]));
+          for (int r = 0; r < 6; r++) acc = FA(acc, FM(FM(FM(Mi[r * 12], wr[r]), 2.f), dk[r]));
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc = FA(acc, FM(t6[r], dk[6 + r]));
         }
         if (dump) ka.dbg_g[(size_t)inst * 12 * N + e] = acc;
         else gq[6 * sl_blk[2 * a + li] + loc_of(ii)] = (double)acc;
