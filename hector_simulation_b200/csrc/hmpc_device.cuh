@@ -722,19 +722,30 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         for (int K = 0; K <= Kmax; K++) {
           const float* Mi = Mb + (K + delta) * 72 + 6 * li + ci;
           const float2* Mj = reinterpret_cast<const float2*>(Mb + K * 72 + 6 * lj);
+          // all shared-memory operands of this step first (one latency instead of one per use)
+          float mi[3];
+          float2 mj[3][3];
 #pragma unroll
           for (int r = 0; r < 3; r++) {
-            const float tv = FM(Mi[r * 12], wr[r]);  // (B'S)(i,k) = B(k,i)*w(k)
-            const float2 m0 = Mj[r * 6], m1 = Mj[r * 6 + 1], m2 = Mj[r * 6 + 2];
-            acc[0] = FA(acc[0], FM(tv, m0.x));
-            acc[1] = FA(acc[1], FM(tv, m0.y));
-            acc[2] = FA(acc[2], FM(tv, m1.x));
-            acc[3] = FA(acc[3], FM(tv, m1.y));
-            acc[4] = FA(acc[4], FM(tv, m2.x));
-            acc[5] = FA(acc[5], FM(tv, m2.y));
+            mi[r] = Mi[r * 12];
+            mj[r][0] = Mj[r * 6];
+            mj[r][1] = Mj[r * 6 + 1];
+            mj[r][2] = Mj[r * 6 + 2];
+          }
+          const float m3i = Mi[(3 + rax) * 12];
+          const float m3j = Mb[K * 72 + (3 + rax) * 12 + 6 * lj + rax];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            const float tv = FM(mi[r], wr[r]);  // (B'S)(i,k) = B(k,i)*w(k)
+            acc[0] = FA(acc[0], FM(tv, mj[r][0].x));
+            acc[1] = FA(acc[1], FM(tv, mj[r][0].y));
+            acc[2] = FA(acc[2], FM(tv, mj[r][1].x));
+            acc[3] = FA(acc[3], FM(tv, mj[r][1].y));
+            acc[4] = FA(acc[4], FM(tv, mj[r][2].x));
+            acc[5] = FA(acc[5], FM(tv, mj[r][2].y));
           }
           if (fax) {  // row 3+axis
-            const float t3 = FM(FM(Mi[(3 + rax) * 12], w3), Mb[K * 72 + (3 + rax) * 12 + 6 * lj + rax]);
+            const float t3 = FM(FM(m3i, w3), m3j);
 #pragma unroll
             for (int c = 0; c < 3; c++) acc[c] = (c == rax) ? FA(acc[c], t3) : acc[c];
           }
@@ -777,6 +788,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           }
         }
       }
+    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 7] = clock64();
       // gradient: g(a,ii) = sum_{s>=a} sum_r (T_{s-a}[r][ii]*2) * d_s[r]
       for (int e = tid; e < N * 12; e += NT) {
         const int a = e / 12, ii = e % 12, li = leg_of(ii);
@@ -788,10 +800,15 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         for (int s = a; s < N; s++) {
           const float* Mi = Mb + (s - a) * 72 + 6 * li + loc_of(ii);
           const float* dk = dd + 12 * s;
+          float mi[6], dkr[12];
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc = FA(acc, FM(FM(FM(Mi[r * 12], wr[r]), 2.f), dk[r]));
+          for (int r = 0; r < 6; r++) mi[r] = Mi[r * 12];
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc = FA(acc, FM(t6[r], dk[6 + r]));
+          for (int r = 0; r < 12; r++) dkr[r] = dk[r];
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc = FA(acc, FM(FM(FM(mi[r], wr[r]), 2.f), dkr[r]));
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc = FA(acc, FM(t6[r], dkr[6 + r]));
         }
         if (dump) ka.dbg_g[(size_t)inst * 12 * N + e] = acc;
         else gq[6 * sl_blk[2 * a + li] + loc_of(ii)] = (double)acc;

@@ -83,6 +83,7 @@ def main():
     dur = np.diff(c[:, :7], axis=1).astype(np.float64)
     names = ["load+prologue", "powers/M/d", "H,g chains", "sweep", "dual active set", "polish+scatter"]
     res["stage_cycles"] = {n: dict(med=float(np.median(dur[:, i])), p99=float(np.percentile(dur[:, i], 99))) for i, n in enumerate(names)}
+    res["stage3_items_cycles_med"] = float(np.median(c[:, 7] - c[:, 2]))
     res["cta_total_cycles"] = dict(med=float(np.median(c[:, 6] - c[:, 0])), max=float((c[:, 6] - c[:, 0]).max()))
     it = interface.status_iters(d_s.cpu().numpy())
     gi = dur[:, 4]
