@@ -48,26 +48,54 @@ def algorithmic_flops_per_qp(N: int, nv: float, k_iter: float) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML every 5 ms; nvidia-smi as fallback)."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.reasons, self.max_sm = [], set(), None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        except Exception:
+            return False
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+        return True
+
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        if self._run_nvml():
+            return
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                self.sm.append(float(r[0]))
+                self.max_sm = float(r[1])
+                self.reasons.update(names[i] for i in range(4) if r[2 + i].lower().startswith("active"))
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def start(self):
         self._t.start()
@@ -75,12 +103,24 @@ class ClockSampler:
     def stop(self) -> dict:
         self._stop.set()
         self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` summary of this round (profiles/ncu_r1_v3_summary.txt); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_r1_v3_summary.txt")
+    if not os.path.exists(p):
+        return None
+    tot, unit_mul = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    found = 0
+    for ln in open(p):
+        if ln.startswith("dram__bytes_read.sum:") or ln.startswith("dram__bytes_write.sum:"):
+            _, v, u = ln.split()
+            tot += float(v) * unit_mul.get(u, 1.0)
+            found += 1
+    return tot if found == 2 else None
 
 
 def measured_peaks() -> dict:
@@ -262,7 +302,7 @@ def main():
     nv = 6.0 * N  # walking gait: one stance leg per step
     flops = algorithmic_flops_per_qp(N, nv, k_mean) * B
     byts = algorithmic_bytes_per_qp(N) * B
-    kern_ms = float(np.mean(step_ms))  # both launches of one step (the empty-class launch is ~2 us)
+    kern_ms = float(np.mean(step_ms))  # all launches of one step (classification + one per size class)
     ach_tf = flops / (kern_ms * 1e-3) / 1e12
     ach_gbs = byts / (kern_ms * 1e-3) / 1e9
     line = {
@@ -277,10 +317,12 @@ def main():
         "solver": {"mean_working_set_changes": k_mean, "max": int(iters.max())},
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int(B * (48 * N + 4)),
                 "ms_per_step": e2e_ms / K, "latency_ms_p99": float(np.percentile(e2e_lat, 99) * 1e3)},
-        "gpu_launches": int(K * mpc.launches_per_solve),
+        "gpu_launches": int(K * mpc.launches_per_solve),  # per step: 1 classification kernel + 1 solve kernel per size class
+        "launch_config": {"class0": mpc.class_config(0), "class1": mpc.class_config(1)},
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["bf16_tflops"],
-                     "traffic": None, "peak_source": peaks["_source"],
+                     "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes per launch (dominant kernel, 1024 QPs; algorithmic = %d)" % byts,
+                     "peak_source": peaks["_source"],
                      "note": "algorithmic flops (SURVEY.md §8d: F_asm + k*F_it, nv=6N) / mean kernel time; the kernel's math is fp32 FMUL/FADD + fp64 DFMA on CUDA cores, see DESIGN.md §6",
                      "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                              "bytes_per_qp": algorithmic_bytes_per_qp(N)}},
