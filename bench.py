@@ -266,18 +266,44 @@ def main():
     total_ms = e_all0.elapsed_time(e_all1)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     # ---------------- end-to-end leg (host buffers through the C-ABI) ----------------
+    # N = 1: the reference-facing call hmpc_solve_batch (pack + H2D + kernels + D2H inside).
+    # N > 1: the batch spans devices, so results are exchanged ON DEVICE — per step every rank packs its shard
+    # into pinned memory (C-ABI hmpc_pack_records), copies it in, solves with hmpc_solve_device, joins ONE NCCL
+    # all_gather of the float results, and reads the gathered result back to the host.
+    if world == 1:
+        out_w = np.zeros((B, 12 * N), dtype=np.float64)  # caller-owned result buffers, reused every tick
+        out_s = np.zeros(B, dtype=np.int32)
+
+        def e2e_step():
+            mpc.solve_batch(recs, out=(out_w, out_s))
+    else:
+        import ctypes
+
+        h_in = torch.empty((B, stride), dtype=torch.uint8).pin_memory()
+        d_in1 = torch.empty((B, stride), dtype=torch.uint8, device="cuda")
+        d_w1 = torch.empty((B, 12 * N), dtype=torch.float32, device="cuda")
+        d_s1 = torch.empty((B,), dtype=torch.int32, device="cuda")
+        d_all = torch.empty((world * B, 12 * N), dtype=torch.float32, device="cuda")
+        h_all = torch.empty((world * B, 12 * N), dtype=torch.float32).pin_memory()
+        h_st = torch.empty((B,), dtype=torch.int32).pin_memory()
+        recs_c = np.ascontiguousarray(recs)
+
+        def e2e_step():
+            interface.lib().hmpc_pack_records(recs_c.ctypes.data, B, N, ctypes.c_void_p(h_in.data_ptr()))
+            d_in1.copy_(h_in, non_blocking=True)
+            mpc.solve_device(d_in1, B, d_w1, d_s1)
+            dist.all_gather_into_tensor(d_all, d_w1)
+            h_all.copy_(d_all, non_blocking=True)
+            h_st.copy_(d_s1, non_blocking=True)
+            torch.cuda.synchronize()
     for _ in range(W):
-        mpc.solve_batch(recs)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_lat = []
     for _ in range(K):
         t1 = time.perf_counter()
-        wrench, status = mpc.solve_batch(recs)
-        if world > 1:  # results of all shards on every rank: the path's only exchange
-            g = [torch.empty((B, 12 * N), dtype=torch.float64, device="cuda") for _ in range(world)]
-            dist.all_gather(g, torch.from_numpy(wrench).cuda())
-            torch.cuda.synchronize()
+        e2e_step()
         e2e_lat.append(time.perf_counter() - t1)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -315,7 +341,7 @@ def main():
         "latency_ms": {"batch_p50": float(np.percentile(step_ms, 50)), "batch_p99": p99_step_ms,
                        "note": "device time for the whole 1024-robot batch; every robot's result is ready within it"},
         "solver": {"mean_working_set_changes": k_mean, "max": int(iters.max())},
-        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int(B * (48 * N + 4)),
+        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int((world * B * 48 * N + B * 4) if world > 1 else B * (48 * N + 4)),
                 "ms_per_step": e2e_ms / K, "latency_ms_p99": float(np.percentile(e2e_lat, 99) * 1e3)},
         "gpu_launches": int(K * mpc.launches_per_solve),  # per step: 1 classification kernel + 1 solve kernel per size class
         "launch_config": {"class0": mpc.class_config(0), "class1": mpc.class_config(1)},

@@ -4,12 +4,19 @@
 // context; part 2 is the batched interface.  There is no CPU solve path in this library.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
 #include <ctime>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/hector_mpc_b200.h"
 #include "hmpc_device.cuh"
@@ -32,6 +39,79 @@ bool cuda_fail(cudaError_t e, const char* what)
     if (cuda_fail((call), #call)) return HMPC_ERR_CUDA; \
   } while (0)
 
+// Small host worker pool for the byte-shuffling around the GPU call (packing records, widening results).
+// Workers spin briefly after a job (a control loop calling at 200 Hz+ keeps them hot), then sleep.
+class HostPool {
+ public:
+  explicit HostPool(int nworkers)
+  {
+    for (int i = 0; i < nworkers; i++) workers_.emplace_back([this, i] { run(i); });
+  }
+  ~HostPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  // run fn(part, nparts) on nparts = size() threads (the caller takes part 0); returns when all are done
+  void parallel(const std::function<void(int, int)>& fn)
+  {
+    const int np = size();
+    if (np == 1) { fn(0, 1); return; }
+    fn_ = &fn;
+    pending_.store(np - 1, std::memory_order_release);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      gen_++;
+    }
+    cv_.notify_all();
+    fn(0, np);
+    while (pending_.load(std::memory_order_acquire) != 0) { /* spin: the parts are equal-sized */ }
+  }
+
+ private:
+  void run(int idx)
+  {
+    unsigned seen = 0;
+    for (;;) {
+      // spin ~50 us for the next generation, then block
+      bool got = false;
+      const auto t0 = std::chrono::steady_clock::now();
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(50)) {
+        if (gen_relaxed() != seen) { got = true; break; }
+      }
+      if (!got) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+      }
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        seen = gen_;
+        if (stop_) return;
+      }
+      (*fn_)(idx + 1, size());
+      pending_.fetch_sub(1, std::memory_order_acq_rel);
+    }
+  }
+  unsigned gen_relaxed()
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    return gen_;
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  unsigned gen_ = 0;
+  bool stop_ = false;
+  const std::function<void(int, int)>* fn_ = nullptr;
+  std::atomic<int> pending_{0};
+};
+
 constexpr int NCHUNK = 4;  // the host-buffer path pipelines pack / H2D / solve / D2H over this many chunks
 
 struct ClassCfg {
@@ -47,15 +127,15 @@ struct hmpc_ctx {
   ClassCfg cls[2];
   int ncls = 0;
   unsigned char* d_rec = nullptr;
-  float* d_wrench = nullptr;       // results of the host-buffer path
-  int* d_status = nullptr;
+  unsigned char* d_out = nullptr;  // host-buffer path: per chunk [wrench floats | status ints], contiguous
+  int* d_status = nullptr;         // scratch status (assembly hook)
   int* d_counts = nullptr;         // [NCHUNK][2] class list lengths
   int* d_lists = nullptr;          // [NCHUNK][2][max_batch] class lists
   unsigned char* h_rec = nullptr;  // pinned
-  float* h_wrench = nullptr;       // pinned
-  int* h_status = nullptr;         // pinned
+  unsigned char* h_out = nullptr;  // pinned mirror of d_out
   cudaStream_t stream = nullptr;   // chunk 0 / single-robot stream
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
+  HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
 };
 
@@ -195,13 +275,13 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->d_rec) cudaFree(c->d_rec);
-  if (c->d_wrench) cudaFree(c->d_wrench);
+  if (c->d_out) cudaFree(c->d_out);
   if (c->d_status) cudaFree(c->d_status);
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->d_lists) cudaFree(c->d_lists);
   if (c->h_rec) cudaFreeHost(c->h_rec);
-  if (c->h_wrench) cudaFreeHost(c->h_wrench);
-  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  delete c->pool;
   if (c->stream) cudaStreamDestroy(c->stream);
   for (int i = 0; i < 3; i++)
     if (c->xstream[i]) cudaStreamDestroy(c->xstream[i]);
@@ -244,14 +324,20 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaStreamCreateWithFlags(&c->xstream[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaStreamCreateWithFlags(&c->xstream[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
-          cuda_fail(cudaMalloc(&c->d_wrench, (size_t)max_batch * nw * 4), "cudaMalloc wrench") ||
+          cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4)), "cudaMalloc results") ||
           cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 2 * sizeof(int)), "cudaMalloc counts") ||
           cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * 2 * max_batch * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
-          cuda_fail(cudaMallocHost(&c->h_wrench, (size_t)max_batch * nw * 4), "cudaMallocHost wrench") ||
-          cuda_fail(cudaMallocHost(&c->h_status, (size_t)max_batch * 4), "cudaMallocHost status") ||
+          cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4)), "cudaMallocHost results") ||
           build_classes(c) != HMPC_OK;
+  }
+  if (!bad && max_batch >= 256) {
+    const char* e = getenv("HMPC_HOST_THREADS");
+    int nt = e ? atoi(e) : 4;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && nt > hw) nt = hw;
+    if (nt > 1) c->pool = new HostPool(nt - 1);
   }
   if (bad) {
     std::string keep = g_err;
@@ -280,10 +366,16 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
   CK(cudaSetDevice(c->device));
   int* counts = c->d_counts + 2 * slot;
   int* lists = c->d_lists + (size_t)slot * 2 * c->max_batch;
-  CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
-  hmpc::hmpc_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride, B,
-                                                             c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts, lists,
-                                                             c->max_batch);
+  if (B <= 1024) {
+    hmpc::hmpc_classify1_kernel<<<1, (B + 31) / 32 * 32, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride,
+                                                                 B, c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts,
+                                                                 lists, c->max_batch);
+  } else {
+    CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+    hmpc::hmpc_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride, B,
+                                                               c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts, lists,
+                                                               c->max_batch);
+  }
   CK(cudaGetLastError());
   for (int i = 0; i < c->ncls; i++) {
     const ClassCfg& k = c->cls[i];
@@ -367,7 +459,10 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
   const size_t nw = (size_t)12 * c->horizon;
   // pipeline over chunks: the host packs chunk k+1 while the GPU copies/solves chunk k, and converts the
   // results of chunk k while later chunks are still in flight
-  const int nch = B >= 512 ? NCHUNK : (B >= 128 ? 2 : 1);
+  static const int nch_env = getenv("HMPC_CHUNKS") ? atoi(getenv("HMPC_CHUNKS")) : 0;
+  int nch = B >= 512 ? 2 : 1;  // with helper threads packing is short: two chunks overlap copy-back with compute
+  if (!c->pool) nch = B >= 512 ? NCHUNK : (B >= 128 ? 2 : 1);
+  if (nch_env >= 1 && nch_env <= NCHUNK) nch = nch_env;
   static const bool trace = getenv("HMPC_TRACE") != nullptr;
   double tr[4 * NCHUNK + 2];
   int ntr = 0;
@@ -379,17 +474,25 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
   for (int k = 0; k < nch; k++) {
     const int b0 = lo[k], nb = lo[k + 1] - lo[k];
     if (nb == 0) continue;
-    int rc = hmpc_pack_records(in + b0, nb, c->horizon, c->h_rec + (size_t)b0 * c->rec_stride);
+    int rc = HMPC_OK;
+    if (c->pool && nb >= 128) {
+      c->pool->parallel([&](int part, int nparts) {
+        const int p0 = (int)((long long)nb * part / nparts), p1 = (int)((long long)nb * (part + 1) / nparts);
+        hmpc_pack_records(in + b0 + p0, p1 - p0, c->horizon, c->h_rec + (size_t)(b0 + p0) * c->rec_stride);
+      });
+    } else {
+      rc = hmpc_pack_records(in + b0, nb, c->horizon, c->h_rec + (size_t)b0 * c->rec_stride);
+    }
     if (rc != HMPC_OK) return rc;
     if (trace) tr[ntr++] = now();
     CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
                        (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
-    rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, c->d_wrench + (size_t)b0 * nw, nullptr,
-                       c->d_status + b0, sts[k], k);
+    const size_t ooff = (size_t)b0 * (nw * 4 + 4), obytes = (size_t)nb * (nw * 4 + 4);
+    float* dw = reinterpret_cast<float*>(c->d_out + ooff);
+    int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
+    rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k);
     if (rc != HMPC_OK) return rc;
-    CK(cudaMemcpyAsync(c->h_wrench + (size_t)b0 * nw, c->d_wrench + (size_t)b0 * nw, (size_t)nb * nw * 4,
-                       cudaMemcpyDeviceToHost, sts[k]));
-    CK(cudaMemcpyAsync(c->h_status + b0, c->d_status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, sts[k]));
+    CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, obytes, cudaMemcpyDeviceToHost, sts[k]));
     if (trace) tr[ntr++] = now();
   }
   bool all_ok = true;
@@ -398,12 +501,22 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
     if (nb == 0) continue;
     CK(cudaStreamSynchronize(sts[k]));
     if (trace) tr[ntr++] = now();
-    const float* src = c->h_wrench + (size_t)b0 * nw;
+    const size_t ooff = (size_t)b0 * (nw * 4 + 4);
+    const float* src = reinterpret_cast<const float*>(c->h_out + ooff);
+    const int* hst = reinterpret_cast<const int*>(c->h_out + ooff + (size_t)nb * nw * 4);
     double* dst = wrench_out + (size_t)b0 * nw;
-    for (size_t i = 0; i < (size_t)nb * nw; i++) dst[i] = (double)src[i];
-    for (int i = b0; i < b0 + nb; i++) {
-      if (status) status[i] = c->h_status[i];
-      if (HMPC_STATUS_CODE(c->h_status[i]) != 0) all_ok = false;
+    const size_t tot = (size_t)nb * nw;
+    if (c->pool && nb >= 128) {
+      c->pool->parallel([&](int part, int nparts) {
+        const size_t i0 = tot * part / nparts, i1 = tot * (part + 1) / nparts;
+        for (size_t i = i0; i < i1; i++) dst[i] = (double)src[i];
+      });
+    } else {
+      for (size_t i = 0; i < tot; i++) dst[i] = (double)src[i];
+    }
+    for (int i = 0; i < nb; i++) {
+      if (status) status[b0 + i] = hst[i];
+      if (HMPC_STATUS_CODE(hst[i]) != 0) all_ok = false;
     }
   }
   if (trace) {

@@ -433,6 +433,30 @@ __device__ __forceinline__ int ws_pack(int blk, int nidx) { return (blk << 8) | 
 // ------------------------------------------------------------------------------------------------
 // classification pre-pass: bucket instances by reduced size (number of stance (step,leg) blocks)
 // ------------------------------------------------------------------------------------------------
+// single-block variant (batch <= 1024): counts via shared-memory atomics, written (not accumulated) at the end,
+// so no memset has to precede it
+__global__ void hmpc_classify1_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,
+                                      int nb_hi0, int* counts, int* lists, int list_stride)
+{
+  __shared__ int cnt[2];
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i < batch) {
+    const unsigned char* g = records + (size_t)i * rec_stride + (54 + 12 * N) * 4;
+    int nb = 0;
+    for (int e = 0; e < 2 * N; e++) {
+      const float ub = FM(f_max, (float)g[e]);
+      nb += !(ub < 0.0001f && ub > -0.0001f);
+    }
+    const int c = (nb <= nb_hi0) ? 0 : 1;
+    const int slot = atomicAdd(&cnt[c], 1);
+    lists[(size_t)c * list_stride + slot] = i;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) counts[threadIdx.x] = cnt[threadIdx.x];
+}
+
 __global__ void hmpc_classify_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,
                                      int nb_hi0, int* counts, int* lists, int list_stride)
 {

@@ -171,12 +171,19 @@ class BatchedMPC:
         _check(lib().hmpc_class_config(self._h, cls, out.ctypes.data))
         return dict(zip(("threads", "smem_bytes", "qmax", "grid_cap", "nb_cap", "strip"), (int(v) for v in out)))
 
-    def solve_batch(self, records: np.ndarray, strict: bool = True):
-        """Host-buffer path: H2D + kernels + D2H inside.  -> (wrench [B,12N] f64, status [B] i32)."""
-        records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+    def solve_batch(self, records: np.ndarray, strict: bool = True, out=None):
+        """Host-buffer path: H2D + kernels + D2H inside.  -> (wrench [B,12N] f64, status [B] i32).
+        `out=(wrench, status)` reuses caller-owned result arrays (what a C caller in a control loop does)."""
+        if records.dtype != UPDATE_DTYPE or not records.flags.c_contiguous:
+            records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
         B = records.shape[0]
-        wrench = np.zeros((B, 12 * self.horizon), dtype=np.float64)
-        status = np.zeros(B, dtype=np.int32)
+        if out is not None:
+            wrench, status = out
+            assert wrench.dtype == np.float64 and wrench.shape == (B, 12 * self.horizon) and wrench.flags.c_contiguous
+            assert status.dtype == np.int32 and status.shape == (B,)
+        else:
+            wrench = np.zeros((B, 12 * self.horizon), dtype=np.float64)
+            status = np.zeros(B, dtype=np.int32)
         _check(lib().hmpc_solve_batch(self._h, records.ctypes.data, B, wrench.ctypes.data, status.ctypes.data),
                allow_not_converged=not strict)
         return wrench, status
