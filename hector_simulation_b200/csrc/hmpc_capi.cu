@@ -324,12 +324,12 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaStreamCreateWithFlags(&c->xstream[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaStreamCreateWithFlags(&c->xstream[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
-          cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4)), "cudaMalloc results") ||
+          cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMalloc results") ||
           cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 2 * sizeof(int)), "cudaMalloc counts") ||
           cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * 2 * max_batch * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
-          cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4)), "cudaMallocHost results") ||
+          cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMallocHost results") ||
           build_classes(c) != HMPC_OK;
   }
   if (!bad && max_batch >= 256) {
@@ -360,7 +360,7 @@ namespace {
 long long* g_dbg_clk = nullptr;  // profiling hook (hmpc_debug_set_clock_buffer)
 // classification pre-pass + one launch per class, all enqueued on `st`
 int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, double* d_wrench64, int* d_status,
-                  cudaStream_t st, int slot = 0)
+                  cudaStream_t st, int slot = 0, float* d_tau = nullptr)
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
@@ -381,6 +381,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     const ClassCfg& k = c->cls[i];
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
+    ka.tau = d_tau;
     ka.list = lists + (size_t)i * c->max_batch;
     ka.counts = counts;
     ka.cls = i;
@@ -420,6 +421,14 @@ HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* c, const void* d_records, int B, fl
   return enqueue_solve(c, d_records, B, d_wrench, nullptr, d_status, static_cast<cudaStream_t>(stream));
 }
 
+HMPC_EXTERNC int hmpc_solve_device_ex(hmpc_ctx* c, const void* d_records, int B, float* d_wrench, int* d_status,
+                                      float* d_tau, void* stream)
+{
+  if (!c || !d_records || !d_wrench || !d_status || B < 0) { g_err = "hmpc_solve_device_ex: bad argument"; return HMPC_ERR_ARG; }
+  if (B == 0) return HMPC_OK;
+  return enqueue_solve(c, d_records, B, d_wrench, nullptr, d_status, static_cast<cudaStream_t>(stream), 0, d_tau);
+}
+
 HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B, float* d_H, float* d_g,
                                       float* d_Fblk, float* d_lb, float* d_ub, void* stream)
 {
@@ -448,7 +457,20 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
   return HMPC_OK;
 }
 
+static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, double* tau_out, int* status);
+
 HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, int* status)
+{
+  return solve_batch_impl(c, in, B, wrench_out, nullptr, status);
+}
+
+HMPC_EXTERNC int hmpc_solve_batch_ex(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, double* tau_out,
+                                     int* status)
+{
+  return solve_batch_impl(c, in, B, wrench_out, tau_out, status);
+}
+
+static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, double* tau_out, int* status)
 {
   if (!c || !in || !wrench_out || B < 0 || B > c->max_batch) {
     g_err = "hmpc_solve_batch: bad argument (null pointer or batch > capacity)";
@@ -487,10 +509,11 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
     if (trace) tr[ntr++] = now();
     CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
                        (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
-    const size_t ooff = (size_t)b0 * (nw * 4 + 4), obytes = (size_t)nb * (nw * 4 + 4);
+    const size_t ooff = (size_t)b0 * (nw * 4 + 4 + 40), obytes = (size_t)nb * (nw * 4 + 4 + (tau_out ? 40 : 0));
     float* dw = reinterpret_cast<float*>(c->d_out + ooff);
     int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
-    rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k);
+    float* dt_ = tau_out ? reinterpret_cast<float*>(c->d_out + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
+    rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k, dt_);
     if (rc != HMPC_OK) return rc;
     CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, obytes, cudaMemcpyDeviceToHost, sts[k]));
     if (trace) tr[ntr++] = now();
@@ -501,7 +524,11 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, d
     if (nb == 0) continue;
     CK(cudaStreamSynchronize(sts[k]));
     if (trace) tr[ntr++] = now();
-    const size_t ooff = (size_t)b0 * (nw * 4 + 4);
+    const size_t ooff = (size_t)b0 * (nw * 4 + 4 + 40);
+    if (tau_out) {
+      const float* ht = reinterpret_cast<const float*>(c->h_out + ooff + (size_t)nb * (nw * 4 + 4));
+      for (int i = 0; i < nb * 10; i++) tau_out[(size_t)b0 * 10 + i] = (double)ht[i];
+    }
     const float* src = reinterpret_cast<const float*>(c->h_out + ooff);
     const int* hst = reinterpret_cast<const int*>(c->h_out + ooff + (size_t)nb * nw * 4);
     double* dst = wrench_out + (size_t)b0 * nw;

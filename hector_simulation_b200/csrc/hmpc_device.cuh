@@ -34,7 +34,7 @@ enum : int { ST_OK = 0, ST_ITER_CAP = 1, ST_WS_CAP = 2, ST_INFEASIBLE = 3, ST_NO
 // shared-memory carve-up (byte offsets), computed once on the host and passed by value
 // ------------------------------------------------------------------------------------------------
 struct Layout {
-  int H, gq, x0, x, HA, nrm, rhs, blk, misc, uni;
+  int H, gq, x0, x, HA, nrm, rhs, blk, keep, misc, uni;
   // solver view of the union
   int Li, lam, dv, yv, rv, Wc, act;
   // assembly view of the union
@@ -58,6 +58,7 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.nrm = o;  o += 2 * 10 * 6 * 8;
   L.rhs = o;  o += m * 8;
   L.blk = o;  o += align16((nb_cap + 2 * N) * 4);  // block -> (step,leg) and (step,leg) -> block
+  L.keep = o; o += 64;     // joint angles + quaternion survive the union's reuse (torque epilogue)
   L.misc = o; o += 512;
   L.uni = o;
   int s = L.uni;  // solver view
@@ -125,6 +126,7 @@ struct KernelArgs {
   float* dbg_F;                  // [batch][192]
   float* dbg_lb;                 // [batch][16N]
   float* dbg_ub;                 // [batch][16N]
+  float* tau;                    // [batch][10] joint torques of the first-step wrench (row f-2), or nullptr
   long long* dbg_clk;            // [batch][8] stage timestamps (clock64), profiling hook; null in production
   Layout L;
 };
@@ -385,6 +387,47 @@ __device__ inline void role_inertia(const float* rf, float dt, float* Bcd)
   }
 }
 
+// Column j of the leg's 6x5 force-and-moment Jacobian (LegController.cpp:130-166, restated with the link lever
+// sums S_k, C_k seen from joints 2..4), dotted with the 6-vector f: one joint torque (LegController.cpp:61).
+__device__ inline double leg_torque(const double* q5, int leg, int j, const double* f)
+{
+  const double side = (leg == 0) ? 1.0 : -1.0;
+  double s0, c0, s1, c1;
+  sincos(q5[0], &s0, &c0);
+  sincos(q5[1], &s1, &c1);
+  double s234, c234, s23, c23, s2, c2;
+  sincos(q5[2] + q5[3] + q5[4], &s234, &c234);
+  sincos(q5[2] + q5[3], &s23, &c23);
+  sincos(q5[2], &s2, &c2);
+  const double h = 0.018 * side + 0.0025, e = 0.015 * side;
+  double J[6];
+  if (j == 0) {
+    const double S = 0.04 * s234 + 0.22 * s23 + 0.22 * s2, C = 0.04 * c234 + 0.22 * c23 + 0.22 * c2;
+    const double a = e + c1 * h - s1 * C;
+    J[0] = s0 * (S + 0.0135) + c0 * a;
+    J[1] = s0 * a - c0 * (S + 0.0135);
+    J[2] = 0.0; J[3] = 0.0; J[4] = 0.0; J[5] = 1.0;
+  } else if (j == 1) {
+    const double C = 0.04 * c234 + 0.22 * c23 + 0.22 * c2;
+    const double b = s1 * h + c1 * C;
+    J[0] = -s0 * b;
+    J[1] = c0 * b;
+    J[2] = s1 * C - c1 * h;
+    J[3] = c0; J[4] = s0; J[5] = 0.0;
+  } else {
+    const double S = 0.04 * s234 + (j <= 3 ? 0.22 * s23 : 0.0) + (j == 2 ? 0.22 * s2 : 0.0);
+    const double C = 0.04 * c234 + (j <= 3 ? 0.22 * c23 : 0.0) + (j == 2 ? 0.22 * c2 : 0.0);
+    J[0] = s0 * s1 * S - c0 * C;
+    J[1] = -s0 * C - c0 * s1 * S;
+    J[2] = c1 * S;
+    J[3] = -c1 * s0; J[4] = c0 * c1; J[5] = s1;
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) t = fma(J[r], f[r], t);
+  return t;
+}
+
 // fast fp64 reciprocal: MUFU.RCP64H seed + Newton steps (<= 2 ulp; the sweep and ratio tests do not need
 // correctly rounded division, and the IEEE division sequence is ~6x the instructions)
 __device__ __forceinline__ double fast_rcp(double x)
@@ -606,6 +649,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     const unsigned stmask[2] = {(unsigned)flags[1], (unsigned)flags[2]};
 
     // ---------------- stage 1: prologue, three roles on different warps ----------------
+    if (tid < 14) reinterpret_cast<float*>(smem + L.keep)[tid] = (tid < 10) ? rf[19 + tid] : rf[6 + tid - 10];
     {
       constexpr int W1 = (NW > 1) ? 1 : 0, W2 = (NW > 2) ? 2 : 0;
       if (wid == 0 && lane < 2) role_leg(rf, lane, Fblk);
@@ -846,6 +890,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (ka.wrench) ka.wrench[(size_t)inst * 12 * N + e] = 0.f;
         if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = 0.0;
       }
+      if (ka.tau && tid < 10) ka.tau[(size_t)inst * 10 + tid] = 0.f;
       if (tid == 0) ka.status[inst] = ST_OK;
       __syncthreads();
       continue;
@@ -1187,6 +1232,34 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const double v = (k >= 0) ? HA[6 * k + loc_of(c12)] : 0.0;
       if (ka.wrench) ka.wrench[(size_t)inst * 12 * N + e] = (float)v;
       if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = (double)(float)v;
+    }
+    if (ka.tau && tid < 10) {
+      // row f-2: tau = J_force_moment^T * f_ff, f_ff = -rBody [F; M] of the first-step wrench
+      // (ConvexMPCLocomotion.cpp:419-440, LegController.cpp:57-63); swing legs get no feed-forward force
+      const float* kp_ = reinterpret_cast<const float*>(smem + L.keep);
+      const int leg = tid / 5, j = tid % 5;
+      const double PI = 3.14159265359;
+      double q5[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) q5[i] = (double)kp_[5 * leg + i];
+      q5[2] -= 0.3 * PI;  // undo the caller's second offset: LegController's own angles
+      q5[3] += 0.6 * PI;
+      q5[4] -= 0.3 * PI;
+      const double qw = kp_[10], qx = kp_[11], qy = kp_[12], qz = kp_[13];
+      const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy),
+                           2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx),
+                           2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)};
+      const int k0 = sl_blk[leg];  // step 0
+      double f[6] = {0, 0, 0, 0, 0, 0};
+      if (k0 >= 0) {
+        const double* w = HA + 6 * k0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {  // rBody = R^T
+          f[r] = -(R[0 * 3 + r] * (double)(float)w[0] + R[1 * 3 + r] * (double)(float)w[1] + R[2 * 3 + r] * (double)(float)w[2]);
+          f[3 + r] = -(R[0 * 3 + r] * (double)(float)w[3] + R[1 * 3 + r] * (double)(float)w[4] + R[2 * 3 + r] * (double)(float)w[5]);
+        }
+      }
+      ka.tau[(size_t)inst * 10 + tid] = (float)leg_torque(q5, leg, j, f);
     }
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 6] = clock64();
     if (tid == 0) {

@@ -24,7 +24,7 @@ EXPORTS = [
     "setup_problem", "get_solution", "update_solver_settings", "update_problem_data",
     "hmpc_record_bytes", "hmpc_pack_records", "hmpc_create", "hmpc_destroy", "hmpc_last_error",
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
-    "hmpc_assemble_device", "hmpc_class_config",
+    "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -72,6 +72,10 @@ def lib() -> ctypes.CDLL:
         L.hmpc_assemble_device.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6
         L.hmpc_assemble_device.restype = ctypes.c_int
         L.hmpc_reference_last_status.restype = ctypes.c_int
+        L.hmpc_solve_batch_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+        L.hmpc_solve_batch_ex.restype = ctypes.c_int
+        L.hmpc_solve_device_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
+        L.hmpc_solve_device_ex.restype = ctypes.c_int
         L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hmpc_class_config.restype = ctypes.c_int
         _lib = L
@@ -187,6 +191,17 @@ class BatchedMPC:
         _check(lib().hmpc_solve_batch(self._h, records.ctypes.data, B, wrench.ctypes.data, status.ctypes.data),
                allow_not_converged=not strict)
         return wrench, status
+
+    def solve_batch_torques(self, records: np.ndarray, strict: bool = True):
+        """Host path with the leg-controller epilogue: -> (wrench [B,12N], tau [B,10], status [B])."""
+        records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+        B = records.shape[0]
+        wrench = np.zeros((B, 12 * self.horizon), dtype=np.float64)
+        tau = np.zeros((B, 10), dtype=np.float64)
+        status = np.zeros(B, dtype=np.int32)
+        _check(lib().hmpc_solve_batch_ex(self._h, records.ctypes.data, B, wrench.ctypes.data, tau.ctypes.data, status.ctypes.data),
+               allow_not_converged=not strict)
+        return wrench, tau, status
 
     def solve_device(self, d_records, B: int, d_wrench, d_status, stream=None) -> None:
         """Device-resident path.  Arguments are torch CUDA tensors (uint8 [B,stride], f32 [B,12N], i32 [B])."""

@@ -161,7 +161,8 @@ def boundary_inputs(pos, rpy, vel, omega, raw_joints, gait_table, horizon: int =
             traj[12 * i + 3] = (traj_initial[3] if v_des_world[0] == 0 else pos[0]) + i * DT_MPC * v_des_world[0]
             traj[12 * i + 4] = (traj_initial[4] if v_des_world[1] == 0 else pos[1]) + i * DT_MPC * v_des_world[1]
             traj[12 * i + 2] = traj_initial[2] if yaw_rate == 0 else yaw + i * DT_MPC * yaw_rate
-    return dict(p=pos.copy(), v=vel.copy(), q=quat, w=omega.copy(), r=r, joint_angles=q, yaw=float(yaw),
+    return dict(q_leg=q_leg.reshape(10).copy(), rBody=R.T.copy(),  # LegController's angles / world->body (row f-2 inputs)
+                p=pos.copy(), v=vel.copy(), q=quat, w=omega.copy(), r=r, joint_angles=q, yaw=float(yaw),
                 weights=MPC_WEIGHTS.copy(), state_trajectory=traj, Alpha_K=MPC_ALPHA.copy(),
                 gait=np.asarray(gait_table, dtype=np.int32).copy())
 

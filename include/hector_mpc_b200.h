@@ -144,6 +144,15 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* ctx, const struct update_data_t* in,
 HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench,
                                    int* d_status, void* stream);
 
+/* Row f-2: the same solves with the leg-controller epilogue fused in — joint torques of the
+ * first-step wrench, tau[leg*5+j] = (J_force_moment^T * f_ff)[j], f_ff = -rBody * [F; M]
+ * (replaces LegController.cpp:57-63 + :108-166 and ConvexMPCLocomotion.cpp:419-440 for stance legs; swing legs 0).
+ * tau_out [B][10] doubles (host) / d_tau [B][10] floats (device); pass NULL to skip. */
+HMPC_EXTERNC int hmpc_solve_batch_ex(hmpc_ctx* ctx, const struct update_data_t* in, int B, double* wrench_out,
+                                     double* tau_out, int* status);
+HMPC_EXTERNC int hmpc_solve_device_ex(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench, int* d_status,
+                                      float* d_tau, void* stream);
+
 /* number of kernel launches hmpc_solve_device enqueues per call (classification pre-pass + one per size class) */
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
 /* launch configuration of size class `cls` (0 or 1): out[0..5] = threads per CTA, dynamic shared memory bytes,

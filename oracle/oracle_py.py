@@ -138,3 +138,23 @@ def reduced_qp(record: np.ndarray, setup: np.ndarray, assembly_fp64: bool = Fals
     nc = nc.value
     return dict(H=H[: nv * nv].reshape(nv, nv).copy(), g=g[:nv].copy(), A=A[: nc * nv].reshape(nc, nv).copy(),
                 lb=lb[:nc].copy(), ub=ub[:nc].copy(), var_ind=vi[:nv].copy(), con_ind=ci[:nc].copy())
+
+
+def leg_jacobian_fm(q5, leg: int) -> np.ndarray:
+    """J_force_moment (6x5) of LegController.cpp:130-166 for one leg (q5 = LegController's angles)."""
+    q5 = np.ascontiguousarray(q5, dtype=np.float64)
+    J = np.zeros((6, 5))
+    lib().oracle_leg_jacobian_fm(_p(q5), ctypes.c_int(leg), _p(J))
+    return J
+
+
+def joint_torques(wrench12, rBody, q_leg, contact) -> np.ndarray:
+    """tau [n,10] = J^T (-rBody [F;M]) per stance leg (LegController.cpp:57-63, ConvexMPCLocomotion.cpp:419-440)."""
+    wrench12 = np.ascontiguousarray(wrench12, dtype=np.float64).reshape(-1, 12)
+    n = wrench12.shape[0]
+    rBody = np.ascontiguousarray(rBody, dtype=np.float64).reshape(n, 9)
+    q_leg = np.ascontiguousarray(q_leg, dtype=np.float64).reshape(n, 10)
+    contact = np.ascontiguousarray(contact, dtype=np.int32).reshape(n, 2)
+    tau = np.zeros((n, 10))
+    lib().oracle_joint_torques(_p(wrench12), _p(rBody), _p(q_leg), _p(contact), ctypes.c_int(n), _p(tau))
+    return tau

@@ -570,4 +570,69 @@ int oracle_reduced_qp(const update_data_t* u, const problem_setup* s, int assemb
   return Q.nv;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Row f-2 of SURVEY.md §8: joint torques from the first-step wrench, restating
+ *   LegController.cpp:108-166 (computeLegJacobianAndPosition, J_force_moment 6x5, double)
+ *   LegController.cpp:57-63   (legtau = J_force_moment^T * feedforwardForce)
+ *   ConvexMPCLocomotion.cpp:419-440 (f_ff[leg] = -rBody * [GRF; GRM])
+ * q5 = the leg's joint angles as LegController holds them (raw + first 0.3/-0.6/0.3*3.14159 offset).
+ * J is written with named sub-sums instead of the reference's expanded literals.
+ * ------------------------------------------------------------------------------------------------ */
+void oracle_leg_jacobian_fm(const double* q5, int leg, double* J /* [6][5] row-major */)
+{
+  const double side = (leg == 0) ? 1.0 : -1.0;
+  const double s0 = sin(q5[0]), c0 = cos(q5[0]), s1 = sin(q5[1]), c1 = cos(q5[1]);
+  const double q23 = q5[2] + q5[3], q234 = q5[2] + q5[3] + q5[4];
+  // lever sums of the thigh (0.22), calf (0.22) and foot (0.04) links seen from joints 2, 3 and 4
+  const double S[3] = {0.04 * sin(q234) + 0.22 * sin(q23) + 0.22 * sin(q5[2]), 0.04 * sin(q234) + 0.22 * sin(q23), 0.04 * sin(q234)};
+  const double C[3] = {0.04 * cos(q234) + 0.22 * cos(q23) + 0.22 * cos(q5[2]), 0.04 * cos(q234) + 0.22 * cos(q23), 0.04 * cos(q234)};
+  const double h = 0.018 * side + 0.0025, e = 0.015 * side;
+  for (int i = 0; i < 30; i++) J[i] = 0.0;
+  const double a = e + c1 * h - 1.0 * s1 * C[0];
+  J[0 * 5 + 0] = s0 * (S[0] + 0.0135) + c0 * a;
+  J[1 * 5 + 0] = s0 * a - 1.0 * c0 * (S[0] + 0.0135);
+  J[5 * 5 + 0] = 1.0;
+  const double b = s1 * h + c1 * C[0];
+  J[0 * 5 + 1] = -1.0 * s0 * b;
+  J[1 * 5 + 1] = c0 * b;
+  J[2 * 5 + 1] = s1 * C[0] - 1.0 * c1 * h;
+  J[3 * 5 + 1] = c0;
+  J[4 * 5 + 1] = s0;
+  for (int k = 0; k < 3; k++) {
+    J[0 * 5 + 2 + k] = s0 * s1 * S[k] - 1.0 * c0 * C[k];
+    J[1 * 5 + 2 + k] = -1.0 * s0 * C[k] - 1.0 * c0 * s1 * S[k];
+    J[2 * 5 + 2 + k] = c1 * S[k];
+    J[3 * 5 + 2 + k] = -c1 * s0;
+    J[4 * 5 + 2 + k] = c0 * c1;
+    J[5 * 5 + 2 + k] = s1;
+  }
+}
+
+/* tau[leg][j] for n robots: wrench12 = first-step wrench (get_solution(0..11)), rBody row-major world->body,
+ * q_leg[2][5] as above, contact[2] = first-step contact flags (swing legs get no feed-forward force). */
+void oracle_joint_torques(const double* wrench12, const double* rBody, const double* q_leg, const int* contact, int n,
+                          double* tau /* [n][10] */)
+{
+  for (int i = 0; i < n; i++) {
+    const double* w = wrench12 + 12 * i;
+    const double* Rb = rBody + 9 * i;
+    for (int leg = 0; leg < 2; leg++) {
+      double f[6] = {0, 0, 0, 0, 0, 0};
+      if (contact[2 * i + leg]) {
+        for (int r = 0; r < 3; r++) {
+          f[r] = -(Rb[r * 3] * w[3 * leg] + Rb[r * 3 + 1] * w[3 * leg + 1] + Rb[r * 3 + 2] * w[3 * leg + 2]);
+          f[3 + r] = -(Rb[r * 3] * w[6 + 3 * leg] + Rb[r * 3 + 1] * w[6 + 3 * leg + 1] + Rb[r * 3 + 2] * w[6 + 3 * leg + 2]);
+        }
+      }
+      double J[30];
+      oracle_leg_jacobian_fm(q_leg + 10 * i + 5 * leg, leg, J);
+      for (int j = 0; j < 5; j++) {
+        double t = 0;
+        for (int r = 0; r < 6; r++) t += J[r * 5 + j] * f[r];
+        tau[10 * i + 5 * leg + j] = t;
+      }
+    }
+  }
+}
+
 }  // extern "C"
