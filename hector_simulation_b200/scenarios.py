@@ -122,7 +122,7 @@ def leg_fk(q, leg: int) -> np.ndarray:
 
 def boundary_inputs(pos, rpy, vel, omega, raw_joints, gait_table, horizon: int = 10,
                     v_des_body=(0.0, 0.0), yaw_rate: float = 0.0, pos_des_err=(0.0, 0.0),
-                    roll_pitch_des=(0.0, 0.0)) -> dict:
+                    roll_pitch_des=(0.0, 0.0), feet_world=None) -> dict:
     """The eleven double-precision arguments of update_problem_data (convexMPC_interface.h:43) that
     the reference's caller would build for this robot state (ConvexMPCLocomotion.cpp:283-406)."""
     pos, rpy, vel, omega = (np.asarray(a, dtype=np.float64) for a in (pos, rpy, vel, omega))
@@ -134,7 +134,10 @@ def boundary_inputs(pos, rpy, vel, omega, raw_joints, gait_table, horizon: int =
     q_leg[:, 2] += 0.3 * 3.14159
     q_leg[:, 3] -= 0.6 * 3.14159
     q_leg[:, 4] += 0.3 * 3.14159
-    p_foot = [pos + R @ (hip_yaw_location(i) + leg_fk(q_leg[i], i)) for i in range(2)]
+    if feet_world is None:
+        p_foot = [pos + R @ (hip_yaw_location(i) + leg_fk(q_leg[i], i)) for i in range(2)]
+    else:  # closed-loop harness: feet pinned in the world
+        p_foot = [np.asarray(feet_world[i], dtype=np.float64) for i in range(2)]
     # updateMPCIfNeeded: second offset (3.14159265359) + fmod
     PI = 3.14159265359
     q = q_leg.reshape(10).copy()
@@ -161,7 +164,7 @@ def boundary_inputs(pos, rpy, vel, omega, raw_joints, gait_table, horizon: int =
             traj[12 * i + 3] = (traj_initial[3] if v_des_world[0] == 0 else pos[0]) + i * DT_MPC * v_des_world[0]
             traj[12 * i + 4] = (traj_initial[4] if v_des_world[1] == 0 else pos[1]) + i * DT_MPC * v_des_world[1]
             traj[12 * i + 2] = traj_initial[2] if yaw_rate == 0 else yaw + i * DT_MPC * yaw_rate
-    return dict(q_leg=q_leg.reshape(10).copy(), rBody=R.T.copy(),  # LegController's angles / world->body (row f-2 inputs)
+    return dict(p_foot=np.array(p_foot), q_leg=q_leg.reshape(10).copy(), rBody=R.T.copy(),  # LegController's angles / world->body (row f-2 inputs)
                 p=pos.copy(), v=vel.copy(), q=quat, w=omega.copy(), r=r, joint_angles=q, yaw=float(yaw),
                 weights=MPC_WEIGHTS.copy(), state_trajectory=traj, Alpha_K=MPC_ALPHA.copy(),
                 gait=np.asarray(gait_table, dtype=np.int32).copy())
