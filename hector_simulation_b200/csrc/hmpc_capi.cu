@@ -124,7 +124,7 @@ struct ClassCfg {
 struct hmpc_ctx {
   int device = 0, max_batch = 0, horizon = 0, rec_stride = 0, sm_count = 0;
   problem_setup setup{};
-  ClassCfg cls[2];
+  ClassCfg cls[3];
   int ncls = 0;
   unsigned char* d_rec = nullptr;
   unsigned char* d_out = nullptr;  // host-buffer path: per chunk [wrench floats | status ints], contiguous
@@ -184,10 +184,29 @@ int build_classes(hmpc_ctx* c)
   const int N = c->horizon;
   // class 0: at most N blocks of 6 variables (e.g. any single-support schedule); class 1: up to 2N.
   // Working-set overflow in class 0 escalates to class 1.
-  c->ncls = 2;
+  // class 2 = class 1's size with a working set as large as the variable count (1 CTA/SM): reached only by
+  // escalation from class 1 (massively degenerate optima, e.g. all contact forces at zero).
+  c->ncls = 3;
   const char* exp = getenv("HMPC_CLS0_STRIPS");  // experiment switch: 6x3 strips on 128 threads for class 0
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     ClassCfg& k = c->cls[i];
+    if (i == 2) {
+      k = c->cls[1];
+      const int n = 6 * k.nb_cap;
+      k.qmax = n;
+      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
+      k.smem = k.L.total;
+      const int nbt = k.nb_cap * (k.nb_cap + 1) / 2;
+      const int need = nbt > n ? nbt : n;
+      const int bucket = need <= 64 ? 0 : (need <= 224 ? 1 : 2);
+      k.variant = 6 + bucket;  // runtime-layout class-1 instantiation
+      k.threads = bucket == 0 ? 64 : (bucket == 1 ? 224 : 544);
+      int occ = 0;
+      if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (class 2)")) return HMPC_ERR_CUDA;
+      if (occ < 1) { g_err = "class-2 kernel does not fit on this device"; return HMPC_ERR_CUDA; }
+      k.grid_cap = occ * c->sm_count;
+      break;
+    }
     k.nb_cap = hmpc::class_nb_cap(N, i);
     k.nb_hi = k.nb_cap;
     const int n = 6 * k.nb_cap;
@@ -325,8 +344,8 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaStreamCreateWithFlags(&c->xstream[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
           cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
           cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMalloc results") ||
-          cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 2 * sizeof(int)), "cudaMalloc counts") ||
-          cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * 2 * max_batch * sizeof(int)), "cudaMalloc lists") ||
+          cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 4 * sizeof(int)), "cudaMalloc counts") ||
+          cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * 3 * max_batch * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
           cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMallocHost results") ||
@@ -364,14 +383,14 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
-  int* counts = c->d_counts + 2 * slot;
-  int* lists = c->d_lists + (size_t)slot * 2 * c->max_batch;
+  int* counts = c->d_counts + 4 * slot;
+  int* lists = c->d_lists + (size_t)slot * 3 * c->max_batch;
   if (B <= 1024) {
     hmpc::hmpc_classify1_kernel<<<1, (B + 31) / 32 * 32, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride,
                                                                  B, c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts,
                                                                  lists, c->max_batch);
   } else {
-    CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(counts, 0, 3 * sizeof(int), st));
     hmpc::hmpc_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride, B,
                                                                c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts, lists,
                                                                c->max_batch);

@@ -498,6 +498,7 @@ __global__ void hmpc_classify1_kernel(const unsigned char* records, int rec_stri
   }
   __syncthreads();
   if (threadIdx.x < 2) counts[threadIdx.x] = cnt[threadIdx.x];
+  if (threadIdx.x == 2) counts[2] = 0;  // class 2 is filled by escalation only
 }
 
 __global__ void hmpc_classify_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,

@@ -54,5 +54,9 @@ def main():
         print(name, "nWSR", info[:, 1].min(), info[:, 1].max(), "nv", np.unique(info[:, 2]))
 
 
+# degenerate_zero_force_h10.npz is not generated here: its record was captured from the closed-loop harness
+# (tools/closed_loop_debug.py, a falling robot) and its solution computed with the same oracle calls as above.
+
+
 if __name__ == "__main__":
     main()

@@ -234,3 +234,15 @@ def test_device_resident_path_and_status_words(torch_cuda):
     assert rel_err(w, g["q_soln"]).max() < TOL
     assert (interface.status_nactive(s) <= interface.status_iters(s)).all()
     mpc.close()
+
+
+def test_massively_degenerate_optimum_escalates_and_converges(torch_cuda):
+    """A falling robot whose optimal contact forces are all zero: ~100 active rows on 120 variables.  The working
+    set outgrows class 1's capacity; the kernel hands the robot to the full-capacity class and still returns
+    a KKT point (status 0), matching qpOASES (which needs 163 working-set changes) in absolute terms."""
+    g = load_golden("degenerate_zero_force_h10")
+    w, st = _solve(g["records"], 10)
+    assert (interface.status_code(st) == 0).all(), st
+    assert interface.status_nactive(st).max() > 64          # really beyond the regular working-set capacity
+    assert np.abs(w - g["q_soln"]).max() < 2e-3             # moments ~0.6 N m, forces ~0: absolute comparison
+    assert np.abs(w[:, :6]).max() < 1e-3                    # first-step forces are (numerically) zero
