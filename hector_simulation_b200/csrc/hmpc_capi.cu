@@ -195,6 +195,11 @@ int build_classes(hmpc_ctx* c)
       const int n = 6 * k.nb_cap;
       k.qmax = n;
       k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
+      while (k.L.total > 226 * 1024 && k.qmax > c->cls[1].qmax) {  // long horizons: as much as one SM's smem allows
+        k.qmax -= 4;
+        k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
+      }
+      if (k.qmax <= c->cls[1].qmax) { c->ncls = 2; break; }
       k.smem = k.L.total;
       const int nbt = k.nb_cap * (k.nb_cap + 1) / 2;
       const int need = nbt > n ? nbt : n;

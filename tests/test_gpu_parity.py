@@ -244,5 +244,8 @@ def test_massively_degenerate_optimum_escalates_and_converges(torch_cuda):
     w, st = _solve(g["records"], 10)
     assert (interface.status_code(st) == 0).all(), st
     assert interface.status_nactive(st).max() > 64          # really beyond the regular working-set capacity
-    assert np.abs(w - g["q_soln"]).max() < 2e-3             # moments ~0.6 N m, forces ~0: absolute comparison
+    # moments ~0.6 N m, forces ~0: absolute comparison.  qpOASES' own point is 2e-3 off in one moment component
+    # (a tight fp64 referee, stored in the fixture, reaches a lower objective); the GPU sits on the referee's optimum
+    assert np.abs(w - g["q_soln"]).max() < 5e-3
+    assert np.abs(w - g["q_referee"]).max() < 2e-5
     assert np.abs(w[:, :6]).max() < 1e-3                    # first-step forces are (numerically) zero
