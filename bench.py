@@ -353,6 +353,26 @@ def main():
                      "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                              "bytes_per_qp": algorithmic_bytes_per_qp(N)}},
     }
+    if world == 1:
+        # one robot through the reference's own boundary (setup_problem / update_problem_data / get_solution),
+        # the call sequence of ConvexMPCLocomotion.cpp:410-430 — per-tick latency against the 500 Hz (2 ms) deadline
+        try:
+            tick = []
+            for name, b in (("stand", scenarios.stand_inputs(N)), ("walk", scenarios.make_batch(2, 1, horizon=N)[1][0])):
+                lat = []
+                for it in range(220):
+                    t1 = time.perf_counter()
+                    interface.setup_problem(scenarios.DT_MPC, N, scenarios.MU_PASSED, scenarios.F_MAX)
+                    interface.update_problem_data(b["p"], b["v"], b["q"], b["w"], b["r"], b["joint_angles"], b["yaw"], b["weights"],
+                                                  b["state_trajectory"], b["Alpha_K"], b["gait"])
+                    u0 = [interface.get_solution(i) for i in range(12)]
+                    lat.append(time.perf_counter() - t1)
+                lat = np.array(lat[20:]) * 1e3
+                tick.append((name, float(np.percentile(lat, 50)), float(np.percentile(lat, 99))))
+            line["single_robot_tick_ms"] = {n: {"p50": a, "p99": b_} for n, a, b_ in tick}
+            line["single_robot_tick_ms"]["note"] = "reference C boundary incl. Python/ctypes call overhead; deadline 2 ms (500 Hz)"
+        except Exception as e:
+            line["single_robot_tick_ms"] = {"unavailable": str(e)}
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import oracle_py as O

@@ -137,6 +137,10 @@ struct hmpc_ctx {
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
+  // working-set warm start (S-pair guess at the unconstrained minimiser): measured SLOWER than the cold start on
+  // B200 (its Schur-factor build costs more instructions than the ~10 iterations it saves), so off unless
+  // HMPC_WARM_START=1; -1 = only for batches beyond one resident wave
+  int warm_mode = 0;
 };
 
 namespace {
@@ -356,6 +360,10 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMallocHost results") ||
           build_classes(c) != HMPC_OK;
   }
+  if (!bad) {
+    const char* wm = getenv("HMPC_WARM_START");
+    if (wm) c->warm_mode = atoi(wm);
+  }
   if (!bad && max_batch >= 256) {
     const char* e = getenv("HMPC_HOST_THREADS");
     int nt = e ? atoi(e) : 4;
@@ -406,6 +414,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
     ka.tau = d_tau;
+    ka.warm_start = (c->warm_mode < 0) ? (B > c->cls[0].grid_cap ? 1 : 0) : c->warm_mode;
     ka.list = lists + (size_t)i * c->max_batch;
     ka.counts = counts;
     ka.cls = i;

@@ -117,6 +117,7 @@ struct KernelArgs {
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
+  int warm_start;                // 1: guess the working set at the unconstrained minimiser (S-pair start)
   float* wrench;                 // [batch][12N] float results, or nullptr
   double* wrench64;              // [batch][12N] double results, or nullptr
   int* status;                   // [batch]
@@ -468,6 +469,46 @@ __device__ __forceinline__ int block_argmin32(float v, int idx, unsigned* redk, 
     if (ok < k || (ok == k && oi < i)) { k = ok; i = oi; }
   }
   return i;
+}
+
+// Inverse Cholesky factor P (P'P = S^-1, packed lower rows) without row/column l: rotate row l against every later
+// row so that column l of those rows vanishes (Givens on rows (l,i), i > l, keeps rows i lower triangular; row l
+// collects the direction that is projected out and is discarded), compacting the rows on the way.  Warp-collective;
+// `scratch` holds q doubles.
+__device__ __forceinline__ void li_downdate(double* Li, double* scratch, int l, int q, int lane)
+{
+  for (int j = lane; j < q; j += 32) scratch[j] = (j <= l) ? Li[l * (l + 1) / 2 + j] : 0.0;
+  double alpha = Li[l * (l + 1) / 2 + l];
+  __syncwarp();
+  for (int i = l + 1; i < q; i++) {
+    const double* ri_ = Li + i * (i + 1) / 2;
+    const double bq = ri_[l];
+    const double rr = sqrt(fma(bq, bq, alpha * alpha));
+    const double ir = fast_rcp(rr);
+    const double cg = alpha * ir, sg = bq * ir;
+    double* rnew = Li + (i - 1) * i / 2;  // ends exactly where the old row i begins
+    for (int j = lane; j <= i; j += 32) {
+      const double rl = scratch[j], rv_ = ri_[j];
+      scratch[j] = fma(cg, rl, sg * rv_);
+      const double ni = fma(-sg, rl, cg * rv_);
+      if (j != l) rnew[j < l ? j : j - 1] = ni;
+    }
+    alpha = rr;
+    __syncwarp();
+  }
+}
+// entries j+1 -> j for j in [l, last) of an int and a double array (warp-collective)
+__device__ __forceinline__ void ws_close_gap(int* wc, double* val, int l, int last, int lane)
+{
+  for (int base = l; base < last; base += 32) {
+    const int j = base + lane;
+    int wn = 0;
+    double vn = 0.0;
+    if (j < last) { wn = wc[j + 1]; vn = val[j + 1]; }
+    __syncwarp();
+    if (j < last) { wc[j] = wn; val[j] = vn; }
+    __syncwarp();
+  }
 }
 
 // working-set entry: block index in the high bits, normal index (leg*10+type) in the low byte
@@ -1028,6 +1069,127 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     int q = 0, iters = 0;
     int code = flags[3];
 
+    // ---- warm start of the working set -------------------------------------------------------------------
+    // Take the most violated row of every block at the unconstrained minimiser, solve for its multipliers and
+    // accept the set if they are all positive: (x, W) is then an S-pair — x minimises the QP on the rows of W held
+    // as equalities, with non-negative multipliers — which is exactly the invariant the dual iteration below
+    // maintains, so it simply continues from there (for a walking gait this is usually already the optimum:
+    // one moment bound per step).  Any doubt (dependent rows, a non-positive multiplier) discards the guess.
+    if (code == ST_OK && ka.warm_start) {
+      if (wid == 0) {
+        int cand = -1, cnidx = 0;
+        double cb = 0.0;
+        if (lane < NB) {
+          const int leg = blk_sl[lane] & 1;
+          const double* xb = xv + 6 * lane;
+          double smin = -tol;
+          for (int t = 0; t < 10; t++) {
+            const double* nn = nrm + (leg * 10 + t) * 6;
+            double sl = -rhs[lane * 10 + t];
+#pragma unroll
+            for (int c = 0; c < 6; c++) sl = fma(nn[c], xb[c], sl);
+            if (sl < smin) { smin = sl; cand = lane * 10 + t; cnidx = leg * 10 + t; }
+          }
+          cb = -smin;
+        }
+        const unsigned has = __ballot_sync(0xffffffffu, cand >= 0);
+        int q0 = __popc(has);
+        if (q0 > qmax) q0 = 0;
+        if (cand >= 0 && q0 > 0) {
+          const int pos = __popc(has & ((1u << lane) - 1u));
+          Wc[pos] = ws_pack(lane, cnidx);
+          rv[pos] = cb;  // right-hand side of S lam = -s_W(x0)
+        }
+        __syncwarp();
+        bool ok = q0 > 0;
+        for (int jn = 0; jn < q0 && ok; jn++) {  // inverse Cholesky factor of S = A_W H^-1 A_W', row by row
+          const int wn = Wc[jn], kn = wn >> 8;
+          const double* nn = nrm + (wn & 0xff) * 6;
+          for (int i = lane; i <= jn; i += 32) {
+            const int wi = Wc[i];
+            const double* ni = nrm + (wi & 0xff) * 6;
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) acc = fma(nn[r], hrow6(H, kn, r, wi >> 8, ni), acc);
+            dv[i] = acc;
+          }
+          __syncwarp();
+          double yy = 0.0;
+          for (int j = lane; j < jn; j += 32) {
+            const double* row = Li + j * (j + 1) / 2;
+            double acc = 0.0;
+            for (int i = 0; i <= j; i++) acc = fma(row[i], dv[i], acc);
+            yv[j] = acc;
+            yy = fma(acc, acc, yy);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+          __syncwarp();
+          const double sjj = dv[jn], znn = sjj - yy;
+          if (!(znn > 1e-9 * sjj)) { ok = false; break; }  // (nearly) dependent rows: not a safe start
+          const double irho = rsqrt(znn);
+          double* row = Li + jn * (jn + 1) / 2;
+          for (int i = lane; i < jn; i += 32) {
+            double acc = 0.0;
+            for (int j = i; j < jn; j++) acc = fma(Li[j * (j + 1) / 2 + i], yv[j], acc);
+            row[i] = -acc * irho;
+          }
+          if (lane == 0) row[jn] = irho;
+          __syncwarp();
+        }
+        // multipliers lam = Li'(Li b); rows with a non-positive multiplier are pruned (Givens downdate) and the
+        // rest re-solved, a few rounds at most
+        for (int round = 0; ok && round < 4; round++) {
+          for (int j = lane; j < q0; j += 32) {
+            const double* row = Li + j * (j + 1) / 2;
+            double acc = 0.0;
+            for (int i = 0; i <= j; i++) acc = fma(row[i], rv[i], acc);
+            yv[j] = acc;
+          }
+          __syncwarp();
+          bool neg = false;
+          if (lane < q0) {  // one row per block: q0 <= NB <= 32
+            double acc = 0.0;
+            for (int j = lane; j < q0; j++) acc = fma(Li[j * (j + 1) / 2 + lane], yv[j], acc);
+            lam[lane] = acc;
+            neg = !(acc > 0.0);
+          }
+          unsigned m_ = __ballot_sync(0xffffffffu, neg);
+          if (!m_) break;
+          if (round == 3) { ok = false; break; }
+          while (m_) {  // highest index first keeps the lower ones valid
+            const int l = 31 - __clz(m_);
+            m_ &= ~(1u << l);
+            li_downdate(Li, dv, l, q0, lane);
+            ws_close_gap(Wc, rv, l, q0 - 1, lane);
+            q0--;
+          }
+          if (q0 == 0) ok = false;
+        }
+        if (ok) {
+          for (int j = lane; j < q0; j += 32) {
+            const int w = Wc[j];
+            act[(w >> 8) * 10 + ((w & 0xff) % 10)] = 1;
+          }
+        }
+        if (lane == 0) flags[7] = ok ? q0 : 0;
+      }
+      __syncthreads();
+      q = flags[7];
+      iters = q;
+      if (q > 0) {
+        if (isvar) {
+          double acc = x0[tid];
+          for (int j = 0; j < q; j++) {
+            const int w = Wc[j];
+            acc = fma(lam[j], hrow6(H, vib, vr, w >> 8, nrm + (w & 0xff) * 6), acc);
+          }
+          xv[tid] = acc;
+        }
+        __syncthreads();
+      }
+    }
+
     while (code == ST_OK) {
       // most violated inactive constraint (slacks straight from x; selection in float, value in double)
       float sbest = 3.0e38f;
@@ -1158,54 +1320,21 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           __syncthreads();
           break;
         }
-        // ---- partial step: drop working-set entry l, rebuild the inverse factor, refresh s_p ----
+        // ---- partial step: drop working-set entry l, downdate the inverse factor, refresh s_p ----
         {
           const int l = flags[5];
           lam_p = lam[q];
           __syncthreads();
-          if (tid == 0) {
-            const int w = Wc[l];
-            act[(w >> 8) * 10 + ((w & 0xff) % 10)] = 0;
-            for (int j = l; j < q; j++) { Wc[j] = Wc[j + 1]; lam[j] = lam[j + 1]; }  // includes the parked p at q
+          if (wid == 0) {
+            li_downdate(Li, dv, l, q, lane);
+            if (lane == 0) {
+              const int w = Wc[l];
+              act[(w >> 8) * 10 + ((w & 0xff) % 10)] = 0;
+            }
+            __syncwarp();
+            ws_close_gap(Wc, lam, l, q, lane);  // the parked p sits at q and moves to q-1
           }
           q--;
-          __syncthreads();
-          // rebuild Li by appending the q remaining constraints one at a time (warp 0)
-          if (wid == 0) {
-            for (int jn = 0; jn < q; jn++) {
-              const int wn = Wc[jn], kn = wn >> 8;
-              const double* nn = nrm + (wn & 0xff) * 6;
-              for (int i = lane; i <= jn; i += 32) {  // S[jn][i] = a_n' H^-1 a_i
-                const int wi = Wc[i];
-                const double* ni = nrm + (wi & 0xff) * 6;
-                double acc = 0.0;
-#pragma unroll
-                for (int r = 0; r < 6; r++) acc = fma(nn[r], hrow6(H, kn, r, wi >> 8, ni), acc);
-                dv[i] = acc;
-              }
-              __syncwarp();
-              double yy = 0.0;
-              for (int j = lane; j < jn; j += 32) {
-                const double* row = Li + j * (j + 1) / 2;
-                double acc = 0.0;
-                for (int i = 0; i <= j; i++) acc = fma(row[i], dv[i], acc);
-                yv[j] = acc;
-                yy = fma(acc, acc, yy);
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
-              __syncwarp();
-              const double irho = rsqrt(fmax(dv[jn] - yy, 1e-300));
-              double* row = Li + jn * (jn + 1) / 2;
-              for (int i = lane; i < jn; i += 32) {
-                double acc = 0.0;
-                for (int j = i; j < jn; j++) acc = fma(Li[j * (j + 1) / 2 + i], yv[j], acc);
-                row[i] = -acc * irho;
-              }
-              if (lane == 0) row[jn] = irho;
-              __syncwarp();
-            }
-          }
           __syncthreads();
           sp = -rhs[p];
 #pragma unroll
