@@ -133,6 +133,7 @@ struct hmpc_ctx {
   int* d_lists = nullptr;          // [NCHUNK][2][max_batch] class lists
   unsigned char* h_rec = nullptr;  // pinned
   unsigned char* h_out = nullptr;  // pinned mirror of d_out
+  int* h_cls = nullptr;            // pinned [NCHUNK][4 + 3*max_batch]: host-built class counts + lists (host-buffer path)
   cudaStream_t stream = nullptr;   // chunk 0 / single-robot stream
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
@@ -309,6 +310,7 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->d_lists) cudaFree(c->d_lists);
   if (c->h_rec) cudaFreeHost(c->h_rec);
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_cls) cudaFreeHost(c->h_cls);
   delete c->pool;
   if (c->stream) cudaStreamDestroy(c->stream);
   for (int i = 0; i < 3; i++)
@@ -354,10 +356,11 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMalloc(&c->d_rec, (size_t)max_batch * c->rec_stride), "cudaMalloc records") ||
           cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMalloc results") ||
           cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 4 * sizeof(int)), "cudaMalloc counts") ||
-          cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * 3 * max_batch * sizeof(int)), "cudaMalloc lists") ||
+          cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
           cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMallocHost results") ||
+          cuda_fail(cudaMallocHost(&c->h_cls, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMallocHost lists") ||
           build_classes(c) != HMPC_OK;
   }
   if (!bad) {
@@ -396,8 +399,8 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
-  int* counts = c->d_counts + 4 * slot;
-  int* lists = c->d_lists + (size_t)slot * 3 * c->max_batch;
+  int* counts = c->d_lists + (size_t)slot * (4 + 3 * (size_t)c->max_batch);  // per slot: [4 counts][3 lists]
+  int* lists = counts + 4;
   if (B <= 1024) {
     hmpc::hmpc_classify1_kernel<<<1, (B + 31) / 32 * 32, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride,
                                                                  B, c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts,
@@ -424,6 +427,57 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     ka.L = k.L;
     ka.dbg_clk = g_dbg_clk;
     const int grid = B < k.grid_cap ? B : k.grid_cap;
+    CK(launch_class(k, ka, grid, st));
+  }
+  return HMPC_OK;
+}
+}  // namespace
+
+namespace {
+// Host-buffer path: the host has the contact tables in hand while it packs, so it builds the class lists itself
+// (same rule as hmpc_classify_kernel) and launches only the non-empty classes — no classification kernel, no
+// empty launches.  Working-set overflow cannot escalate here; the caller re-runs such a chunk through enqueue_solve.
+void classify_host(const hmpc_ctx* c, const update_data_t* in, int nb, int* blockbuf)
+{
+  int* counts = blockbuf;
+  int* lists = blockbuf + 4;
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  const int N = c->horizon;
+  for (int i = 0; i < nb; i++) {
+    int k = 0;
+    for (int e = 0; e < 2 * N; e++) {
+      const float ub = c->setup.f_max * (float)in[i].gait[e];
+      k += !(ub < 0.0001f && ub > -0.0001f);
+    }
+    const int cl = (k <= c->cls[0].nb_hi) ? 0 : 1;
+    lists[(size_t)cl * c->max_batch + counts[cl]++] = i;
+  }
+}
+
+int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, const int* h_block, float* d_wrench32, int* d_status,
+                            cudaStream_t st, int slot, float* d_tau)
+{
+  int* d_block = c->d_lists + (size_t)slot * (4 + 3 * (size_t)c->max_batch);
+  const int n0 = h_block[0], n1 = h_block[1];
+  // counts + class-0 list (+ class-1 list when it is not empty) in one copy
+  const size_t ints = (n1 > 0) ? (size_t)4 + c->max_batch + n1 : (size_t)4 + n0;
+  CK(cudaMemcpyAsync(d_block, h_block, ints * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < 2; i++) {
+    const int cnt = i == 0 ? n0 : n1;
+    if (cnt == 0) continue;
+    const ClassCfg& k = c->cls[i];
+    hmpc::KernelArgs ka = base_args(c, d_records, nb, d_wrench32, d_status);
+    ka.tau = d_tau;
+    ka.warm_start = (c->warm_mode < 0) ? (nb > c->cls[0].grid_cap ? 1 : 0) : c->warm_mode;
+    ka.list = d_block + 4 + (size_t)i * c->max_batch;
+    ka.counts = d_block;
+    ka.cls = i;
+    ka.esc_list = nullptr;  // overflow is handled by the caller's retry
+    ka.nb_cap = k.nb_cap;
+    ka.qmax = k.qmax;
+    ka.L = k.L;
+    ka.dbg_clk = g_dbg_clk;
+    const int grid = cnt < k.grid_cap ? cnt : k.grid_cap;
     CK(launch_class(k, ka, grid, st));
   }
   return HMPC_OK;
@@ -546,7 +600,9 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double*
     float* dw = reinterpret_cast<float*>(c->d_out + ooff);
     int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
     float* dt_ = tau_out ? reinterpret_cast<float*>(c->d_out + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
-    rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k, dt_);
+    int* hblk = c->h_cls + (size_t)k * (4 + 3 * (size_t)c->max_batch);
+    classify_host(c, in + b0, nb, hblk);
+    rc = enqueue_solve_hostlists(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, hblk, dw, ds, sts[k], k, dt_);
     if (rc != HMPC_OK) return rc;
     CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, obytes, cudaMemcpyDeviceToHost, sts[k]));
     if (trace) tr[ntr++] = now();
@@ -558,6 +614,21 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double*
     CK(cudaStreamSynchronize(sts[k]));
     if (trace) tr[ntr++] = now();
     const size_t ooff = (size_t)b0 * (nw * 4 + 4 + 40);
+    {  // working-set overflow (rare, massively degenerate optima): redo the chunk through the escalating device path
+      const int* hs = reinterpret_cast<const int*>(c->h_out + ooff + (size_t)nb * nw * 4);
+      bool overflow = false;
+      for (int i = 0; i < nb; i++) overflow |= (HMPC_STATUS_CODE(hs[i]) == hmpc::ST_WS_CAP);
+      if (overflow) {
+        float* dw = reinterpret_cast<float*>(c->d_out + ooff);
+        int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
+        float* dt_ = tau_out ? reinterpret_cast<float*>(c->d_out + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
+        int rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k, dt_);
+        if (rc != HMPC_OK) return rc;
+        CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, (size_t)nb * (nw * 4 + 4 + (tau_out ? 40 : 0)),
+                           cudaMemcpyDeviceToHost, sts[k]));
+        CK(cudaStreamSynchronize(sts[k]));
+      }
+    }
     if (tau_out) {
       const float* ht = reinterpret_cast<const float*>(c->h_out + ooff + (size_t)nb * (nw * 4 + 4));
       for (int i = 0; i < nb * 10; i++) tau_out[(size_t)b0 * 10 + i] = (double)ht[i];
