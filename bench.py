@@ -109,8 +109,8 @@ class ClockSampler:
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-    `ncu --set full` summary of this round (profiles/ncu_r1_v3_summary.txt); None if absent."""
-    p = os.path.join(ROOT, "profiles", "ncu_r1_v3_summary.txt")
+    `ncu --set full` summary of this round (profiles/ncu_r1_final_summary.txt); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_r1_final_summary.txt")
     if not os.path.exists(p):
         return None
     tot, unit_mul = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
