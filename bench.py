@@ -231,7 +231,7 @@ def main():
     K, W = args.steps, args.warmup
 
     # synthetic walking-gait states (configs[1]); each rank gets its own shard (different seed)
-    recs, _ = scenarios.make_batch(2, B, horizon=N, seed=scenarios.config_seed(2) + 1000 * rank)
+    recs, inputs = scenarios.make_batch(2, B, horizon=N, seed=scenarios.config_seed(2) + 1000 * rank)
     mpc = interface.BatchedMPC(B, N, device=local_rank)
     stride = interface.record_bytes(N)
     packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
@@ -373,6 +373,19 @@ def main():
             line["single_robot_tick_ms"]["note"] = "reference C boundary incl. Python/ctypes call overhead; deadline 2 ms (500 Hz)"
         except Exception as e:
             line["single_robot_tick_ms"] = {"unavailable": str(e)}
+        # row f-1 variant of the end-to-end call: the caller hands over 352-byte robot states and the data
+        # preparation (trajectory, foot positions, joint offsets) runs on the device (hmpc_solve_batch_states)
+        states = scenarios.make_states(inputs, N)
+        for _ in range(W):
+            mpc.solve_batch_states(states, out=(out_w, out_s))
+        t1 = time.perf_counter()
+        for _ in range(K):
+            mpc.solve_batch_states(states, out=(out_w, out_s))
+        dt_states = time.perf_counter() - t1
+        assert (interface.status_code(out_s) == 0).all()
+        line["e2e_states"] = {"value": B * K / dt_states, "unit": UNIT, "ms_per_step": dt_states / K * 1e3,
+                              "h2d_bytes_per_step": int(B * scenarios.STATE_DTYPE.itemsize), "d2h_bytes_per_step": int(B * (48 * N + 4)),
+                              "note": "hmpc_solve_batch_states: updateMPCIfNeeded's data preparation on the device (SURVEY 8f row f-1)"}
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import oracle_py as O

@@ -133,6 +133,8 @@ struct hmpc_ctx {
   int* d_lists = nullptr;          // [NCHUNK][2][max_batch] class lists
   unsigned char* h_rec = nullptr;  // pinned
   unsigned char* h_out = nullptr;  // pinned mirror of d_out
+  unsigned char* d_states = nullptr;  // hmpc_state_t staging of hmpc_solve_batch_states (row f-1)
+  unsigned char* h_states = nullptr;  // pinned
   int* h_cls = nullptr;            // pinned [NCHUNK][4 + 3*max_batch]: host-built class counts + lists (host-buffer path)
   cudaStream_t stream = nullptr;   // chunk 0 / single-robot stream
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
@@ -308,6 +310,8 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->d_status) cudaFree(c->d_status);
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->d_lists) cudaFree(c->d_lists);
+  if (c->d_states) cudaFree(c->d_states);
+  if (c->h_states) cudaFreeHost(c->h_states);
   if (c->h_rec) cudaFreeHost(c->h_rec);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_cls) cudaFreeHost(c->h_cls);
@@ -358,6 +362,8 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 4 * sizeof(int)), "cudaMalloc counts") ||
           cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMalloc lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
+          cuda_fail(cudaMalloc(&c->d_states, (size_t)max_batch * sizeof(hmpc_state_t)), "cudaMalloc states") ||
+          cuda_fail(cudaMallocHost(&c->h_states, (size_t)max_batch * sizeof(hmpc_state_t)), "cudaMallocHost states") ||
           cuda_fail(cudaMallocHost(&c->h_rec, (size_t)max_batch * c->rec_stride), "cudaMallocHost records") ||
           cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMallocHost results") ||
           cuda_fail(cudaMallocHost(&c->h_cls, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMallocHost lists") ||
@@ -437,7 +443,7 @@ namespace {
 // Host-buffer path: the host has the contact tables in hand while it packs, so it builds the class lists itself
 // (same rule as hmpc_classify_kernel) and launches only the non-empty classes — no classification kernel, no
 // empty launches.  Working-set overflow cannot escalate here; the caller re-runs such a chunk through enqueue_solve.
-void classify_host(const hmpc_ctx* c, const update_data_t* in, int nb, int* blockbuf)
+void classify_host(const hmpc_ctx* c, const unsigned char* gait0, size_t gait_stride, int nb, int* blockbuf)
 {
   int* counts = blockbuf;
   int* lists = blockbuf + 4;
@@ -446,7 +452,7 @@ void classify_host(const hmpc_ctx* c, const update_data_t* in, int nb, int* bloc
   for (int i = 0; i < nb; i++) {
     int k = 0;
     for (int e = 0; e < 2 * N; e++) {
-      const float ub = c->setup.f_max * (float)in[i].gait[e];
+      const float ub = c->setup.f_max * (float)gait0[(size_t)i * gait_stride + e];
       k += !(ub < 0.0001f && ub > -0.0001f);
     }
     const int cl = (k <= c->cls[0].nb_hi) ? 0 : 1;
@@ -544,22 +550,44 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
   return HMPC_OK;
 }
 
-static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, double* tau_out, int* status);
+static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_state_t* sin, int B, double* wrench_out,
+                            double* tau_out, int* status);
 
 HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, int* status)
 {
-  return solve_batch_impl(c, in, B, wrench_out, nullptr, status);
+  return solve_batch_impl(c, in, nullptr, B, wrench_out, nullptr, status);
 }
 
 HMPC_EXTERNC int hmpc_solve_batch_ex(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, double* tau_out,
                                      int* status)
 {
-  return solve_batch_impl(c, in, B, wrench_out, tau_out, status);
+  return solve_batch_impl(c, in, nullptr, B, wrench_out, tau_out, status);
 }
 
-static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, double* tau_out, int* status)
+static_assert(sizeof(hmpc_state_t) == 352 && offsetof(hmpc_state_t, gait) == 39 * 8, "hmpc_state_t layout (hmpc_prepare_kernel)");
+
+HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* c, const hmpc_state_t* d_states, int B, void* d_records, void* stream)
 {
-  if (!c || !in || !wrench_out || B < 0 || B > c->max_batch) {
+  if (!c || !d_states || !d_records || B < 0) { g_err = "hmpc_prepare_device: bad argument"; return HMPC_ERR_ARG; }
+  if (B == 0) return HMPC_OK;
+  CK(cudaSetDevice(c->device));
+  hmpc::hmpc_prepare_kernel<<<(B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned char*>(d_states), B, c->horizon, (double)c->setup.dt,
+      static_cast<unsigned char*>(d_records), c->rec_stride);
+  CK(cudaGetLastError());
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* c, const hmpc_state_t* in, int B, double* wrench_out, double* tau_out,
+                                         int* status)
+{
+  return solve_batch_impl(c, nullptr, in, B, wrench_out, tau_out, status);
+}
+
+static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_state_t* sin, int B, double* wrench_out,
+                            double* tau_out, int* status)
+{
+  if (!c || (!in && !sin) || !wrench_out || B < 0 || B > c->max_batch) {
     g_err = "hmpc_solve_batch: bad argument (null pointer or batch > capacity)";
     return HMPC_ERR_ARG;
   }
@@ -584,24 +612,36 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, int B, double*
     const int b0 = lo[k], nb = lo[k + 1] - lo[k];
     if (nb == 0) continue;
     int rc = HMPC_OK;
-    if (c->pool && nb >= 128) {
-      c->pool->parallel([&](int part, int nparts) {
-        const int p0 = (int)((long long)nb * part / nparts), p1 = (int)((long long)nb * (part + 1) / nparts);
-        hmpc_pack_records(in + b0 + p0, p1 - p0, c->horizon, c->h_rec + (size_t)(b0 + p0) * c->rec_stride);
-      });
+    if (sin) {
+      // row f-1: ship the 352-byte states and build the packed records on the device
+      const size_t sb = sizeof(hmpc_state_t);
+      memcpy(c->h_states + (size_t)b0 * sb, sin + b0, (size_t)nb * sb);
+      if (trace) tr[ntr++] = now();
+      CK(cudaMemcpyAsync(c->d_states + (size_t)b0 * sb, c->h_states + (size_t)b0 * sb, (size_t)nb * sb, cudaMemcpyHostToDevice, sts[k]));
+      rc = hmpc_prepare_device(c, reinterpret_cast<const hmpc_state_t*>(c->d_states + (size_t)b0 * sb), nb,
+                               c->d_rec + (size_t)b0 * c->rec_stride, sts[k]);
+      if (rc != HMPC_OK) return rc;
     } else {
-      rc = hmpc_pack_records(in + b0, nb, c->horizon, c->h_rec + (size_t)b0 * c->rec_stride);
+      if (c->pool && nb >= 128) {
+        c->pool->parallel([&](int part, int nparts) {
+          const int p0 = (int)((long long)nb * part / nparts), p1 = (int)((long long)nb * (part + 1) / nparts);
+          hmpc_pack_records(in + b0 + p0, p1 - p0, c->horizon, c->h_rec + (size_t)(b0 + p0) * c->rec_stride);
+        });
+      } else {
+        rc = hmpc_pack_records(in + b0, nb, c->horizon, c->h_rec + (size_t)b0 * c->rec_stride);
+      }
+      if (rc != HMPC_OK) return rc;
+      if (trace) tr[ntr++] = now();
+      CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
+                         (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
     }
-    if (rc != HMPC_OK) return rc;
-    if (trace) tr[ntr++] = now();
-    CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
-                       (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
     const size_t ooff = (size_t)b0 * (nw * 4 + 4 + 40), obytes = (size_t)nb * (nw * 4 + 4 + (tau_out ? 40 : 0));
     float* dw = reinterpret_cast<float*>(c->d_out + ooff);
     int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
     float* dt_ = tau_out ? reinterpret_cast<float*>(c->d_out + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
     int* hblk = c->h_cls + (size_t)k * (4 + 3 * (size_t)c->max_batch);
-    classify_host(c, in + b0, nb, hblk);
+    if (sin) classify_host(c, sin[b0].gait, sizeof(hmpc_state_t), nb, hblk);
+    else classify_host(c, in[b0].gait, sizeof(update_data_t), nb, hblk);
     rc = enqueue_solve_hostlists(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, hblk, dw, ds, sts[k], k, dt_);
     if (rc != HMPC_OK) return rc;
     CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, obytes, cudaMemcpyDeviceToHost, sts[k]));

@@ -515,6 +515,89 @@ __device__ __forceinline__ void ws_close_gap(int* wc, double* val, int l, int la
 __device__ __forceinline__ int ws_pack(int blk, int nidx) { return (blk << 8) | nidx; }
 
 // ------------------------------------------------------------------------------------------------
+// row f-1: the caller's data preparation, one thread per robot (ConvexMPCLocomotion.cpp:283-406 followed by the
+// double -> float narrowing of update_problem_data, convexMPC_interface.cpp:87-99).  Double arithmetic with
+// explicitly rounded operations in the reference's order, so the packed record equals the host-prepared one.
+// `st` points at hmpc_state_t records (352 bytes): 39 doubles then the gait bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void hmpc_prepare_kernel(const unsigned char* states, int batch, int N, double dtMPC, unsigned char* records,
+                                    int rec_stride)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const double* s = reinterpret_cast<const double*>(states + (size_t)i * 352);
+  const unsigned char* gait = states + (size_t)i * 352 + 39 * 8;
+  const double* pos = s;            // [3]
+  const double* vw = s + 3;         // [3]
+  const double* qt = s + 6;         // [4]
+  const double* ow = s + 10;        // [3]
+  const double* rpy = s + 13;       // [3]
+  const double* lq = s + 16;        // [10]
+  const double* lp = s + 26;        // [2][3]
+  const double* sd = s + 32;        // roll, pitch, vx, vy, yaw rate
+  const double* wpd = s + 37;       // [2]
+  float* f = reinterpret_cast<float*>(records + (size_t)i * rec_stride);
+  // body -> world rotation (= rBody^T), ori::quaternionToRotationMatrix before its transpose
+  const double e0 = qt[0], e1 = qt[1], e2 = qt[2], e3 = qt[3];
+  const double R[9] = {DS(1.0, DM(2.0, DA(DM(e2, e2), DM(e3, e3)))), DM(2.0, DS(DM(e1, e2), DM(e0, e3))), DM(2.0, DA(DM(e1, e3), DM(e0, e2))),
+                       DM(2.0, DA(DM(e1, e2), DM(e0, e3))), DS(1.0, DM(2.0, DA(DM(e1, e1), DM(e3, e3)))), DM(2.0, DS(DM(e2, e3), DM(e0, e1))),
+                       DM(2.0, DS(DM(e1, e3), DM(e0, e2))), DM(2.0, DA(DM(e2, e3), DM(e0, e1))), DS(1.0, DM(2.0, DA(DM(e1, e1), DM(e2, e2))))};
+  for (int k = 0; k < 3; k++) { f[k] = (float)pos[k]; f[3 + k] = (float)vw[k]; f[10 + k] = (float)ow[k]; }
+  for (int k = 0; k < 4; k++) f[6 + k] = (float)qt[k];
+  // foot positions: pFoot = position + rBody^T (hip + leg.p); r[k] = pFoot[k%2][k/2] - position[k/2]   (:58-62, :315-319)
+  double pf[2][3];
+  for (int leg = 0; leg < 2; leg++) {
+    const double hp[3] = {DA(-0.005, lp[3 * leg]), DA(leg == 0 ? -0.057 : 0.057, lp[3 * leg + 1]), DA(-0.126, lp[3 * leg + 2])};
+    for (int a = 0; a < 3; a++)
+      pf[leg][a] = DA(pos[a], DA(DA(DM(R[a * 3], hp[0]), DM(R[a * 3 + 1], hp[1])), DM(R[a * 3 + 2], hp[2])));
+  }
+  for (int k = 0; k < 6; k++) f[13 + k] = (float)DS(pf[k % 2][k / 2], pos[k / 2]);
+  // joint angles: second offset + fmod (:289-313)
+  const double PI = 3.14159265359, PI2 = DM(2.0, PI);
+  for (int leg = 0; leg < 2; leg++) {
+    double q5[5];
+    for (int k = 0; k < 5; k++) q5[k] = lq[5 * leg + k];
+    q5[2] = DA(q5[2], DM(0.3, PI));
+    q5[3] = DS(q5[3], DM(0.6, PI));
+    q5[4] = DA(q5[4], DM(0.3, PI));
+    for (int k = 0; k < 5; k++) f[19 + 5 * leg + k] = (float)fmod(q5[k], PI2);
+  }
+  const double yaw = rpy[2];
+  f[29] = (float)yaw;
+  const float Qw[12] = {100, 100, 250, 200, 200, 300, 1, 1, 1, 1, 1, 1};                           // :321
+  const float Al[12] = {1e-4f, 1e-4f, 5e-4f, 1e-4f, 1e-4f, 5e-4f, 1e-2f, 1e-2f, 1e-2f, 1e-2f, 1e-2f, 1e-2f};  // :322
+  for (int k = 0; k < 12; k++) { f[30 + k] = Qw[k]; f[42 + k] = Al[k]; }
+  // reference trajectory (:331-399)
+  const double vdr[3] = {sd[2], sd[3], 0.0};
+  double vdw[3];
+  for (int a = 0; a < 3; a++) vdw[a] = DA(DA(DM(R[a * 3], vdr[0]), DM(R[a * 3 + 1], vdr[1])), DM(R[a * 3 + 2], vdr[2]));
+  const double mpe = .05;
+  double xS = wpd[0], yS = wpd[1];
+  if (DS(xS, pos[0]) > mpe) xS = DA(pos[0], mpe);
+  if (DS(pos[0], xS) > mpe) xS = DS(pos[0], mpe);
+  if (DS(yS, pos[1]) > mpe) yS = DA(pos[1], mpe);
+  if (DS(pos[1], yS) > mpe) yS = DS(pos[1], mpe);
+  const double ti[12] = {sd[0], sd[1], 0.0, xS, yS, 0.55, 0, 0, sd[4], vdw[0], vdw[1], 0};
+  for (int st = 0; st < N; st++) {
+    double tr[12];
+    for (int j = 0; j < 12; j++) tr[j] = ti[j];
+    if (st == 0) {
+      tr[0] = rpy[0]; tr[1] = rpy[1]; tr[2] = rpy[2];
+      tr[3] = pos[0]; tr[4] = pos[1]; tr[5] = pos[2];
+    } else {
+      const double idt = DM((double)st, dtMPC);
+      tr[3] = DA(vdw[0] == 0 ? ti[3] : pos[0], DM(idt, vdw[0]));
+      tr[4] = DA(vdw[1] == 0 ? ti[4] : pos[1], DM(idt, vdw[1]));
+      tr[2] = (sd[4] == 0) ? ti[2] : DA(yaw, DM(idt, sd[4]));
+    }
+    for (int j = 0; j < 12; j++) f[54 + 12 * st + j] = (float)tr[j];
+  }
+  unsigned char* g = records + (size_t)i * rec_stride + (54 + 12 * N) * 4;
+  for (int e = 0; e < 2 * N; e++) g[e] = gait[e];
+  for (int e = (54 + 12 * N) * 4 + 2 * N; e < rec_stride; e++) records[(size_t)i * rec_stride + e] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // classification pre-pass: bucket instances by reduced size (number of stance (step,leg) blocks)
 // ------------------------------------------------------------------------------------------------
 // single-block variant (batch <= 1024): counts via shared-memory atomics, written (not accumulated) at the end,

@@ -25,6 +25,7 @@ EXPORTS = [
     "hmpc_record_bytes", "hmpc_pack_records", "hmpc_create", "hmpc_destroy", "hmpc_last_error",
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
     "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
+    "hmpc_prepare_device", "hmpc_solve_batch_states",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -76,6 +77,10 @@ def lib() -> ctypes.CDLL:
         L.hmpc_solve_batch_ex.restype = ctypes.c_int
         L.hmpc_solve_device_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.hmpc_solve_device_ex.restype = ctypes.c_int
+        L.hmpc_prepare_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_prepare_device.restype = ctypes.c_int
+        L.hmpc_solve_batch_states.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+        L.hmpc_solve_batch_states.restype = ctypes.c_int
         L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hmpc_class_config.restype = ctypes.c_int
         _lib = L
@@ -202,6 +207,33 @@ class BatchedMPC:
         _check(lib().hmpc_solve_batch_ex(self._h, records.ctypes.data, B, wrench.ctypes.data, tau.ctypes.data, status.ctypes.data),
                allow_not_converged=not strict)
         return wrench, tau, status
+
+    def solve_batch_states(self, states: np.ndarray, strict: bool = True, torques: bool = False, out=None):
+        """Row f-1: `hmpc_state_t` records in, data preparation on the device.  -> (wrench, [tau,] status)."""
+        from .scenarios import STATE_DTYPE
+
+        if states.dtype != STATE_DTYPE or not states.flags.c_contiguous:
+            states = np.ascontiguousarray(states, dtype=STATE_DTYPE)
+        B = states.shape[0]
+        if out is not None:
+            wrench, status = out
+            assert wrench.dtype == np.float64 and wrench.shape == (B, 12 * self.horizon) and wrench.flags.c_contiguous
+            assert status.dtype == np.int32 and status.shape == (B,)
+        else:
+            wrench = np.zeros((B, 12 * self.horizon), dtype=np.float64)
+            status = np.zeros(B, dtype=np.int32)
+        tau = np.zeros((B, 10), dtype=np.float64) if torques else None
+        _check(lib().hmpc_solve_batch_states(self._h, states.ctypes.data, B, wrench.ctypes.data,
+                                             tau.ctypes.data if torques else None, status.ctypes.data),
+               allow_not_converged=not strict)
+        return (wrench, tau, status) if torques else (wrench, status)
+
+    def prepare_device(self, d_states, B: int, d_records, stream=None) -> None:
+        """Row f-1 on device-resident data: torch uint8 [B,352] states -> packed records [B,stride]."""
+        import torch
+
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _check(lib().hmpc_prepare_device(self._h, d_states.data_ptr(), B, d_records.data_ptr(), ctypes.c_void_p(st)))
 
     def solve_device(self, d_records, B: int, d_wrench, d_status, stream=None) -> None:
         """Device-resident path.  Arguments are torch CUDA tensors (uint8 [B,stride], f32 [B,12N], i32 [B])."""

@@ -164,7 +164,11 @@ def boundary_inputs(pos, rpy, vel, omega, raw_joints, gait_table, horizon: int =
             traj[12 * i + 3] = (traj_initial[3] if v_des_world[0] == 0 else pos[0]) + i * DT_MPC * v_des_world[0]
             traj[12 * i + 4] = (traj_initial[4] if v_des_world[1] == 0 else pos[1]) + i * DT_MPC * v_des_world[1]
             traj[12 * i + 2] = traj_initial[2] if yaw_rate == 0 else yaw + i * DT_MPC * yaw_rate
-    return dict(p_foot=np.array(p_foot), q_leg=q_leg.reshape(10).copy(), rBody=R.T.copy(),  # LegController's angles / world->body (row f-2 inputs)
+    leg_p = np.array([R.T @ (p_foot[i] - pos) - hip_yaw_location(i) for i in range(2)]) if feet_world is not None \
+        else np.array([leg_fk(q_leg[i], i) for i in range(2)])
+    return dict(leg_p=leg_p, rpy_est=est_rpy.copy(), wpd=np.array([pos[0] + pos_des_err[0], pos[1] + pos_des_err[1]]),
+                state_des=np.array([roll_pitch_des[0], roll_pitch_des[1], v_des_body[0], v_des_body[1], yaw_rate]),
+                p_foot=np.array(p_foot), q_leg=q_leg.reshape(10).copy(), rBody=R.T.copy(),  # LegController's angles / world->body (row f-2 inputs)
                 p=pos.copy(), v=vel.copy(), q=quat, w=omega.copy(), r=r, joint_angles=q, yaw=float(yaw),
                 weights=MPC_WEIGHTS.copy(), state_trajectory=traj, Alpha_K=MPC_ALPHA.copy(),
                 gait=np.asarray(gait_table, dtype=np.int32).copy())
@@ -179,6 +183,30 @@ def to_record(b: dict, horizon: int, out: np.ndarray | None = None) -> np.ndarra
     rec["Alpha_K"] = b["Alpha_K"]
     rec["gait"][: 2 * horizon] = b["gait"]
     return rec
+
+
+# numpy mirror of `hmpc_state_t` (include/hector_mpc_b200.h): what updateMPCIfNeeded reads, before any data preparation
+STATE_DTYPE = np.dtype([("position", "<f8", 3), ("vWorld", "<f8", 3), ("orientation", "<f8", 4), ("omegaWorld", "<f8", 3),
+                        ("rpy", "<f8", 3), ("leg_q", "<f8", 10), ("leg_p", "<f8", 6), ("state_des", "<f8", 5),
+                        ("world_position_desired", "<f8", 2), ("gait", "u1", K_MAX_GAIT_SEGMENTS), ("pad", "u1", 4)])
+assert STATE_DTYPE.itemsize == 352
+
+
+def to_state(b: dict, horizon: int, out: np.ndarray | None = None) -> np.ndarray:
+    """The caller-side state of one robot (row f-1 input) for the same tick as `to_record(b)`."""
+    st = np.zeros((), dtype=STATE_DTYPE) if out is None else out
+    st["position"], st["vWorld"], st["orientation"], st["omegaWorld"] = b["p"], b["v"], b["q"], b["w"]
+    st["rpy"], st["leg_q"], st["leg_p"] = b["rpy_est"], b["q_leg"], b["leg_p"].reshape(6)
+    st["state_des"], st["world_position_desired"] = b["state_des"], b["wpd"]
+    st["gait"][: 2 * horizon] = b["gait"]
+    return st
+
+
+def make_states(inputs, horizon: int = 10) -> np.ndarray:
+    out = np.zeros(len(inputs), dtype=STATE_DTYPE)
+    for i, b in enumerate(inputs):
+        to_state(b, horizon, out[i])
+    return out
 
 
 def stand_inputs(horizon: int = 10) -> dict:

@@ -153,6 +153,32 @@ HMPC_EXTERNC int hmpc_solve_batch_ex(hmpc_ctx* ctx, const struct update_data_t* 
 HMPC_EXTERNC int hmpc_solve_device_ex(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench, int* d_status,
                                       float* d_tau, void* stream);
 
+/* Row f-1: the caller's data preparation on the device.  `hmpc_state_t` is what
+ * ConvexMPCLocomotion::updateMPCIfNeeded reads before it builds the MPC inputs (ConvexMPCLocomotion.cpp:279-346),
+ * in double precision as the reference holds it; hmpc_prepare_device turns B of them into packed records (joint
+ * offsets + fmod, foot positions r, weights, the 12 x horizon reference trajectory, double -> float narrowing:
+ * ConvexMPCLocomotion.cpp:283-406 + convexMPC_interface.cpp:87-99) with one GPU thread per robot, so a tick moves
+ * 352 bytes per robot to the device instead of a 720-byte record.  hmpc_solve_batch_states = H2D of the states +
+ * hmpc_prepare_device + the solve of hmpc_solve_batch_ex. */
+struct hmpc_state_t
+{
+  double position[3];              /* seResult.position */
+  double vWorld[3];
+  double orientation[4];           /* (w,x,y,z) */
+  double omegaWorld[3];
+  double rpy[3];                   /* seResult.rpy */
+  double leg_q[10];                /* _legController->data[leg].q (LegController's own offset already applied) */
+  double leg_p[6];                 /* _legController->data[leg].p, [leg][xyz] */
+  double state_des[5];             /* stateDes[3], [4] (roll, pitch), [6], [7] (body-frame vx, vy), [11] (yaw rate) */
+  double world_position_desired[2];
+  unsigned char gait[K_MAX_GAIT_SEGMENTS]; /* mpcTable, [step][leg] */
+  unsigned char pad[4];
+};
+HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* ctx, const struct hmpc_state_t* d_states, int B, void* d_records,
+                                     void* stream);
+HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* ctx, const struct hmpc_state_t* in, int B, double* wrench_out,
+                                         double* tau_out, int* status);
+
 /* number of kernel launches hmpc_solve_device enqueues per call (classification pre-pass + one per size class) */
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
 /* launch configuration of size class `cls` (0 or 1): out[0..5] = threads per CTA, dynamic shared memory bytes,
