@@ -551,7 +551,7 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
 }
 
 static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_state_t* sin, int B, double* wrench_out,
-                            double* tau_out, int* status);
+                            double* tau_out, int* status, double dtMPC = 0.0);
 
 HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* c, const update_data_t* in, int B, double* wrench_out, int* status)
 {
@@ -566,26 +566,27 @@ HMPC_EXTERNC int hmpc_solve_batch_ex(hmpc_ctx* c, const update_data_t* in, int B
 
 static_assert(sizeof(hmpc_state_t) == 352 && offsetof(hmpc_state_t, gait) == 39 * 8, "hmpc_state_t layout (hmpc_prepare_kernel)");
 
-HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* c, const hmpc_state_t* d_states, int B, void* d_records, void* stream)
+HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* c, const hmpc_state_t* d_states, int B, double dtMPC, void* d_records,
+                                     void* stream)
 {
   if (!c || !d_states || !d_records || B < 0) { g_err = "hmpc_prepare_device: bad argument"; return HMPC_ERR_ARG; }
   if (B == 0) return HMPC_OK;
   CK(cudaSetDevice(c->device));
   hmpc::hmpc_prepare_kernel<<<(B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const unsigned char*>(d_states), B, c->horizon, (double)c->setup.dt,
+      reinterpret_cast<const unsigned char*>(d_states), B, c->horizon, dtMPC,
       static_cast<unsigned char*>(d_records), c->rec_stride);
   CK(cudaGetLastError());
   return HMPC_OK;
 }
 
-HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* c, const hmpc_state_t* in, int B, double* wrench_out, double* tau_out,
-                                         int* status)
+HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* c, const hmpc_state_t* in, int B, double dtMPC, double* wrench_out,
+                                         double* tau_out, int* status)
 {
-  return solve_batch_impl(c, nullptr, in, B, wrench_out, tau_out, status);
+  return solve_batch_impl(c, nullptr, in, B, wrench_out, tau_out, status, dtMPC);
 }
 
 static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_state_t* sin, int B, double* wrench_out,
-                            double* tau_out, int* status)
+                            double* tau_out, int* status, double dtMPC)
 {
   if (!c || (!in && !sin) || !wrench_out || B < 0 || B > c->max_batch) {
     g_err = "hmpc_solve_batch: bad argument (null pointer or batch > capacity)";
@@ -618,7 +619,7 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
       memcpy(c->h_states + (size_t)b0 * sb, sin + b0, (size_t)nb * sb);
       if (trace) tr[ntr++] = now();
       CK(cudaMemcpyAsync(c->d_states + (size_t)b0 * sb, c->h_states + (size_t)b0 * sb, (size_t)nb * sb, cudaMemcpyHostToDevice, sts[k]));
-      rc = hmpc_prepare_device(c, reinterpret_cast<const hmpc_state_t*>(c->d_states + (size_t)b0 * sb), nb,
+      rc = hmpc_prepare_device(c, reinterpret_cast<const hmpc_state_t*>(c->d_states + (size_t)b0 * sb), nb, dtMPC,
                                c->d_rec + (size_t)b0 * c->rec_stride, sts[k]);
       if (rc != HMPC_OK) return rc;
     } else {

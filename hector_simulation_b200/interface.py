@@ -77,9 +77,9 @@ def lib() -> ctypes.CDLL:
         L.hmpc_solve_batch_ex.restype = ctypes.c_int
         L.hmpc_solve_device_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.hmpc_solve_device_ex.restype = ctypes.c_int
-        L.hmpc_prepare_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_prepare_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
         L.hmpc_prepare_device.restype = ctypes.c_int
-        L.hmpc_solve_batch_states.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+        L.hmpc_solve_batch_states.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double] + [ctypes.c_void_p] * 3
         L.hmpc_solve_batch_states.restype = ctypes.c_int
         L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hmpc_class_config.restype = ctypes.c_int
@@ -208,7 +208,7 @@ class BatchedMPC:
                allow_not_converged=not strict)
         return wrench, tau, status
 
-    def solve_batch_states(self, states: np.ndarray, strict: bool = True, torques: bool = False, out=None):
+    def solve_batch_states(self, states: np.ndarray, strict: bool = True, torques: bool = False, out=None, dt_mpc: float = 0.04):
         """Row f-1: `hmpc_state_t` records in, data preparation on the device.  -> (wrench, [tau,] status)."""
         from .scenarios import STATE_DTYPE
 
@@ -223,17 +223,17 @@ class BatchedMPC:
             wrench = np.zeros((B, 12 * self.horizon), dtype=np.float64)
             status = np.zeros(B, dtype=np.int32)
         tau = np.zeros((B, 10), dtype=np.float64) if torques else None
-        _check(lib().hmpc_solve_batch_states(self._h, states.ctypes.data, B, wrench.ctypes.data,
+        _check(lib().hmpc_solve_batch_states(self._h, states.ctypes.data, B, dt_mpc, wrench.ctypes.data,
                                              tau.ctypes.data if torques else None, status.ctypes.data),
                allow_not_converged=not strict)
         return (wrench, tau, status) if torques else (wrench, status)
 
-    def prepare_device(self, d_states, B: int, d_records, stream=None) -> None:
+    def prepare_device(self, d_states, B: int, d_records, stream=None, dt_mpc: float = 0.04) -> None:
         """Row f-1 on device-resident data: torch uint8 [B,352] states -> packed records [B,stride]."""
         import torch
 
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        _check(lib().hmpc_prepare_device(self._h, d_states.data_ptr(), B, d_records.data_ptr(), ctypes.c_void_p(st)))
+        _check(lib().hmpc_prepare_device(self._h, d_states.data_ptr(), B, dt_mpc, d_records.data_ptr(), ctypes.c_void_p(st)))
 
     def solve_device(self, d_records, B: int, d_wrench, d_status, stream=None) -> None:
         """Device-resident path.  Arguments are torch CUDA tensors (uint8 [B,stride], f32 [B,12N], i32 [B])."""

@@ -174,10 +174,12 @@ struct hmpc_state_t
   unsigned char gait[K_MAX_GAIT_SEGMENTS]; /* mpcTable, [step][leg] */
   unsigned char pad[4];
 };
-HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* ctx, const struct hmpc_state_t* d_states, int B, void* d_records,
-                                     void* stream);
-HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* ctx, const struct hmpc_state_t* in, int B, double* wrench_out,
-                                         double* tau_out, int* status);
+/* dtMPC is the caller's double `dt * iterationsBetweenMPC` (ConvexMPCLocomotion.cpp:20) used for the trajectory;
+ * the QP itself keeps the float dt of hmpc_set_problem, exactly as the reference splits the two. */
+HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* ctx, const struct hmpc_state_t* d_states, int B, double dtMPC,
+                                     void* d_records, void* stream);
+HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* ctx, const struct hmpc_state_t* in, int B, double dtMPC,
+                                         double* wrench_out, double* tau_out, int* status);
 
 /* number of kernel launches hmpc_solve_device enqueues per call (classification pre-pass + one per size class) */
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
