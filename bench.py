@@ -386,6 +386,34 @@ def main():
         line["e2e_states"] = {"value": B * K / dt_states, "unit": UNIT, "ms_per_step": dt_states / K * 1e3,
                               "h2d_bytes_per_step": int(B * scenarios.STATE_DTYPE.itemsize), "d2h_bytes_per_step": int(B * (48 * N + 4)),
                               "note": "hmpc_solve_batch_states: updateMPCIfNeeded's data preparation on the device (SURVEY 8f row f-1)"}
+        # BASELINE configs[4]: 4096 robots, 200 consecutive ticks, closed loop resident on the device (row f-3):
+        # per tick prepare -> classify -> solve -> advance, nothing crosses PCIe inside the timed region
+        try:
+            Bc, Tc = 4096, 200
+            _, cin = scenarios.make_batch(5, Bc, horizon=N, seed=4242)
+            cst, clo = scenarios.make_rollout(cin, N)
+            mpc5 = interface.BatchedMPC(Bc, N, device=local_rank)
+            h_st = torch.from_numpy(cst.view(np.uint8).reshape(Bc, -1).copy())
+            h_lo = torch.from_numpy(clo.view(np.uint8).reshape(Bc, -1).copy())
+            d_cst, d_clo = h_st.cuda(), h_lo.cuda()
+            mpc5.rollout_device(d_cst, d_clo, Bc, 10)  # warm-up ticks
+            d_cst.copy_(h_st); d_clo.copy_(h_lo)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            mpc5.rollout_device(d_cst, d_clo, Bc, Tc)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            ms5 = c0.elapsed_time(c1)
+            lo5 = d_clo.cpu().numpy().view(scenarios.ROLLOUT_DTYPE).reshape(Bc)
+            z5 = d_cst.cpu().numpy().view(scenarios.STATE_DTYPE).reshape(Bc)["position"][:, 2]
+            line["closed_loop"] = {"workload": "configs[4]: batch=4096 walking robots, 200 consecutive ticks, cold start each tick, loop resident on the device",
+                                   "value": Bc * Tc / (ms5 * 1e-3), "unit": UNIT, "ms_per_tick": ms5 / Tc, "failures": int(lo5["failures"].sum()),
+                                   "mean_working_set_changes": float(lo5["iters_total"].sum() / lo5["ticks"].sum()),
+                                   "body_height_min_max": [float(z5.min()), float(z5.max())]}
+            mpc5.close()
+        except Exception as e:
+            line["closed_loop"] = {"unavailable": str(e)}
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import oracle_py as O

@@ -579,6 +579,37 @@ HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* c, const hmpc_state_t* d_states, 
   return HMPC_OK;
 }
 
+static_assert(sizeof(hmpc_rollout_t) == 80 && offsetof(hmpc_rollout_t, gait_offset) == 48, "hmpc_rollout_t layout (hmpc_advance_kernel)");
+
+HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* c, hmpc_state_t* d_states, hmpc_rollout_t* d_loop, int B, int ticks,
+                                     double dtMPC, float* d_wrench_log, void* d_record_log, void* stream)
+{
+  if (!c || !d_states || !d_loop || B < 0 || B > c->max_batch || ticks < 1) {
+    g_err = "hmpc_rollout_device: bad argument (null pointer, batch > capacity or ticks < 1)";
+    return HMPC_ERR_ARG;
+  }
+  if (B == 0) return HMPC_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nw = (size_t)12 * c->horizon;
+  float* dw = reinterpret_cast<float*>(c->d_out);  // the context's own result area is the loop's scratch
+  int* ds = reinterpret_cast<int*>(c->d_out + (size_t)c->max_batch * nw * 4);
+  for (int t = 0; t < ticks; t++) {
+    int rc = hmpc_prepare_device(c, d_states, B, dtMPC, c->d_rec, st);
+    if (rc != HMPC_OK) return rc;
+    if (d_record_log)
+      CK(cudaMemcpyAsync(static_cast<unsigned char*>(d_record_log) + (size_t)t * B * c->rec_stride, c->d_rec,
+                         (size_t)B * c->rec_stride, cudaMemcpyDeviceToDevice, st));
+    rc = enqueue_solve(c, c->d_rec, B, dw, nullptr, ds, st, 0, nullptr);
+    if (rc != HMPC_OK) return rc;
+    hmpc::hmpc_advance_kernel<<<(B + 63) / 64, 64, 0, st>>>(reinterpret_cast<unsigned char*>(d_states),
+                                                            reinterpret_cast<unsigned char*>(d_loop), B, c->horizon, dtMPC, dw, ds,
+                                                            d_wrench_log ? d_wrench_log + (size_t)t * B * 12 : nullptr);
+    CK(cudaGetLastError());
+  }
+  return HMPC_OK;
+}
+
 HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* c, const hmpc_state_t* in, int B, double dtMPC, double* wrench_out,
                                          double* tau_out, int* status)
 {

@@ -598,6 +598,120 @@ __global__ void hmpc_prepare_kernel(const unsigned char* states, int batch, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// row f-3: advance every robot by one MPC tick after a solve (one thread per robot, plain fp64).
+//   states  hmpc_state_t [batch] (352 B)      loop  hmpc_rollout_t [batch] (80 B)
+//   wrench  float [batch][12N] (solution)      status int [batch]
+// Plant: the single rigid body of SolverMPC.cpp:312-331 integrated with forward Euler (SolverMPC.cpp:145-146), feet
+// pinned in the world.  Gait: GaitGenerator.cpp:85-103.  Touch-down placement: ConvexMPCLocomotion.cpp:119-160.
+// ------------------------------------------------------------------------------------------------
+__device__ inline int gait_contact(int it, int N, int offset, int duration)
+{
+  int progress = it % N - offset;
+  if (progress < 0) progress += N;
+  return progress < duration ? 1 : 0;
+}
+__device__ inline void quat_to_R_f64(const double* qt, double* R)
+{
+  const double e0 = qt[0], e1 = qt[1], e2 = qt[2], e3 = qt[3];
+  R[0] = DS(1.0, DM(2.0, DA(DM(e2, e2), DM(e3, e3)))); R[1] = DM(2.0, DS(DM(e1, e2), DM(e0, e3))); R[2] = DM(2.0, DA(DM(e1, e3), DM(e0, e2)));
+  R[3] = DM(2.0, DA(DM(e1, e2), DM(e0, e3))); R[4] = DS(1.0, DM(2.0, DA(DM(e1, e1), DM(e3, e3)))); R[5] = DM(2.0, DS(DM(e2, e3), DM(e0, e1)));
+  R[6] = DM(2.0, DS(DM(e1, e3), DM(e0, e2))); R[7] = DM(2.0, DA(DM(e2, e3), DM(e0, e1))); R[8] = DS(1.0, DM(2.0, DA(DM(e1, e1), DM(e2, e2))));
+}
+__global__ void hmpc_advance_kernel(unsigned char* states, unsigned char* loop, int batch, int N, double dtMPC,
+                                    const float* wrench, const int* status, float* wrench_log)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  double* s = reinterpret_cast<double*>(states + (size_t)i * 352);
+  unsigned char* gait = states + (size_t)i * 352 + 39 * 8;
+  double* feet = reinterpret_cast<double*>(loop + (size_t)i * 80);
+  int* li = reinterpret_cast<int*>(loop + (size_t)i * 80 + 48);  // offset[2] duration[2] iteration failures iters ticks
+  double* pos = s; double* vw = s + 3; double* qt = s + 6; double* ow = s + 10; double* rpy = s + 13;
+  double* lp = s + 26; const double* sd = s + 32; double* wpd = s + 37;
+  double u[12];
+  for (int k = 0; k < 12; k++) u[k] = (double)wrench[(size_t)i * 12 * N + k];
+  if (wrench_log) for (int k = 0; k < 12; k++) wrench_log[(size_t)i * 12 + k] = wrench[(size_t)i * 12 * N + k];
+  const int stw = status[i];
+  li[5] += ((stw & 0xFF) != 0);
+  li[6] += (stw >> 8) & 0xFFF;
+  li[7] += 1;
+  double R[9];
+  quat_to_R_f64(qt, R);
+  // commanded velocity in the world and the position set-point (ConvexMPCLocomotion.cpp:46-56, 338-346)
+  double vdw[3];
+  for (int a = 0; a < 3; a++) vdw[a] = R[a * 3] * sd[2] + R[a * 3 + 1] * sd[3];
+  for (int a = 0; a < 2; a++) {
+    double w = wpd[a];
+    if (w - pos[a] > 0.05) w = pos[a] + 0.05;
+    if (pos[a] - w > 0.05) w = pos[a] - 0.05;
+    wpd[a] = w + dtMPC * vdw[a];
+  }
+  // rigid body: torque about the CoM and net force of the two foot wrenches [F0 F1 M0 M1]
+  double tq[3] = {u[6] + u[9], u[7] + u[10], u[8] + u[11]};
+  for (int leg = 0; leg < 2; leg++) {
+    const double rx = feet[3 * leg] - pos[0], ry = feet[3 * leg + 1] - pos[1], rz = feet[3 * leg + 2] - pos[2];
+    const double fx = u[3 * leg], fy = u[3 * leg + 1], fz = u[3 * leg + 2];
+    tq[0] += ry * fz - rz * fy;
+    tq[1] += rz * fx - rx * fz;
+    tq[2] += rx * fy - ry * fx;
+  }
+  // world inertia R I R^T and its inverse applied to the torque:  I_w^-1 tq = R I^-1 R^T tq
+  const double Iinv[3] = {1.0 / 0.5413, 1.0 / 0.5200, 1.0 / 0.0691};  // RobotState.cpp:45
+  double tb[3], dw[3];
+  for (int a = 0; a < 3; a++) tb[a] = (R[a] * tq[0] + R[3 + a] * tq[1] + R[6 + a] * tq[2]) * Iinv[a];
+  for (int a = 0; a < 3; a++) dw[a] = R[a * 3] * tb[0] + R[a * 3 + 1] * tb[1] + R[a * 3 + 2] * tb[2];
+  // Euler-angle rates: rpy' = E^-1 omega, E = [[cy cp, -sy, 0], [sy cp, cy, 0], [-sp, 0, 1]]
+  double sy, cy, sp, cp;
+  sincos(rpy[2], &sy, &cy);
+  sincos(rpy[1], &sp, &cp);
+  const double a0 = (cy * ow[0] + sy * ow[1]) / cp;     // roll rate
+  const double a1 = -sy * ow[0] + cy * ow[1];           // pitch rate
+  const double a2 = ow[2] + sp * a0;                    // yaw rate
+  const double mass = 9.0;                              // SolverMPC.cpp:423
+  const double nrpy[3] = {rpy[0] + dtMPC * a0, rpy[1] + dtMPC * a1, rpy[2] + dtMPC * a2};
+  const double np_[3] = {pos[0] + dtMPC * vw[0], pos[1] + dtMPC * vw[1], pos[2] + dtMPC * vw[2]};
+  const double nw[3] = {ow[0] + dtMPC * dw[0], ow[1] + dtMPC * dw[1], ow[2] + dtMPC * dw[2]};
+  const double nv[3] = {vw[0] + dtMPC * ((u[0] + u[3]) / mass), vw[1] + dtMPC * ((u[1] + u[4]) / mass),
+                        vw[2] + dtMPC * ((u[2] + u[5]) / mass - 9.81)};
+  for (int a = 0; a < 3; a++) { rpy[a] = nrpy[a]; pos[a] = np_[a]; ow[a] = nw[a]; vw[a] = nv[a]; }
+  // orientation quaternion of the new Euler angles (ori::rpyToQuat: yaw * pitch * roll)
+  double sr, cr, spp, cpp, syy, cyy;
+  sincos(nrpy[0] * 0.5, &sr, &cr);
+  sincos(nrpy[1] * 0.5, &spp, &cpp);
+  sincos(nrpy[2] * 0.5, &syy, &cyy);
+  qt[0] = cyy * cpp * cr + syy * spp * sr;
+  qt[1] = cyy * cpp * sr - syy * spp * cr;
+  qt[2] = cyy * spp * cr + syy * cpp * sr;
+  qt[3] = syy * cpp * cr - cyy * spp * sr;
+  quat_to_R_f64(qt, R);
+  // next tick's contact table; a leg that goes swing -> stance is placed
+  const int it = li[4] + 1;
+  li[4] = it;
+  for (int leg = 0; leg < 2; leg++) {
+    const int was = gait[leg];
+    const int now = gait_contact(it, N, li[leg], li[2 + leg]);
+    if (!was && now) {
+      const double hip[3] = {-0.005, leg == 0 ? -0.057 : 0.057, -0.126};
+      const double stance_t = 0.5 * (double)li[2 + leg] * dtMPC;
+      for (int a = 0; a < 2; a++) {
+        double rel = nv[a] * stance_t + 0.02 * (nv[a] - vdw[a]);
+        rel = fmin(fmax(rel, -0.4), 0.4);
+        feet[3 * leg + a] = np_[a] + R[a * 3] * hip[0] + R[a * 3 + 1] * hip[1] + R[a * 3 + 2] * hip[2] + rel;
+      }
+      feet[3 * leg + 2] = 0.0;
+    }
+  }
+  for (int st = 0; st < N; st++)
+    for (int leg = 0; leg < 2; leg++) gait[2 * st + leg] = (unsigned char)gait_contact(it + st, N, li[leg], li[2 + leg]);
+  // leg-frame foot positions the next preparation will read: p = rBody (pFoot - position) - hip
+  for (int leg = 0; leg < 2; leg++) {
+    const double hip[3] = {-0.005, leg == 0 ? -0.057 : 0.057, -0.126};
+    const double d0 = feet[3 * leg] - np_[0], d1 = feet[3 * leg + 1] - np_[1], d2 = feet[3 * leg + 2] - np_[2];
+    for (int a = 0; a < 3; a++) lp[3 * leg + a] = R[a] * d0 + R[3 + a] * d1 + R[6 + a] * d2 - hip[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // classification pre-pass: bucket instances by reduced size (number of stance (step,leg) blocks)
 // ------------------------------------------------------------------------------------------------
 // single-block variant (batch <= 1024): counts via shared-memory atomics, written (not accumulated) at the end,

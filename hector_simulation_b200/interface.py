@@ -25,7 +25,7 @@ EXPORTS = [
     "hmpc_record_bytes", "hmpc_pack_records", "hmpc_create", "hmpc_destroy", "hmpc_last_error",
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
     "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
-    "hmpc_prepare_device", "hmpc_solve_batch_states",
+    "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -81,6 +81,9 @@ def lib() -> ctypes.CDLL:
         L.hmpc_prepare_device.restype = ctypes.c_int
         L.hmpc_solve_batch_states.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double] + [ctypes.c_void_p] * 3
         L.hmpc_solve_batch_states.restype = ctypes.c_int
+        L.hmpc_rollout_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_rollout_device.restype = ctypes.c_int
         L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hmpc_class_config.restype = ctypes.c_int
         _lib = L
@@ -140,6 +143,21 @@ def pack_records(records: np.ndarray, horizon: int) -> np.ndarray:
     records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
     out = np.zeros((records.shape[0], record_bytes(horizon)), dtype=np.uint8)
     _check(lib().hmpc_pack_records(records.ctypes.data, records.shape[0], horizon, out.ctypes.data))
+    return out
+
+
+def unpack_records(packed: np.ndarray, horizon: int) -> np.ndarray:
+    """Inverse of pack_records (numpy): packed device records -> `update_data_t` records, e.g. to hand what a device
+    loop logged to another consumer of the reference's record format."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint8).reshape(-1, record_bytes(horizon))
+    n = packed.shape[0]
+    f = packed[:, : (54 + 12 * horizon) * 4].copy().view(np.float32)
+    out = np.zeros(n, dtype=UPDATE_DTYPE)
+    out["p"], out["v"], out["q"], out["w"], out["r"] = f[:, 0:3], f[:, 3:6], f[:, 6:10], f[:, 10:13], f[:, 13:19]
+    out["joint_angles"], out["yaw"], out["weights"], out["Alpha_K"] = f[:, 19:29], f[:, 29], f[:, 30:42], f[:, 42:54]
+    out["traj"][:, : 12 * horizon] = f[:, 54: 54 + 12 * horizon]
+    g0 = (54 + 12 * horizon) * 4
+    out["gait"][:, : 2 * horizon] = packed[:, g0: g0 + 2 * horizon]
     return out
 
 
@@ -234,6 +252,17 @@ class BatchedMPC:
 
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         _check(lib().hmpc_prepare_device(self._h, d_states.data_ptr(), B, dt_mpc, d_records.data_ptr(), ctypes.c_void_p(st)))
+
+    def rollout_device(self, d_states, d_loop, B: int, ticks: int, d_wrench_log=None, d_record_log=None, stream=None,
+                       dt_mpc: float = 0.04) -> None:
+        """Row f-3: `ticks` closed-loop ticks (prepare -> solve -> advance) enqueued on one stream, no host in the
+        loop.  torch CUDA tensors: states uint8 [B,352], loop uint8 [B,80], logs f32 [ticks,B,12] / uint8 [ticks,B,stride]."""
+        import torch
+
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _check(lib().hmpc_rollout_device(self._h, d_states.data_ptr(), d_loop.data_ptr(), B, ticks, dt_mpc,
+                                         d_wrench_log.data_ptr() if d_wrench_log is not None else None,
+                                         d_record_log.data_ptr() if d_record_log is not None else None, ctypes.c_void_p(st)))
 
     def solve_device(self, d_records, B: int, d_wrench, d_status, stream=None) -> None:
         """Device-resident path.  Arguments are torch CUDA tensors (uint8 [B,stride], f32 [B,12N], i32 [B])."""

@@ -209,6 +209,94 @@ def make_states(inputs, horizon: int = 10) -> np.ndarray:
     return out
 
 
+# numpy mirror of `hmpc_rollout_t` (include/hector_mpc_b200.h): per-robot state of the device-resident closed loop
+ROLLOUT_DTYPE = np.dtype([("feet_world", "<f8", 6), ("gait_offset", "<i4", 2), ("gait_duration", "<i4", 2),
+                          ("iteration", "<i4"), ("failures", "<i4"), ("iters_total", "<i4"), ("ticks", "<i4")])
+assert ROLLOUT_DTYPE.itemsize == 80
+
+
+def make_rollout(inputs, horizon: int = 10, standing=None, phases=None):
+    """-> (states, loop) for hmpc_rollout_device: robot i walks from gait iteration phases[i] (default i mod horizon)
+    unless standing[i]; its feet are pinned where `inputs[i]` has them."""
+    n = len(inputs)
+    loop = np.zeros(n, dtype=ROLLOUT_DTYPE)
+    half = horizon // 2
+    for i, b in enumerate(inputs):
+        loop["feet_world"][i] = np.asarray(b["p_foot"]).reshape(6)
+        if standing is not None and standing[i]:
+            loop["gait_offset"][i], loop["gait_duration"][i], loop["iteration"][i] = (0, 0), (horizon, horizon), 0
+        else:
+            loop["gait_offset"][i], loop["gait_duration"][i] = (0, half), (half, horizon - half)
+            loop["iteration"][i] = (i % horizon) if phases is None else phases[i]
+    states = make_states(inputs, horizon)
+    for i in range(n):  # the table must be the one of the loop's iteration counter; a standing robot has no velocity command
+        if standing is not None and standing[i]:
+            states["state_des"][i] = 0.0
+        states["gait"][i, : 2 * horizon] = mpc_gait(horizon, loop["gait_offset"][i], loop["gait_duration"][i], int(loop["iteration"][i]))
+    return states, loop
+
+
+I_BODY_DIAG = np.array([0.5413, 0.5200, 0.0691])  # RobotState.cpp:45
+BODY_MASS = 9.0                                    # SolverMPC.cpp:423
+
+
+def advance_numpy(states: np.ndarray, loop: np.ndarray, wrench: np.ndarray, status: np.ndarray, horizon: int,
+                  dt: float = DT_MPC) -> None:
+    """In-place numpy mirror of hmpc_advance_kernel (csrc/hmpc_device.cuh): one closed-loop tick for every robot."""
+    N = horizon
+    for i in range(len(states)):
+        st, lo = states[i], loop[i]
+        u = np.asarray(wrench[i][:12], dtype=np.float64)
+        lo["failures"] += int((int(status[i]) & 0xFF) != 0)
+        lo["iters_total"] += (int(status[i]) >> 8) & 0xFFF
+        lo["ticks"] += 1
+        pos, vw, ow, rpy = st["position"].copy(), st["vWorld"].copy(), st["omegaWorld"].copy(), st["rpy"].copy()
+        R = quat_to_R(st["orientation"])
+        feet = lo["feet_world"].reshape(2, 3)
+        vdw = R[:, 0] * st["state_des"][2] + R[:, 1] * st["state_des"][3]
+        for a in range(2):
+            w = st["world_position_desired"][a]
+            if w - pos[a] > 0.05:
+                w = pos[a] + 0.05
+            if pos[a] - w > 0.05:
+                w = pos[a] - 0.05
+            st["world_position_desired"][a] = w + dt * vdw[a]
+        tq = u[6:9] + u[9:12]
+        for leg in range(2):
+            tq = tq + np.cross(feet[leg] - pos, u[3 * leg: 3 * leg + 3])
+        dw = R @ ((R.T @ tq) / I_BODY_DIAG)
+        sy, cy, sp, cp = np.sin(rpy[2]), np.cos(rpy[2]), np.sin(rpy[1]), np.cos(rpy[1])
+        a0 = (cy * ow[0] + sy * ow[1]) / cp
+        a1 = -sy * ow[0] + cy * ow[1]
+        a2 = ow[2] + sp * a0
+        nrpy = rpy + dt * np.array([a0, a1, a2])
+        npos = pos + dt * vw
+        nw = ow + dt * dw
+        nv = vw + dt * ((u[0:3] + u[3:6]) / BODY_MASS + np.array([0.0, 0.0, -9.81]))
+        st["rpy"], st["position"], st["omegaWorld"], st["vWorld"] = nrpy, npos, nw, nv
+        # (w,x,y,z) of yaw*pitch*roll, written like the kernel
+        sr, cr, spp, cpp, syy, cyy = (np.sin(nrpy[0] / 2), np.cos(nrpy[0] / 2), np.sin(nrpy[1] / 2), np.cos(nrpy[1] / 2),
+                                      np.sin(nrpy[2] / 2), np.cos(nrpy[2] / 2))
+        q = np.array([cyy * cpp * cr + syy * spp * sr, cyy * cpp * sr - syy * spp * cr,
+                      cyy * spp * cr + syy * cpp * sr, syy * cpp * cr - cyy * spp * sr])
+        st["orientation"] = q
+        R = quat_to_R(q)
+        it = int(lo["iteration"]) + 1
+        lo["iteration"] = it
+        new_table = mpc_gait(N, lo["gait_offset"], lo["gait_duration"], it % N)
+        for leg in range(2):
+            if st["gait"][leg] == 0 and new_table[leg] == 1:
+                hip = hip_yaw_location(leg)
+                stance_t = 0.5 * float(lo["gait_duration"][leg]) * dt
+                for a in range(2):
+                    rel = min(max(nv[a] * stance_t + 0.02 * (nv[a] - vdw[a]), -0.4), 0.4)
+                    feet[leg, a] = npos[a] + R[a] @ hip + rel
+                feet[leg, 2] = 0.0
+        st["gait"][: 2 * N] = new_table
+        for leg in range(2):
+            st["leg_p"][3 * leg: 3 * leg + 3] = R.T @ (feet[leg] - npos) - hip_yaw_location(leg)
+
+
 def stand_inputs(horizon: int = 10) -> dict:
     """Config 1: spawn pose, double support."""
     return boundary_inputs((0, 0, BODY_HEIGHT), (0, 0, 0), (0, 0, 0), (0, 0, 0), np.zeros(10),

@@ -181,6 +181,30 @@ HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* ctx, const struct hmpc_state_t* d
 HMPC_EXTERNC int hmpc_solve_batch_states(hmpc_ctx* ctx, const struct hmpc_state_t* in, int B, double dtMPC,
                                          double* wrench_out, double* tau_out, int* status);
 
+/* Row f-3: the closed loop on the device — BASELINE config 5 (consecutive ticks of the same robots).
+ * One tick = hmpc_prepare_device -> the solve -> hmpc_advance, all enqueued on one stream, no host in the loop:
+ *   - the next tick's contact table is Gait::mpc_gait of the advanced iteration counter (GaitGenerator.cpp:85-103);
+ *   - the body is integrated one forward-Euler step of the single rigid body the MPC predicts with
+ *     (SolverMPC.cpp:145-146, 312-331: x+ = x + dt f(x,u)), feet pinned in the world, first-step wrench fed back;
+ *   - a leg that touches down is placed by the heuristic of ConvexMPCLocomotion.cpp:119-160 (hip projection +
+ *     0.5 v T_stance + 0.02 (v - v_des), clamped, z = 0) — the swing trajectory itself is out of scope (row f-4);
+ *   - world_position_desired integrates the commanded velocity with the clamp write-back of :338-346.
+ * hmpc_rollout_t is the per-robot loop state that lives next to hmpc_state_t. */
+struct hmpc_rollout_t
+{
+  double feet_world[6];   /* [leg][xyz]: where each foot is pinned (stance) or was last pinned (swing) */
+  int gait_offset[2];     /* Gait(nIterations = horizon, offsets, durations)  (ConvexMPCLocomotion.cpp:16-17) */
+  int gait_duration[2];
+  int iteration;          /* MPC tick counter; Gait::_iteration = iteration % horizon */
+  int failures;           /* ticks whose solver status code was not 0 (accumulated) */
+  int iters_total;        /* working-set changes, accumulated */
+  int ticks;              /* ticks advanced so far */
+};
+/* ticks >= 1.  d_wrench_log: NULL or float [ticks][B][12] (first-step wrench of every tick); d_record_log: NULL or
+ * [ticks][B][hmpc_record_bytes] (the packed records the solver saw, for after-the-fact parity checks). */
+HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* ctx, struct hmpc_state_t* d_states, struct hmpc_rollout_t* d_loop, int B,
+                                     int ticks, double dtMPC, float* d_wrench_log, void* d_record_log, void* stream);
+
 /* number of kernel launches hmpc_solve_device enqueues per call (classification pre-pass + one per size class) */
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
 /* launch configuration of size class `cls` (0 or 1): out[0..5] = threads per CTA, dynamic shared memory bytes,
