@@ -144,6 +144,7 @@ struct hmpc_ctx {
   // B200 (its Schur-factor build costs more instructions than the ~10 iterations it saves), so off unless
   // HMPC_WARM_START=1; -1 = only for batches beyond one resident wave
   int warm_mode = 0;
+  int zero_copy_default = 0;  // host-buffer path reads/writes pinned host memory from the kernels (HMPC_ZEROCOPY overrides)
 };
 
 namespace {
@@ -460,14 +461,18 @@ void classify_host(const hmpc_ctx* c, const unsigned char* gait0, size_t gait_st
   }
 }
 
-int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, const int* h_block, float* d_wrench32, int* d_status,
-                            cudaStream_t st, int slot, float* d_tau)
+int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_block, float* d_wrench32, int* d_status,
+                            cudaStream_t st, int slot, float* d_tau, bool zero_copy)
 {
   int* d_block = c->d_lists + (size_t)slot * (4 + 3 * (size_t)c->max_batch);
   const int n0 = h_block[0], n1 = h_block[1];
-  // counts + class-0 list (+ class-1 list when it is not empty) in one copy
-  const size_t ints = (n1 > 0) ? (size_t)4 + c->max_batch + n1 : (size_t)4 + n0;
-  CK(cudaMemcpyAsync(d_block, h_block, ints * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (zero_copy) {
+    d_block = h_block;  // pinned + mapped: the kernels read the lists over PCIe, no copy launch
+  } else {
+    // counts + class-0 list (+ class-1 list when it is not empty) in one copy
+    const size_t ints = (n1 > 0) ? (size_t)4 + c->max_batch + n1 : (size_t)4 + n0;
+    CK(cudaMemcpyAsync(d_block, h_block, ints * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   for (int i = 0; i < 2; i++) {
     const int cnt = i == 0 ? n0 : n1;
     if (cnt == 0) continue;
@@ -633,6 +638,10 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
   if (!c->pool) nch = B >= 512 ? NCHUNK : (B >= 128 ? 2 : 1);
   if (nch_env >= 1 && nch_env <= NCHUNK) nch = nch_env;
   static const bool trace = getenv("HMPC_TRACE") != nullptr;
+  // zero-copy mode: the kernels read the packed records from, and write the results to, pinned host memory
+  // directly (UVA-mapped), so a tick has no copy launches at all
+  static const int zc_env = getenv("HMPC_ZEROCOPY") ? atoi(getenv("HMPC_ZEROCOPY")) : c->zero_copy_default;
+  const bool zc = zc_env != 0;
   double tr[4 * NCHUNK + 2];
   int ntr = 0;
   auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
@@ -649,8 +658,8 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
       const size_t sb = sizeof(hmpc_state_t);
       memcpy(c->h_states + (size_t)b0 * sb, sin + b0, (size_t)nb * sb);
       if (trace) tr[ntr++] = now();
-      CK(cudaMemcpyAsync(c->d_states + (size_t)b0 * sb, c->h_states + (size_t)b0 * sb, (size_t)nb * sb, cudaMemcpyHostToDevice, sts[k]));
-      rc = hmpc_prepare_device(c, reinterpret_cast<const hmpc_state_t*>(c->d_states + (size_t)b0 * sb), nb, dtMPC,
+      if (!zc) CK(cudaMemcpyAsync(c->d_states + (size_t)b0 * sb, c->h_states + (size_t)b0 * sb, (size_t)nb * sb, cudaMemcpyHostToDevice, sts[k]));
+      rc = hmpc_prepare_device(c, reinterpret_cast<const hmpc_state_t*>((zc ? c->h_states : c->d_states) + (size_t)b0 * sb), nb, dtMPC,
                                c->d_rec + (size_t)b0 * c->rec_stride, sts[k]);
       if (rc != HMPC_OK) return rc;
     } else {
@@ -664,19 +673,22 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
       }
       if (rc != HMPC_OK) return rc;
       if (trace) tr[ntr++] = now();
-      CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
-                         (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
+      if (!zc)
+        CK(cudaMemcpyAsync(c->d_rec + (size_t)b0 * c->rec_stride, c->h_rec + (size_t)b0 * c->rec_stride,
+                           (size_t)nb * c->rec_stride, cudaMemcpyHostToDevice, sts[k]));
     }
     const size_t ooff = (size_t)b0 * (nw * 4 + 4 + 40), obytes = (size_t)nb * (nw * 4 + 4 + (tau_out ? 40 : 0));
-    float* dw = reinterpret_cast<float*>(c->d_out + ooff);
-    int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
-    float* dt_ = tau_out ? reinterpret_cast<float*>(c->d_out + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
+    unsigned char* obase = zc ? c->h_out : c->d_out;
+    float* dw = reinterpret_cast<float*>(obase + ooff);
+    int* ds = reinterpret_cast<int*>(obase + ooff + (size_t)nb * nw * 4);
+    float* dt_ = tau_out ? reinterpret_cast<float*>(obase + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
+    const unsigned char* rbase = (zc && !sin) ? c->h_rec : c->d_rec;
     int* hblk = c->h_cls + (size_t)k * (4 + 3 * (size_t)c->max_batch);
     if (sin) classify_host(c, sin[b0].gait, sizeof(hmpc_state_t), nb, hblk);
     else classify_host(c, in[b0].gait, sizeof(update_data_t), nb, hblk);
-    rc = enqueue_solve_hostlists(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, hblk, dw, ds, sts[k], k, dt_);
+    rc = enqueue_solve_hostlists(c, rbase + (size_t)b0 * c->rec_stride, nb, hblk, dw, ds, sts[k], k, dt_, zc);
     if (rc != HMPC_OK) return rc;
-    CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, obytes, cudaMemcpyDeviceToHost, sts[k]));
+    if (!zc) CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, obytes, cudaMemcpyDeviceToHost, sts[k]));
     if (trace) tr[ntr++] = now();
   }
   bool all_ok = true;
@@ -691,13 +703,16 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
       bool overflow = false;
       for (int i = 0; i < nb; i++) overflow |= (HMPC_STATUS_CODE(hs[i]) == hmpc::ST_WS_CAP);
       if (overflow) {
-        float* dw = reinterpret_cast<float*>(c->d_out + ooff);
-        int* ds = reinterpret_cast<int*>(c->d_out + ooff + (size_t)nb * nw * 4);
-        float* dt_ = tau_out ? reinterpret_cast<float*>(c->d_out + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
-        int rc = enqueue_solve(c, c->d_rec + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k, dt_);
+        unsigned char* obase = zc ? c->h_out : c->d_out;
+        float* dw = reinterpret_cast<float*>(obase + ooff);
+        int* ds = reinterpret_cast<int*>(obase + ooff + (size_t)nb * nw * 4);
+        float* dt_ = tau_out ? reinterpret_cast<float*>(obase + ooff + (size_t)nb * (nw * 4 + 4)) : nullptr;
+        const unsigned char* rbase = (zc && !sin) ? c->h_rec : c->d_rec;
+        int rc = enqueue_solve(c, rbase + (size_t)b0 * c->rec_stride, nb, dw, nullptr, ds, sts[k], k, dt_);
         if (rc != HMPC_OK) return rc;
-        CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, (size_t)nb * (nw * 4 + 4 + (tau_out ? 40 : 0)),
-                           cudaMemcpyDeviceToHost, sts[k]));
+        if (!zc)
+          CK(cudaMemcpyAsync(c->h_out + ooff, c->d_out + ooff, (size_t)nb * (nw * 4 + 4 + (tau_out ? 40 : 0)),
+                             cudaMemcpyDeviceToHost, sts[k]));
         CK(cudaStreamSynchronize(sts[k]));
       }
     }
