@@ -47,64 +47,76 @@ def algorithmic_flops_per_qp(N: int, nv: float, k_iter: float) -> float:
     return f_asm + k_iter * f_it
 
 
+_SAMPLER_SRC = r"""
+import subprocess, sys, time
+gpu = int(sys.argv[1])
+names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(gpu)
+    mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+    bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+    def sample():
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        return float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx, [n for b, n in zip(bits, names) if r & b]
+    period = 0.004
+except Exception:
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def sample():
+        out = subprocess.run(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        return float(r[0]), float(r[1]), [names[i] for i in range(4) if r[2 + i].lower().startswith("active")]
+    period = 0.05
+print("ready", flush=True)
+while True:
+    try:
+        sm, mx_, rs = sample()
+        print("%.6f %.1f %.1f %s" % (time.monotonic(), sm, mx_, ",".join(rs)), flush=True)
+    except Exception:
+        pass
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region (NVML every 5 ms; nvidia-smi as fallback)."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML every ~4 ms; nvidia-smi as fallback).
+    Runs as a separate process so that sampling never contends with the timed host code for the interpreter
+    lock; samples carry CLOCK_MONOTONIC stamps and only those inside [start(), stop()] are kept."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.sm, self.reasons, self.max_sm = [], set(), None
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run_nvml(self) -> bool:
-        try:
-            import pynvml as nv
-
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
-            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-        except Exception:
-            return False
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.005)
-        return True
-
-    def _run(self):
-        if self._run_nvml():
-            return
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                r = [c.strip() for c in out.split(",")]
-                self.sm.append(float(r[0]))
-                self.max_sm = float(r[1])
-                self.reasons.update(names[i] for i in range(4) if r[2 + i].lower().startswith("active"))
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+        self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(gpu_index)], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True)
+        self.proc.stdout.readline()  # "ready": interpreter and NVML are up
+        self.t0 = None
 
     def start(self):
-        self._t.start()
+        self.t0 = time.monotonic()
 
     def stop(self) -> dict:
-        self._stop.set()
-        self._t.join(timeout=6)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        t1 = time.monotonic()
+        time.sleep(0.01)
+        self.proc.terminate()
+        out, _ = self.proc.communicate(timeout=10)
+        sm, reasons, mx = [], set(), None
+        for ln in out.splitlines():
+            f = ln.split(" ")
+            if len(f) < 3:
+                continue
+            try:
+                t, v, m = float(f[0]), float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = m
+            if self.t0 <= t <= t1:
+                sm.append(v)
+                if len(f) > 3 and f[3]:
+                    reasons.update(f[3].split(","))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def ncu_traffic_bytes():
@@ -273,6 +285,10 @@ def main():
     if world == 1:
         out_w = np.zeros((B, 12 * N), dtype=np.float64)  # caller-owned result buffers, reused every tick
         out_s = np.zeros(B, dtype=np.int32)
+        recs = np.ascontiguousarray(recs)
+        # a control loop reuses its record / result arrays every tick: registered once, hmpc_solve_batch lets the GPU
+        # read the update_data_t records and write the double wrenches in place (same bytes over PCIe, no staging)
+        mpc.pin(recs, out_w, out_s)
 
         def e2e_step():
             mpc.solve_batch(recs, out=(out_w, out_s))
@@ -341,7 +357,9 @@ def main():
         "latency_ms": {"batch_p50": float(np.percentile(step_ms, 50)), "batch_p99": p99_step_ms,
                        "note": "device time for the whole 1024-robot batch; every robot's result is ready within it"},
         "solver": {"mean_working_set_changes": k_mean, "max": int(iters.max())},
-        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int((world * B * 48 * N + B * 4) if world > 1 else B * (48 * N + 4)),
+        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int((world * B * 48 * N + B * 4) if world > 1 else B * (96 * N + 4)),
+                "transfer": ("pack + H2D copy + all_gather + D2H copy" if world > 1 else
+                             "in place: kernels gather the live 720 B of every host update_data_t over PCIe and store double wrenches + status into the caller's registered arrays"),
                 "ms_per_step": e2e_ms / K, "latency_ms_p99": float(np.percentile(e2e_lat, 99) * 1e3)},
         "gpu_launches": int(K * mpc.launches_per_solve),  # per step: 1 classification kernel + 1 solve kernel per size class
         "launch_config": {"class0": mpc.class_config(0), "class1": mpc.class_config(1)},

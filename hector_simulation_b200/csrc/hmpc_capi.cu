@@ -6,6 +6,7 @@
 
 #include <chrono>
 #include <cstddef>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -144,7 +145,19 @@ struct hmpc_ctx {
   // B200 (its Schur-factor build costs more instructions than the ~10 iterations it saves), so off unless
   // HMPC_WARM_START=1; -1 = only for batches beyond one resident wave
   int warm_mode = 0;
-  int zero_copy_default = 0;  // host-buffer path reads/writes pinned host memory from the kernels (HMPC_ZEROCOPY overrides)
+  // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
+  // reference records from them and write results to them in place (no packing, no staging copies, no widening)
+  struct Pin { char* base; size_t bytes; };   // what the caller asked for
+  struct Run { uintptr_t lo, hi; };           // page runs actually registered with CUDA (arrays may share pages)
+  std::vector<Pin> pins;
+  std::vector<Run> runs;
+  bool pinned(const void* p, size_t bytes) const
+  {
+    const char* q = static_cast<const char*>(p);
+    for (const Pin& r : pins)
+      if (q >= r.base && q + bytes <= r.base + r.bytes) return true;
+    return false;
+  }
 };
 
 namespace {
@@ -306,6 +319,9 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
+  for (const hmpc_ctx::Run& r : c->runs) cudaHostUnregister(reinterpret_cast<void*>(r.lo));
+  c->runs.clear();
+  c->pins.clear();
   if (c->d_rec) cudaFree(c->d_rec);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_status) cudaFree(c->d_status);
@@ -462,7 +478,8 @@ void classify_host(const hmpc_ctx* c, const unsigned char* gait0, size_t gait_st
 }
 
 int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_block, float* d_wrench32, int* d_status,
-                            cudaStream_t st, int slot, float* d_tau, bool zero_copy)
+                            cudaStream_t st, int slot, float* d_tau, bool zero_copy, const update_data_t* raw = nullptr,
+                            double* wrench64 = nullptr)
 {
   int* d_block = c->d_lists + (size_t)slot * (4 + 3 * (size_t)c->max_batch);
   const int n0 = h_block[0], n1 = h_block[1];
@@ -478,6 +495,8 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
     if (cnt == 0) continue;
     const ClassCfg& k = c->cls[i];
     hmpc::KernelArgs ka = base_args(c, d_records, nb, d_wrench32, d_status);
+    ka.raw_records = reinterpret_cast<const unsigned char*>(raw);
+    ka.wrench64 = wrench64;
     ka.tau = d_tau;
     ka.warm_start = (c->warm_mode < 0) ? (nb > c->cls[0].grid_cap ? 1 : 0) : c->warm_mode;
     ka.list = d_block + 4 + (size_t)i * c->max_batch;
@@ -584,6 +603,65 @@ HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* c, const hmpc_state_t* d_states, 
   return HMPC_OK;
 }
 
+HMPC_EXTERNC int hmpc_pin_host_buffer(hmpc_ctx* c, void* ptr, size_t bytes)
+{
+  if (!c || !ptr || bytes == 0) { g_err = "hmpc_pin_host_buffer: bad argument"; return HMPC_ERR_ARG; }
+  if (c->pinned(ptr, bytes)) return HMPC_OK;
+  CK(cudaSetDevice(c->device));
+  // registration is page-granular and two small caller arrays may share a page: register only the page runs of
+  // [ptr, ptr+bytes) that no earlier pin covers
+  const uintptr_t PG = 4096;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(ptr) & ~(PG - 1);
+  const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes + PG - 1) & ~(PG - 1);
+  auto covered = [&](uintptr_t pg) {
+    for (const hmpc_ctx::Run& r : c->runs)
+      if (pg >= r.lo && pg < r.hi) return true;
+    return false;
+  };
+  for (uintptr_t pg = lo; pg < hi;) {
+    if (covered(pg)) { pg += PG; continue; }
+    uintptr_t end = pg + PG;
+    while (end < hi && !covered(end)) end += PG;
+    void* base = reinterpret_cast<void*>(pg);
+    CK(cudaHostRegister(base, end - pg, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    void* dptr = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dptr, base, 0);
+    if (e != cudaSuccess || dptr != base) {  // the in-place mode hands host addresses to the kernels
+      cudaHostUnregister(base);
+      g_err = "hmpc_pin_host_buffer: this device cannot address registered host memory through the host pointer";
+      return HMPC_ERR_CUDA;
+    }
+    c->runs.push_back({pg, end});
+    pg = end;
+  }
+  c->pins.push_back({static_cast<char*>(ptr), bytes});
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_unpin_host_buffer(hmpc_ctx* c, void* ptr)
+{
+  if (!c || !ptr) { g_err = "hmpc_unpin_host_buffer: bad argument"; return HMPC_ERR_ARG; }
+  size_t idx = c->pins.size();
+  for (size_t i = 0; i < c->pins.size(); i++)
+    if (c->pins[i].base == static_cast<char*>(ptr)) idx = i;
+  if (idx == c->pins.size()) { g_err = "hmpc_unpin_host_buffer: pointer was not pinned through this context"; return HMPC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->pins.erase(c->pins.begin() + idx);
+  // release the page runs no remaining pin touches
+  for (size_t r = 0; r < c->runs.size();) {
+    bool used = false;
+    for (const hmpc_ctx::Pin& p : c->pins) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(p.base), b = a + p.bytes;
+      used |= (a < c->runs[r].hi && b > c->runs[r].lo);
+    }
+    if (used) { r++; continue; }
+    CK(cudaHostUnregister(reinterpret_cast<void*>(c->runs[r].lo)));
+    c->runs.erase(c->runs.begin() + r);
+  }
+  return HMPC_OK;
+}
+
 static_assert(sizeof(hmpc_rollout_t) == 80 && offsetof(hmpc_rollout_t, gait_offset) == 48, "hmpc_rollout_t layout (hmpc_advance_kernel)");
 
 HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* c, hmpc_state_t* d_states, hmpc_rollout_t* d_loop, int B, int ticks,
@@ -639,9 +717,38 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
   if (nch_env >= 1 && nch_env <= NCHUNK) nch = nch_env;
   static const bool trace = getenv("HMPC_TRACE") != nullptr;
   // zero-copy mode: the kernels read the packed records from, and write the results to, pinned host memory
-  // directly (UVA-mapped), so a tick has no copy launches at all
-  static const int zc_env = getenv("HMPC_ZEROCOPY") ? atoi(getenv("HMPC_ZEROCOPY")) : c->zero_copy_default;
-  const bool zc = zc_env != 0;
+  // directly (UVA-mapped), so a tick has no copy launches at all.  Measured on B200: 0.224 vs 0.243 ms per
+  // 1024-robot tick; beyond ~1.5k robots the two-chunk copy pipeline wins (0.66 vs 0.80 ms at 4096) because packing
+  // overlaps the kernels there.  HMPC_ZEROCOPY=0/1 forces a mode.
+  static const int zc_env = getenv("HMPC_ZEROCOPY") ? atoi(getenv("HMPC_ZEROCOPY")) : -1;
+  const bool zc = zc_env >= 0 ? (zc_env != 0) : (B <= 1536);
+  if (zc && nch_env < 1) nch = 1;
+  // in-place mode: records, wrenches and status all live in buffers the caller registered (hmpc_pin_host_buffer):
+  // the kernels gather the live bytes of every update_data_t over PCIe and store double results where the caller
+  // wants them — the call is host classification + launches + one synchronize
+  if (in && zc_env != 0 && !c->pins.empty() && c->pinned(in, (size_t)B * sizeof(update_data_t)) &&
+      c->pinned(wrench_out, (size_t)B * nw * sizeof(double)) && (!status || c->pinned(status, (size_t)B * sizeof(int)))) {
+    int* hblk = c->h_cls;
+    classify_host(c, in[0].gait, sizeof(update_data_t), B, hblk);
+    int* ds = status ? status : reinterpret_cast<int*>(c->h_out + (size_t)c->max_batch * nw * 4);
+    float* dt_ = tau_out ? reinterpret_cast<float*>(c->h_out + (size_t)c->max_batch * (nw * 4 + 4)) : nullptr;
+    int rc = enqueue_solve_hostlists(c, nullptr, B, hblk, nullptr, ds, c->stream, 0, dt_, true, in, wrench_out);
+    if (rc != HMPC_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    bool all_ok = true, overflow = false;
+    for (int i = 0; i < B; i++) {
+      const int cd = HMPC_STATUS_CODE(ds[i]);
+      overflow |= (cd == hmpc::ST_WS_CAP);
+      all_ok &= (cd == 0);
+    }
+    if (!overflow) {
+      if (tau_out)
+        for (int i = 0; i < B * 10; i++) tau_out[i] = (double)dt_[i];
+      if (!all_ok) { g_err = "hmpc_solve_batch: at least one instance did not reach a KKT point (see status[])"; return HMPC_ERR_NOT_CONVERGED; }
+      return HMPC_OK;
+    }
+    // working-set overflow (rare): fall through to the staged path, which escalates
+  }
   double tr[4 * NCHUNK + 2];
   int ntr = 0;
   auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
@@ -753,11 +860,18 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
 // ---------------------------------------------------------------------------------------------------
 namespace {
 hmpc_ctx* g_ctx = nullptr;
-update_data_t g_update;  // zero-initialised static storage, like the reference's `update`
-double* g_soln = nullptr;
+// the reference's `update` record, the solution buffer and the status word live in ONE page-aligned block that is
+// registered with the context, so the one-robot tick runs in place (no packing / staging copies)
+struct RefBlock {
+  update_data_t update;                       // zero-initialised, like the reference's static `update`
+  double soln[12 * HMPC_MAX_HORIZON];
+  int status;
+};
+RefBlock* g_blk = nullptr;
+update_data_t g_update_early;  // update_solver_settings may be called before setup_problem
+update_data_t& ref_update() { return g_blk ? g_blk->update : g_update_early; }
 int g_soln_len = 0;
 int g_has_solved = 0;
-int g_last_status = 0;
 
 [[noreturn]] void die(const char* where)
 {
@@ -774,11 +888,21 @@ HMPC_EXTERNC void setup_problem(double dt, int horizon, double mu, double f_max)
   }
   if (!g_ctx || g_ctx->horizon != horizon) {
     if (g_ctx) hmpc_destroy(g_ctx);
-    g_ctx = hmpc_create(1, horizon, 0);
+    g_ctx = hmpc_create(1, horizon, 0);  // refuses horizons above HMPC_MAX_HORIZON
     if (!g_ctx) die("setup_problem");
-    free(g_soln);
-    g_soln = static_cast<double*>(calloc((size_t)12 * horizon, sizeof(double)));
+    if (!g_blk) {
+      void* mem = nullptr;
+      const size_t bytes = (sizeof(RefBlock) + 4095) / 4096 * 4096;
+      if (posix_memalign(&mem, 4096, bytes) != 0) { g_err = "out of memory"; die("setup_problem"); }
+      memset(mem, 0, bytes);
+      g_blk = static_cast<RefBlock*>(mem);
+      g_blk->update = g_update_early;
+    }
+    memset(g_blk->soln, 0, sizeof(g_blk->soln));
     g_soln_len = 12 * horizon;
+    // in-place ticks; if registration is not possible the staged path is used (same results)
+    if (hmpc_pin_host_buffer(g_ctx, g_blk, (sizeof(RefBlock) + 4095) / 4096 * 4096) != HMPC_OK)
+      fprintf(stderr, "[hector_mpc_b200] setup_problem: %s (using staged copies)\n", hmpc_last_error());
   }
   problem_setup s;
   s.dt = (float)dt;
@@ -795,16 +919,16 @@ HMPC_EXTERNC void update_problem_data(double* p, double* v, double* q, double* w
   if (!g_ctx) { g_err = "update_problem_data called before setup_problem"; die("update_problem_data"); }
   const int N = g_ctx->horizon;
   // double -> float narrowing, convexMPC_interface.cpp:87-99
-  for (int i = 0; i < 3; i++) { g_update.p[i] = (float)p[i]; g_update.v[i] = (float)v[i]; g_update.w[i] = (float)w[i]; }
-  for (int i = 0; i < 4; i++) g_update.q[i] = (float)q[i];
-  for (int i = 0; i < 6; i++) g_update.r[i] = (float)r[i];
-  for (int i = 0; i < 10; i++) g_update.joint_angles[i] = (float)joint_angles[i];
-  g_update.yaw = (float)yaw;
-  for (int i = 0; i < 12; i++) { g_update.weights[i] = (float)weights[i]; g_update.Alpha_K[i] = (float)Alpha_K[i]; }
-  for (int i = 0; i < 12 * N; i++) g_update.traj[i] = (float)state_trajectory[i];
-  for (int i = 0; i < 2 * N; i++) g_update.gait[i] = (unsigned char)gait[i];
-  int rc = hmpc_solve_batch(g_ctx, &g_update, 1, g_soln, &g_last_status);
-  if (rc == HMPC_ERR_NOT_CONVERGED) printf("failed to solve!\n");  // SolverMPC.cpp:714-715 (status word kept in g_last_status)
+  for (int i = 0; i < 3; i++) { ref_update().p[i] = (float)p[i]; ref_update().v[i] = (float)v[i]; ref_update().w[i] = (float)w[i]; }
+  for (int i = 0; i < 4; i++) ref_update().q[i] = (float)q[i];
+  for (int i = 0; i < 6; i++) ref_update().r[i] = (float)r[i];
+  for (int i = 0; i < 10; i++) ref_update().joint_angles[i] = (float)joint_angles[i];
+  ref_update().yaw = (float)yaw;
+  for (int i = 0; i < 12; i++) { ref_update().weights[i] = (float)weights[i]; ref_update().Alpha_K[i] = (float)Alpha_K[i]; }
+  for (int i = 0; i < 12 * N; i++) ref_update().traj[i] = (float)state_trajectory[i];
+  for (int i = 0; i < 2 * N; i++) ref_update().gait[i] = (unsigned char)gait[i];
+  int rc = hmpc_solve_batch(g_ctx, &g_blk->update, 1, g_blk->soln, &g_blk->status);
+  if (rc == HMPC_ERR_NOT_CONVERGED) printf("failed to solve!\n");  // SolverMPC.cpp:714-715 (status word: hmpc_reference_last_status())
   else if (rc != HMPC_OK) die("update_problem_data");
   g_has_solved = 1;
 }
@@ -813,19 +937,19 @@ HMPC_EXTERNC double get_solution(int index)
 {
   if (!g_has_solved) return 0.f;  // convexMPC_interface.cpp:107
   if (index < 0 || index >= g_soln_len) return 0.0;
-  return g_soln[index];
+  return g_blk->soln[index];
 }
 
 HMPC_EXTERNC void update_solver_settings(int max_iter, double rho, double sigma, double solver_alpha, double terminate,
                                          double use_jcqp)
 {
   (void)use_jcqp;  // convexMPC_interface.cpp:112-118: stored, not used by the solve
-  g_update.max_iterations = max_iter;
-  g_update.rho = rho;
-  g_update.sigma = sigma;
-  g_update.solver_alpha = solver_alpha;
-  g_update.terminate = terminate;
+  ref_update().max_iterations = max_iter;
+  ref_update().rho = rho;
+  ref_update().sigma = sigma;
+  ref_update().solver_alpha = solver_alpha;
+  ref_update().terminate = terminate;
 }
 
 // status word of the last update_problem_data (additive; not part of the reference boundary)
-HMPC_EXTERNC int hmpc_reference_last_status(void) { return g_last_status; }
+HMPC_EXTERNC int hmpc_reference_last_status(void) { return g_blk ? g_blk->status : 0; }

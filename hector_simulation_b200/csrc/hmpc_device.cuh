@@ -105,6 +105,8 @@ __host__ __device__ constexpr Layout class_layout(int N, int cls)
 
 struct KernelArgs {
   const unsigned char* records;  // packed device records
+  const unsigned char* raw_records;  // or: the caller's own update_data_t array (3016-byte stride, pinned + mapped host
+                                     // memory), read in place over PCIe — nullptr in the packed modes
   int rec_stride;                // bytes, multiple of 16
   int batch;
   int horizon;                   // N
@@ -829,7 +831,21 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     const int inst = ka.list ? ka.list[idx] : idx;
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 0] = clock64();
     // ---------------- stage 0: record -> shared memory (TMA bulk copy) ----------------
-    if (tid == 0) {
+    const bool raw = ka.raw_records != nullptr;
+    if (raw) {
+      // in-place mode: gather the live pieces of the reference record (convexMPC_interface.h:19-37; 8-byte aligned,
+      // so no bulk copy) into the packed layout with 8-byte loads: p..weights | Alpha_K | traj | gait
+      const unsigned char* src = ka.raw_records + (size_t)inst * 3016;
+      const int nt = 6 * N, ng = (2 * N + 7) / 8;
+      for (int e = tid; e < 27 + nt + ng; e += NT) {
+        int so, dw;  // source byte offset, destination 8-byte word
+        if (e < 21) { so = 8 * e; dw = e; }
+        else if (e < 27) { so = 1896 + 8 * (e - 21); dw = e; }
+        else if (e < 27 + nt) { so = 168 + 8 * (e - 27); dw = e; }
+        else { so = 1944 + 8 * (e - 27 - nt); dw = e; }
+        reinterpret_cast<uint2*>(rec)[dw] = *reinterpret_cast<const uint2*>(src + so);
+      }
+    } else if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the union
       mbar_expect_tx(bar, (uint32_t)rec_stride);
       bulk_g2s(rec, ka.records + (size_t)inst * rec_stride, (uint32_t)rec_stride, bar);
@@ -838,8 +854,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     for (int e = tid; e < 169; e += NT) Acd[e] = 0.f;
     for (int e = tid; e < 156; e += NT) Bcd[e] = 0.f;
     for (int e = tid; e < 192; e += NT) Fblk[e] = 0.f;
-    mbar_wait(bar, phase);
-    phase ^= 1;
+    if (raw) {
+      __syncthreads();
+    } else {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
 
     // ---------------- contact table -> reduced block list (SolverMPC.cpp:589-637) ----------------
     const unsigned char* gait = rec + (54 + 12 * N) * 4;

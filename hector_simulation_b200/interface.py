@@ -26,6 +26,7 @@ EXPORTS = [
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
     "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
     "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device",
+    "hmpc_pin_host_buffer", "hmpc_unpin_host_buffer",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -84,6 +85,10 @@ def lib() -> ctypes.CDLL:
         L.hmpc_rollout_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.hmpc_rollout_device.restype = ctypes.c_int
+        L.hmpc_pin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.hmpc_pin_host_buffer.restype = ctypes.c_int
+        L.hmpc_unpin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_unpin_host_buffer.restype = ctypes.c_int
         L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hmpc_class_config.restype = ctypes.c_int
         _lib = L
@@ -197,6 +202,18 @@ class BatchedMPC:
         out = np.zeros(6, dtype=np.int32)
         _check(lib().hmpc_class_config(self._h, cls, out.ctypes.data))
         return dict(zip(("threads", "smem_bytes", "qmax", "grid_cap", "nb_cap", "strip"), (int(v) for v in out)))
+
+    def pin(self, *arrays: np.ndarray) -> None:
+        """Register caller-owned arrays (records, wrench, status) for the in-place mode of solve_batch: the GPU then
+        reads the records where they lie and writes the results where the caller wants them (hmpc_pin_host_buffer).
+        The arrays must stay alive until unpin()/close()."""
+        for a in arrays:
+            assert a.flags.c_contiguous
+            _check(lib().hmpc_pin_host_buffer(self._h, a.ctypes.data, a.nbytes))
+
+    def unpin(self, *arrays: np.ndarray) -> None:
+        for a in arrays:
+            _check(lib().hmpc_unpin_host_buffer(self._h, a.ctypes.data))
 
     def solve_batch(self, records: np.ndarray, strict: bool = True, out=None):
         """Host-buffer path: H2D + kernels + D2H inside.  -> (wrench [B,12N] f64, status [B] i32).

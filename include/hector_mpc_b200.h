@@ -153,6 +153,15 @@ HMPC_EXTERNC int hmpc_solve_batch_ex(hmpc_ctx* ctx, const struct update_data_t* 
 HMPC_EXTERNC int hmpc_solve_device_ex(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench, int* d_status,
                                       float* d_tau, void* stream);
 
+/* In-place mode of hmpc_solve_batch(_ex).  A control loop reuses the same record / result arrays every tick; register
+ * them once (cudaHostRegister underneath) and hmpc_solve_batch lets the GPU read the update_data_t records where they
+ * lie and write the double wrenches (and status) where the caller wants them: no packing, no staging copies, no
+ * float->double pass on the host.  It is used whenever `in`, `wrench_out` and `status` (if given) of a call all lie
+ * inside pinned ranges; results are identical to the staged path.  The caller keeps the memory allocated until
+ * hmpc_unpin_host_buffer / hmpc_destroy.  (The reference-style entry points pin their own globals.) */
+HMPC_EXTERNC int hmpc_pin_host_buffer(hmpc_ctx* ctx, void* ptr, size_t bytes);
+HMPC_EXTERNC int hmpc_unpin_host_buffer(hmpc_ctx* ctx, void* ptr);
+
 /* Row f-1: the caller's data preparation on the device.  `hmpc_state_t` is what
  * ConvexMPCLocomotion::updateMPCIfNeeded reads before it builds the MPC inputs (ConvexMPCLocomotion.cpp:279-346),
  * in double precision as the reference holds it; hmpc_prepare_device turns B of them into packed records (joint

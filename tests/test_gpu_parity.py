@@ -294,3 +294,38 @@ def test_stress_large_perturbations_all_converge(torch_cuda, oracle):
             full[Q["var_ind"]] = x
             assert inf["status"] == 0 and rel_err(w[idx[k]][None], full[None])[0] < 1e-6
         assert ef[good].max() < 3e-4
+
+
+def test_in_place_mode_equals_staged_path():
+    """hmpc_pin_host_buffer: records read in place from the caller's update_data_t array, double results written in
+    place — bit-identical to the staged (pack + copy + widen) path, at every horizon, mixed size classes."""
+    for horizon, cfg, B in ((10, 3, 700), (5, 4, 64), (16, 4, 48), (10, 1, 1)):
+        recs, _ = scenarios.make_batch(cfg, B, horizon=horizon, seed=31 + horizon)
+        mpc = interface.BatchedMPC(B, horizon)
+        w_ref, s_ref = mpc.solve_batch(recs)                      # staged: nothing pinned yet
+        w = np.full((B, 12 * horizon), np.nan)
+        s = np.full(B, -1, dtype=np.int32)
+        mpc.pin(recs, w, s)
+        mpc.solve_batch(recs, out=(w, s))
+        assert np.array_equal(s, s_ref) and np.array_equal(w, w_ref), (horizon, np.abs(w - w_ref).max())
+        # a second tick with changed records in the same buffers (what a control loop does)
+        recs2, _ = scenarios.make_batch(cfg, B, horizon=horizon, seed=77)
+        recs[:] = recs2
+        mpc.solve_batch(recs, out=(w, s))
+        mpc.unpin(recs, w, s)
+        w2, s2 = mpc.solve_batch(recs2)
+        assert np.array_equal(s, s2) and np.array_equal(w, w2)
+        mpc.close()
+
+
+def test_in_place_mode_escalates_through_the_staged_path():
+    g = load_golden("degenerate_zero_force_h10")
+    recs = np.ascontiguousarray(np.repeat(g["records"].view(scenarios.UPDATE_DTYPE).reshape(-1)[:1], 3))
+    mpc = interface.BatchedMPC(3, 10)
+    w_ref, s_ref = mpc.solve_batch(recs)
+    w = np.zeros_like(w_ref)
+    s = np.zeros_like(s_ref)
+    mpc.pin(recs, w, s)
+    mpc.solve_batch(recs, out=(w, s))
+    assert (interface.status_code(s) == 0).all() and np.array_equal(w, w_ref)
+    mpc.close()

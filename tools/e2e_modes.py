@@ -15,6 +15,7 @@ B = int(sys.argv[1])
 recs, inputs = scenarios.make_batch(2, B)
 mpc = interface.BatchedMPC(B, 10)
 w = np.zeros((B, 120)); s = np.zeros(B, np.int32)
+if os.environ.get("HMPC_PIN") == "1": mpc.pin(recs, w, s)
 for _ in range(20): mpc.solve_batch(recs, out=(w, s))
 lat = []
 for _ in range(300):
@@ -44,11 +45,10 @@ print(json.dumps({"ms_p50": float(np.percentile(lat, 50)), "ms_mean": float(lat.
 
 def main():
     B = sys.argv[1] if len(sys.argv) > 1 else "1024"
-    for zc in ("0", "1"):
-        for ch in ("1", "2"):
-            env = dict(os.environ, HMPC_ZEROCOPY=zc, HMPC_CHUNKS=ch)
-            r = subprocess.run([sys.executable, "-c", CHILD, B], env=env, capture_output=True, text=True, timeout=600)
-            print("zero_copy=%s chunks=%s  %s %s" % (zc, ch, r.stdout.strip(), r.stderr.strip()[-300:]), flush=True)
+    for mode in ({"HMPC_ZEROCOPY": "0", "HMPC_CHUNKS": "2"}, {"HMPC_ZEROCOPY": "1", "HMPC_CHUNKS": "1"}, {}, {"HMPC_PIN": "1"}):
+        env = dict(os.environ, **mode)
+        r = subprocess.run([sys.executable, "-c", CHILD, B], env=env, capture_output=True, text=True, timeout=600)
+        print("%s  %s %s" % (mode or "default", r.stdout.strip(), r.stderr.strip()[-300:]), flush=True)
 
 
 if __name__ == "__main__":
