@@ -125,10 +125,12 @@ def test_config5_200_ticks_on_device():
     straight = st["state_des"][:, 4] == 0
     disp = (st["position"][:, 0] - x0)[straight]
     want = cmd[straight] * T * scenarios.DT_MPC
-    fast = np.abs(want) > 0.5  # commanded more than half a metre: travelled 60-110 % of it, in the commanded direction
+    # the reference's weights/clamped position set-point track ~76 % of the commanded speed in steady state (the same
+    # ratio with qpOASES in the loop, tools/rollout_cpu_sim.py); initial-velocity transients move it by a few cm
+    fast = np.abs(want) > 1.0
     ratio = disp[fast] / want[fast]
-    assert ratio.min() > 0.6 and ratio.max() < 1.1, (ratio.min(), ratio.max())
-    assert np.abs(disp[~fast] - want[~fast]).max() < 0.3
+    assert ratio.min() > 0.65 and ratio.max() < 0.9, (ratio.min(), ratio.max())
+    assert np.abs(disp[~fast] - 0.76 * want[~fast]).max() < 0.25
     turn = st["rpy"][~straight, 2] / (T * scenarios.DT_MPC) - st["state_des"][~straight, 4]
     assert np.abs(turn).max() < 0.08, np.abs(turn).max()  # commanded yaw rate is followed
     print("config 5: mean working-set changes per tick %.2f" % (lo["iters_total"].sum() / lo["ticks"].sum()))
