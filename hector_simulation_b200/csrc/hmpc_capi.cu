@@ -192,12 +192,39 @@ cudaError_t prep_class(ClassCfg& c, int* occ)
   return e;
 }
 
-cudaError_t launch_class(const ClassCfg& c, const hmpc::KernelArgs& ka, int grid, cudaStream_t st)
+// programmatic dependent launch for the device-resident chain (classification -> class 0 -> class 1 -> class 2):
+// every kernel of the chain may become resident while its predecessor drains and waits (griddepcontrol.wait) before it
+// reads what the predecessor wrote.  HMPC_PDL=0 switches back to plain stream order.
+bool pdl_enabled()
 {
-#define HMPC_LAUNCH(NT, MB, BW, NF, CL) hmpc::hmpc_solve_kernel<NT, MB, BW, NF, CL><<<grid, NT, c.smem, st>>>(ka);
+  static const bool on = !(getenv("HMPC_PDL") && atoi(getenv("HMPC_PDL")) == 0);
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+cudaError_t launch_class(const ClassCfg& c, const hmpc::KernelArgs& ka, int grid, cudaStream_t st, bool pdl = false)
+{
+  cudaError_t e = cudaSuccess;
+#define HMPC_LAUNCH(NT, MB, BW, NF, CL) \
+  e = launch_chain(hmpc::hmpc_solve_kernel<NT, MB, BW, NF, CL>, dim3(grid), dim3(NT), (size_t)c.smem, st, pdl, ka);
   HMPC_FOR_VARIANT(c.variant, HMPC_LAUNCH)
 #undef HMPC_LAUNCH
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 int build_classes(hmpc_ctx* c)
@@ -424,15 +451,16 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
   CK(cudaSetDevice(c->device));
   int* counts = c->d_lists + (size_t)slot * (4 + 3 * (size_t)c->max_batch);  // per slot: [4 counts][3 lists]
   int* lists = counts + 4;
+  const bool pdl = pdl_enabled();
   if (B <= 1024) {
-    hmpc::hmpc_classify1_kernel<<<1, (B + 31) / 32 * 32, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride,
-                                                                 B, c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts,
-                                                                 lists, c->max_batch);
+    CK(launch_chain(hmpc::hmpc_classify1_kernel, dim3(1), dim3((B + 31) / 32 * 32), 0, st, pdl,
+                    static_cast<const unsigned char*>(d_records), c->rec_stride, B, c->horizon, c->setup.f_max,
+                    c->cls[0].nb_hi, counts, lists, c->max_batch));
   } else {
     CK(cudaMemsetAsync(counts, 0, 3 * sizeof(int), st));
-    hmpc::hmpc_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(static_cast<const unsigned char*>(d_records), c->rec_stride, B,
-                                                               c->horizon, c->setup.f_max, c->cls[0].nb_hi, counts, lists,
-                                                               c->max_batch);
+    CK(launch_chain(hmpc::hmpc_classify_kernel, dim3((B + 255) / 256), dim3(256), 0, st, false,
+                    static_cast<const unsigned char*>(d_records), c->rec_stride, B, c->horizon, c->setup.f_max,
+                    c->cls[0].nb_hi, counts, lists, c->max_batch));
   }
   CK(cudaGetLastError());
   for (int i = 0; i < c->ncls; i++) {
@@ -450,7 +478,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     ka.L = k.L;
     ka.dbg_clk = g_dbg_clk;
     const int grid = B < k.grid_cap ? B : k.grid_cap;
-    CK(launch_class(k, ka, grid, st));
+    CK(launch_class(k, ka, grid, st, pdl));
   }
   return HMPC_OK;
 }

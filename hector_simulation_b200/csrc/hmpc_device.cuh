@@ -139,6 +139,12 @@ struct KernelArgs {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// programmatic dependent launch (sm_90+): a kernel launched with the stream-serialization attribute may start while
+// its predecessor drains; it must not touch anything the predecessor (or, transitively, earlier kernels) produces or
+// still reads before pdl_wait() returns.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -723,6 +729,8 @@ __global__ void hmpc_classify1_kernel(const unsigned char* records, int rec_stri
 {
   __shared__ int cnt[2];
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+  pdl_wait();     // the previous solve's kernels may still read counts/lists
+  pdl_trigger();  // the class kernels may set up while this block classifies
   __syncthreads();
   const int i = threadIdx.x;
   if (i < batch) {
@@ -744,6 +752,8 @@ __global__ void hmpc_classify1_kernel(const unsigned char* records, int rec_stri
 __global__ void hmpc_classify_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,
                                      int nb_hi0, int* counts, int* lists, int list_stride)
 {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
   const unsigned char* g = records + (size_t)i * rec_stride + (54 + 12 * N) * 4;
@@ -819,12 +829,14 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   float* Fblk = reinterpret_cast<float*>(smem + L.fbl);
   int* comb = reinterpret_cast<int*>(smem + L.HA);     // stage-3 work list (HA is free until the sweep)
 
+  pdl_trigger();  // the next class's kernel may become resident while this one works
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   uint32_t phase = 0;
+  pdl_wait();     // counts / lists / records come from the kernels before this one
   const int count = ka.list ? ka.counts[ka.cls] : ka.batch;
 
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
