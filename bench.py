@@ -280,7 +280,7 @@ def main():
     # ---------------- end-to-end leg (host buffers through the C-ABI) ----------------
     # N = 1: the reference-facing call hmpc_solve_batch (pack + H2D + kernels + D2H inside).
     # N > 1: the batch spans devices, so results are exchanged ON DEVICE — per step every rank packs its shard
-    # into pinned memory (C-ABI hmpc_pack_records), copies it in, solves with hmpc_solve_device, joins ONE NCCL
+    # into pinned memory (C-ABI hmpc_pack_records), solves with hmpc_solve_device reading it in place, joins ONE NCCL
     # all_gather of the float results, and reads the gathered result back to the host.
     if world == 1:
         out_w = np.zeros((B, 12 * N), dtype=np.float64)  # caller-owned result buffers, reused every tick
@@ -296,7 +296,6 @@ def main():
         import ctypes
 
         h_in = torch.empty((B, stride), dtype=torch.uint8).pin_memory()
-        d_in1 = torch.empty((B, stride), dtype=torch.uint8, device="cuda")
         d_w1 = torch.empty((B, 12 * N), dtype=torch.float32, device="cuda")
         d_s1 = torch.empty((B,), dtype=torch.int32, device="cuda")
         d_all = torch.empty((world * B, 12 * N), dtype=torch.float32, device="cuda")
@@ -306,8 +305,7 @@ def main():
 
         def e2e_step():
             interface.lib().hmpc_pack_records(recs_c.ctypes.data, B, N, ctypes.c_void_p(h_in.data_ptr()))
-            d_in1.copy_(h_in, non_blocking=True)
-            mpc.solve_device(d_in1, B, d_w1, d_s1)
+            mpc.solve_device(h_in, B, d_w1, d_s1)  # pinned + mapped: the kernels pull the packed records over PCIe
             dist.all_gather_into_tensor(d_all, d_w1)
             h_all.copy_(d_all, non_blocking=True)
             h_st.copy_(d_s1, non_blocking=True)
@@ -358,7 +356,7 @@ def main():
                        "note": "device time for the whole 1024-robot batch; every robot's result is ready within it"},
         "solver": {"mean_working_set_changes": k_mean, "max": int(iters.max())},
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int((world * B * 48 * N + B * 4) if world > 1 else B * (96 * N + 4)),
-                "transfer": ("pack + H2D copy + all_gather + D2H copy" if world > 1 else
+                "transfer": ("pack into pinned memory, kernels read it over PCIe, device all_gather, D2H copy" if world > 1 else
                              "in place: kernels gather the live 720 B of every host update_data_t over PCIe and store double wrenches + status into the caller's registered arrays"),
                 "ms_per_step": e2e_ms / K, "latency_ms_p99": float(np.percentile(e2e_lat, 99) * 1e3)},
         "gpu_launches": int(K * mpc.launches_per_solve),  # per step: 1 classification kernel + 1 solve kernel per size class
