@@ -238,6 +238,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set)
+        # goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, N = args.batch, HORIZON
     K, W = args.steps, args.warmup
