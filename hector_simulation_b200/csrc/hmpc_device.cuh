@@ -892,19 +892,30 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         st0 |= ((mask >> (2 * s)) & 1u) << s;
         st1 |= ((mask >> (2 * s + 1)) & 1u) << s;
       }
-      // stage-3 work list: (li, lj, delta) combinations that own at least one wanted H block
+      // stage-3 work list: (li, lj, delta) combinations that own at least one wanted H block, sorted by chain
+      // length (longest first) so that the 32 items a warp runs in lockstep have similar trip counts and the
+      // warps can balance their load by grabbing chunks from a shared counter
       int ncomb = 0;
-      for (int base = 0; base < 4 * N; base += 32) {
-        const int c = base + lane;
-        const int li = (c / N) >> 1, lj = (c / N) & 1, delta = c % N;
-        unsigned need = 0;
-        if (c < 4 * N) need = (li ? st1 : st0) & ((lj ? st1 : st0) >> delta);
-        const unsigned has = __ballot_sync(0xffffffffu, need != 0);
-        if (need) {
-          const int kmax = N - 1 - delta - (__ffs(need) - 1);
-          comb[ncomb + __popc(has & ((1u << lane) - 1u))] = li | (lj << 1) | (delta << 2) | (kmax << 8);
+      {
+        int pk[2], km[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int c = 32 * h + lane;
+          const int li = (c / N) >> 1, lj = (c / N) & 1, delta = c % N;
+          unsigned need = 0;
+          if (c < 4 * N) need = (li ? st1 : st0) & ((lj ? st1 : st0) >> delta);
+          km[h] = need ? N - 1 - delta - (__ffs(need) - 1) : -1;
+          pk[h] = li | (lj << 1) | (delta << 2) | (km[h] << 8);
         }
-        ncomb += __popc(has);
+        const unsigned lt = (1u << lane) - 1u;
+        for (int v = N - 1; v >= 0; v--) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const unsigned has = __ballot_sync(0xffffffffu, km[h] == v);
+            if (km[h] == v) comb[ncomb + __popc(has & lt)] = pk[h];
+            ncomb += __popc(has);
+          }
+        }
       }
       if (lane == 0) {
         flags[0] = __popc(mask);
@@ -912,6 +923,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         flags[2] = (int)st1;
         flags[3] = ST_OK;
         flags[6] = ncomb;
+        flags[7] = 0;  // stage-3 chunk counter
       }
     }
     __syncthreads();
@@ -1037,8 +1049,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       // item = (li, lj, delta, i): running sums G_delta(K)[i][leg lj's six columns] = sum_{e<=K} T_{e+delta}^T M_e;
       // block (a,b) of B'SB, b - a = delta, equals G_delta(N-1-b) — the oracle's own summation order.
       const int nitems = flags[6] * 6;
-      for (int rd = 0; rd * NT < nitems; rd++) {
-        const int it = rd * NT + ((rd & 1) ? (NT - 1 - tid) : tid);  // serpentine: long and short chains pair up
+      while (true) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&flags[7], 1);  // next 32 items (longest chains first)
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk * 32 >= nitems) break;
+        const int it = chunk * 32 + lane;
         if (it >= nitems) continue;
         const int cm = comb[it / 6], ci = it % 6;
         const int li = cm & 1, lj = (cm >> 1) & 1, delta = (cm >> 2) & 63, Kmax = cm >> 8;
