@@ -17,8 +17,7 @@ def main():
         rows = rows[: len(lt)]
     src = open(os.path.join(ROOT, "hector_simulation_b200", "csrc", "hmpc_device.cuh")).read().splitlines()
     marks = [(i + 1, l.strip()) for i, l in enumerate(src)
-             if "// ----------------" in l or l.startswith("__device__ inline void") or l.startswith("__device__ __forceinline__ void block_argmin")
-             or l.startswith("__device__ __forceinline__ double hrow6")]
+             if "// ----------------" in l or l.startswith("__device__") or l.startswith("__global__")]
     starts = [m[0] for m in marks]
     agg, tot, toti = {}, 0, 0
     for i, r in enumerate(rows):
