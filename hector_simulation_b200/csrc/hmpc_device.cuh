@@ -720,6 +720,135 @@ __global__ void hmpc_advance_kernel(unsigned char* states, unsigned char* loop, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// row f-4: the swing-leg controller, one thread per robot (swingLegController::updateSwingLeg,
+// src/common/SwingLegController.cpp:46-219; Gait::getSwingSubPhase, GaitGenerator.cpp:54-80; Bezier swing trajectory,
+// FootSwingTrajectory.cpp:17-36 + Interpolation.h:53-74).  fp64 with explicitly rounded operations in the reference's
+// order (no FMA contraction), so the only differences to the CPU restatement are the last bits of asin/acos.
+//   states hmpc_state_t (352 B)   loop hmpc_rollout_t (80 B)   swing hmpc_swing_t (72 B)   cmd hmpc_swing_cmd_t (232 B)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bezier_f64(double y0, double yf, double x)
+{
+  const double b = DA(DM(DM(x, x), x), DM(3.0, DM(DM(x, x), DS(1.0, x))));
+  return DA(y0, DM(b, DS(yf, y0)));
+}
+__device__ __forceinline__ double clamp_f64(double v, double lo, double hi) { return fmax(lo, fmin(v, hi)); }
+__device__ __forceinline__ double dot3_rn(double a0, double b0, double a1, double b1, double a2, double b2)
+{
+  return DA(DA(DM(a0, b0), DM(a1, b1)), DM(a2, b2));
+}
+__global__ void hmpc_swing_kernel(const unsigned char* states, const unsigned char* loop, const double* phase,
+                                  unsigned char* swing, int batch, int n_iterations, double dt, double dtSwing,
+                                  unsigned char* cmd)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const double* s = reinterpret_cast<const double*>(states + (size_t)i * 352);
+  const double* pos = s; const double* vw = s + 3; const double* qt = s + 6;
+  const double* lq = s + 16; const double* lp = s + 26; const double* sd = s + 32;
+  const int* li = reinterpret_cast<const int*>(loop + (size_t)i * 80 + 48);  // offset[2] duration[2] ...
+  double* sw_p0 = reinterpret_cast<double*>(swing + (size_t)i * 72);
+  double* sw_time = sw_p0 + 6;
+  int* sw_first = reinterpret_cast<int*>(swing + (size_t)i * 72 + 64);
+  double* out = reinterpret_cast<double*>(cmd + (size_t)i * 232);  // pf[6] p_des[6] v_des[6] q_des[10] | swing[2]
+  int* out_swing = reinterpret_cast<int*>(cmd + (size_t)i * 232 + 224);
+  for (int k = 0; k < 28; k++) out[k] = 0.0;
+  out_swing[0] = out_swing[1] = 0;
+  double R[9];  // body -> world; rBody = R^T
+  quat_to_R_f64(qt, R);
+  const double hipy[2] = {-0.057, 0.057};
+  // updateFootPosition (:61-70)
+  double pfw[2][3];
+  for (int leg = 0; leg < 2; leg++) {
+    const double hp0 = DA(-0.005, lp[3 * leg]), hp1 = DA(hipy[leg], lp[3 * leg + 1]), hp2 = DA(-0.126, lp[3 * leg + 2]);
+    for (int a = 0; a < 3; a++) pfw[leg][a] = DA(pos[a], dot3_rn(R[a * 3], hp0, R[a * 3 + 1], hp1, R[a * 3 + 2], hp2));
+    pfw[leg][2] = 0.0;
+  }
+  // Gait::getSwingSubPhase (GaitGenerator.cpp:54-80)
+  double sst[2];
+  for (int leg = 0; leg < 2; leg++) {
+    const double offp = __ddiv_rn((double)li[leg], (double)n_iterations);
+    const double durp = __ddiv_rn((double)li[2 + leg], (double)n_iterations);
+    double so = DA(offp, durp);
+    if (so > 1) so = DS(so, 1.);
+    const double sdur = DS(1., durp);
+    double pr = DS(phase[i], so);
+    if (pr < 0) pr = DA(pr, 1.);
+    if (pr > sdur) pr = 0.;
+    else pr = __ddiv_rn(pr, sdur);
+    sst[leg] = pr;
+  }
+  const int g_stance = li[2], g_swing = n_iterations - li[2];
+  // updateSwingTimes (:82-93)
+  for (int leg = 0; leg < 2; leg++) {
+    if (sw_first[leg]) {
+      sw_time[leg] = DM(dtSwing, (double)g_swing);
+    } else {
+      sw_time[leg] = DS(sw_time[leg], dt);
+      if (sw_time[leg] <= 0) sw_first[leg] = 1;
+    }
+  }
+  // computeFootPlacement (:98-128)
+  double vdw[3];
+  for (int a = 0; a < 3; a++) vdw[a] = dot3_rn(R[a * 3], sd[2], R[a * 3 + 1], sd[3], R[a * 3 + 2], 0.0);
+  double Pf[2][3];
+  for (int leg = 0; leg < 2; leg++) {
+    for (int a = 0; a < 3; a++)
+      Pf[leg][a] = DA(DA(pos[a], dot3_rn(R[a * 3], -0.005, R[a * 3 + 1], hipy[leg], R[a * 3 + 2], -0.126)), DM(vw[a], sw_time[leg]));
+    for (int a = 0; a < 2; a++) {
+      const double rel = DA(DM(DM(DM(DM(1.75, vw[a]), 0.5), (double)g_stance), dtSwing), DM(0.1, DS(vw[a], vdw[a])));
+      const float relf = fminf(fmaxf((float)rel, -(float)0.3), (float)0.3);  // float clamp as written (:117-118)
+      Pf[leg][a] = DA(Pf[leg][a], (double)relf);
+    }
+    Pf[leg][2] = 0.0;
+    for (int a = 0; a < 3; a++) out[3 * leg + a] = Pf[leg][a];
+  }
+  // computeFootDesiredPosition (:134-155) + computeIK (:160-193)
+  const double PI = 3.14159265358979323846;  // M_PI
+  for (int leg = 0; leg < 2; leg++) {
+    if (!(sst[leg] > 0)) continue;
+    out_swing[leg] = 1;
+    if (sw_first[leg]) {
+      sw_first[leg] = 0;
+      for (int a = 0; a < 3; a++) sw_p0[3 * leg + a] = pfw[leg][a];
+    }
+    const double ph = sst[leg], height = 0.15;
+    const double* p0 = sw_p0 + 3 * leg;
+    double pd[3];
+    for (int a = 0; a < 2; a++) pd[a] = bezier_f64(p0[a], Pf[leg][a], ph);
+    pd[2] = (ph < 0.5) ? bezier_f64(p0[2], DA(p0[2], height), DM(ph, 2.0)) : bezier_f64(DA(p0[2], height), Pf[leg][2], DS(DM(ph, 2.0), 1.0));
+    const double side_w = (leg == 1) ? 1.0 : -1.0;
+    const double hoff[3] = {-0.015, DM(side_w, -0.055), 0.0};
+    const double d0 = DS(pd[0], pos[0]), d1 = DS(pd[1], pos[1]), d2 = DS(pd[2], pos[2]);
+    double pb[3];
+    for (int a = 0; a < 3; a++) {  // rBody = R^T: row a of rBody = column a of R
+      pb[a] = DA(dot3_rn(R[a], d0, R[3 + a], d1, R[6 + a], d2), hoff[a]);
+      out[6 + 3 * leg + a] = pb[a];
+      out[12 + 3 * leg + a] = dot3_rn(R[a], DS(0.0, vw[0]), R[3 + a], DS(0.0, vw[1]), R[6 + a], DS(0.0, vw[2]));
+    }
+    const double side = (leg == 0) ? -1.0 : 1.0;
+    const double f0 = DS(pb[0], DS(0.0465, 0.06)), f1 = DS(pb[1], 0.0), f2 = DS(pb[2], DA(-0.126, DM(-0.0705, 2.0)));
+    const double d3 = sqrt(DA(DA(DM(f0, f0), DM(f1, f1)), DM(f2, f2)));
+    const double dyz = sqrt(DA(DM(f1, f1), DM(f2, f2)));
+    const double dh = 0.0205;
+    const double dv_ = sqrt(fmax(0.00001, DS(DM(dyz, dyz), DM(dh, dh))));
+    const double dxz = sqrt(DS(DM(d3, d3), DM(dh, dh)));
+    const double a1 = clamp_f64(__ddiv_rn(dxz, DM(2.0, 0.22)), -1.0, 1.0);
+    const double a2 = clamp_f64(__ddiv_rn(dv_, dxz), -1.0, 1.0);
+    double divisor = fabs(f0);
+    divisor = (divisor == 0.0) ? 1e-6 : divisor;
+    double* q = out + 18 + 5 * leg;
+    q[0] = 0.0;
+    q[1] = DA(asin(clamp_f64(__ddiv_rn(f1, dyz), -1.0, 1.0)), asin(clamp_f64(__ddiv_rn(DM(dh, side), dyz), -1.0, 1.0)));
+    q[2] = DS(acos(a1), __ddiv_rn(DM(acos(a2), f0), divisor));
+    q[3] = DS(DM(2.0, asin(clamp_f64(__ddiv_rn(__ddiv_rn(dxz, 2.0), 0.22), -1.0, 1.0))), PI);
+    q[4] = DS(-lq[5 * leg + 3], lq[5 * leg + 2]);
+    q[2] = DS(q[2], DM(0.3, PI));
+    q[3] = DA(q[3], DM(0.6, PI));
+    q[4] = DS(q[4], DM(0.3, PI));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // classification pre-pass: bucket instances by reduced size (number of stance (step,leg) blocks)
 // ------------------------------------------------------------------------------------------------
 // single-block variant (batch <= 1024): counts via shared-memory atomics, written (not accumulated) at the end,

@@ -26,7 +26,7 @@ EXPORTS = [
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
     "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
     "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device",
-    "hmpc_pin_host_buffer", "hmpc_unpin_host_buffer",
+    "hmpc_pin_host_buffer", "hmpc_unpin_host_buffer", "hmpc_swing_device",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -89,6 +89,8 @@ def lib() -> ctypes.CDLL:
         L.hmpc_pin_host_buffer.restype = ctypes.c_int
         L.hmpc_unpin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.hmpc_unpin_host_buffer.restype = ctypes.c_int
+        L.hmpc_swing_device.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_swing_device.restype = ctypes.c_int
         L.hmpc_class_config.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hmpc_class_config.restype = ctypes.c_int
         _lib = L
@@ -280,6 +282,16 @@ class BatchedMPC:
         _check(lib().hmpc_rollout_device(self._h, d_states.data_ptr(), d_loop.data_ptr(), B, ticks, dt_mpc,
                                          d_wrench_log.data_ptr() if d_wrench_log is not None else None,
                                          d_record_log.data_ptr() if d_record_log is not None else None, ctypes.c_void_p(st)))
+
+    def swing_device(self, d_states, d_loop, d_phase, d_swing, B: int, d_cmd, dt: float = 0.001, dt_swing: float = 0.04,
+                     stream=None) -> None:
+        """Row f-4: one swingLegController::updateSwingLeg per robot on the device.  torch CUDA tensors: states uint8
+        [B,352], loop uint8 [B,80], phase f64 [B], swing uint8 [B,72] (updated in place), cmd uint8 [B,232]."""
+        import torch
+
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _check(lib().hmpc_swing_device(self._h, d_states.data_ptr(), d_loop.data_ptr(), d_phase.data_ptr(), d_swing.data_ptr(),
+                                       B, dt, dt_swing, d_cmd.data_ptr(), ctypes.c_void_p(st)))
 
     def solve_device(self, d_records, B: int, d_wrench, d_status, stream=None) -> None:
         """Device-resident path.  Arguments are torch CUDA tensors (uint8 [B,stride], f32 [B,12N], i32 [B])."""

@@ -236,6 +236,25 @@ def make_rollout(inputs, horizon: int = 10, standing=None, phases=None):
     return states, loop
 
 
+# numpy mirrors of `hmpc_swing_t` / `hmpc_swing_cmd_t` (include/hector_mpc_b200.h): swing-leg controller memory and output
+SWING_DTYPE = np.dtype([("p0", "<f8", 6), ("swing_time", "<f8", 2), ("first_swing", "<i4", 2)])
+SWING_CMD_DTYPE = np.dtype([("pf", "<f8", 6), ("p_des", "<f8", 6), ("v_des", "<f8", 6), ("q_des", "<f8", 10), ("swing", "<i4", 2)])
+assert SWING_DTYPE.itemsize == 72 and SWING_CMD_DTYPE.itemsize == 232
+
+
+def make_swing(n: int) -> np.ndarray:
+    """Fresh swing-controller memory: firstSwing = {true, true} (SwingLegController.h:65)."""
+    sw = np.zeros(n, dtype=SWING_DTYPE)
+    sw["first_swing"] = 1
+    return sw
+
+
+def gait_phase(iteration_counter, iterations_per_mpc: int, n_iterations: int):
+    """Gait::_phase of Gait::setIterations (GaitGenerator.cpp:109-113)."""
+    period = iterations_per_mpc * n_iterations
+    return (np.asarray(iteration_counter) % period) / float(period)
+
+
 I_BODY_DIAG = np.array([0.5413, 0.5200, 0.0691])  # RobotState.cpp:45
 BODY_MASS = 9.0                                    # SolverMPC.cpp:423
 

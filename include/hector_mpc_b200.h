@@ -214,6 +214,33 @@ struct hmpc_rollout_t
 HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* ctx, struct hmpc_state_t* d_states, struct hmpc_rollout_t* d_loop, int B,
                                      int ticks, double dtMPC, float* d_wrench_log, void* d_record_log, void* stream);
 
+/* Row f-4: the swing-leg controller, batched — swingLegController::updateSwingLeg
+ * (src/common/SwingLegController.cpp:46-219): foot position, swing sub-phase (Gait::getSwingSubPhase,
+ * GaitGenerator.cpp:54-80), swing-time countdown, touch-down placement (:98-128), Bezier swing trajectory
+ * (FootSwingTrajectory.cpp:17-36, Interpolation.h:53-74) and the approximate 5-DoF inverse kinematics (:160-193), one GPU
+ * thread per robot, fp64.  hmpc_swing_t is the controller's per-robot memory (swingLegController's members);
+ * hmpc_swing_cmd_t is what setDesiredJointState (:198-219) hands to the leg controller for the legs in swing
+ * (zeros and swing[leg] = 0 for stance legs).  `d_phase[i]` is Gait::_phase of robot i (GaitGenerator.cpp:112); the
+ * gait's offsets/durations come from hmpc_rollout_t (nIterations = the context's horizon). */
+struct hmpc_swing_t
+{
+  double p0[6];          /* footSwingTrajectory[leg]._p0, world */
+  double swing_time[2];  /* swingTimes[leg] */
+  int first_swing[2];    /* firstSwing[leg] (initially 1, 1) */
+};
+struct hmpc_swing_cmd_t
+{
+  double pf[6];          /* planned touch-down position of each leg, world (footSwingTrajectory[leg]._pf) */
+  double p_des[6];       /* commands[leg].pDes = pFoot_b, body frame */
+  double v_des[6];       /* commands[leg].vDes = vFoot_b */
+  double q_des[10];      /* commands[leg].qDes from computeIK */
+  int swing[2];          /* swingStates[leg] > 0 */
+};
+/* dt = the controller's own period (0.001, SwingLegController.h:79), dtSwing = dtMPC (ConvexMPCLocomotion.cpp:70). */
+HMPC_EXTERNC int hmpc_swing_device(hmpc_ctx* ctx, const struct hmpc_state_t* d_states, const struct hmpc_rollout_t* d_loop,
+                                   const double* d_phase, struct hmpc_swing_t* d_swing, int B, double dt, double dtSwing,
+                                   struct hmpc_swing_cmd_t* d_cmd, void* stream);
+
 /* number of kernel launches hmpc_solve_device enqueues per call (classification pre-pass + one per size class) */
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* ctx);
 /* launch configuration of size class `cls` (0 or 1): out[0..5] = threads per CTA, dynamic shared memory bytes,

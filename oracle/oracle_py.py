@@ -158,3 +158,18 @@ def joint_torques(wrench12, rBody, q_leg, contact) -> np.ndarray:
     tau = np.zeros((n, 10))
     lib().oracle_joint_torques(_p(wrench12), _p(rBody), _p(q_leg), _p(contact), ctypes.c_int(n), _p(tau))
     return tau
+
+
+def swing_update(states: np.ndarray, loop: np.ndarray, phase: np.ndarray, swing: np.ndarray, n_iterations: int,
+                 dt: float = 0.001, dt_swing: float = 0.04) -> np.ndarray:
+    """One swingLegController::updateSwingLeg for every robot (swing_leg_oracle.cpp); `swing` is updated in place.
+    Arrays use the hmpc_state_t / hmpc_rollout_t / hmpc_swing_t layouts; returns hmpc_swing_cmd_t records."""
+    n = states.shape[0]
+    assert states.dtype.itemsize == 352 and loop.dtype.itemsize == 80 and swing.dtype.itemsize == 72
+    assert states.flags.c_contiguous and loop.flags.c_contiguous and swing.flags.c_contiguous
+    phase = np.ascontiguousarray(phase, dtype=np.float64)
+    cmd = np.zeros(n, dtype=np.dtype([("pf", "<f8", 6), ("p_des", "<f8", 6), ("v_des", "<f8", 6), ("q_des", "<f8", 10), ("swing", "<i4", 2)]))
+    assert cmd.dtype.itemsize == 232
+    lib().oracle_swing_update(_p(states), _p(loop), _p(phase), _p(swing), ctypes.c_int(n), ctypes.c_int(n_iterations),
+                              ctypes.c_double(dt), ctypes.c_double(dt_swing), _p(cmd))
+    return cmd
