@@ -163,13 +163,12 @@ struct hmpc_ctx {
 namespace {
 
 // kernel variants <threads, min CTAs/SM, sweep strip width, fixed horizon (0 = runtime), size class>
-//   0/1: horizon 10 fixed at compile time (class 0 / class 1)      2: horizon-10 class 0 with 6x3 strips (experiment)
+//   0/1: horizon 10 fixed at compile time (class 0 / class 1)
 //   3..8: runtime horizon, 64 / 224 / 544 threads for class 0 and class 1
 #define HMPC_FOR_VARIANT(V, X)                      \
   switch (V) {                                      \
     case 0: X(64, 8, 6, 10, 0); break;              \
     case 1: X(224, 2, 6, 10, 1); break;             \
-    case 2: X(128, 7, 3, 10, 0); break;             \
     case 3: X(64, 8, 6, 0, 0); break;               \
     case 4: X(224, 2, 6, 0, 0); break;              \
     case 5: X(544, 1, 6, 0, 0); break;              \
@@ -235,7 +234,6 @@ int build_classes(hmpc_ctx* c)
   // class 2 = class 1's size with a working set as large as the variable count (1 CTA/SM): reached only by
   // escalation from class 1 (massively degenerate optima, e.g. all contact forces at zero).
   c->ncls = 3;
-  const char* exp = getenv("HMPC_CLS0_STRIPS");  // experiment switch: 6x3 strips on 128 threads for class 0
   for (int i = 0; i < 3; i++) {
     ClassCfg& k = c->cls[i];
     if (i == 2) {
@@ -270,7 +268,6 @@ int build_classes(hmpc_ctx* c)
     if (N == 10) {
       k.variant = i;
       k.threads = (i == 0) ? 64 : 224;
-      if (i == 0 && exp && exp[0] == '1') { k.variant = 2; k.threads = 128; }
     } else {
       k.variant = 3 + 3 * i + bucket;
       k.threads = bucket_threads[bucket];
@@ -554,7 +551,7 @@ HMPC_EXTERNC int hmpc_class_config(const hmpc_ctx* c, int cls, int* out)
   if (!c || !out || cls < 0 || cls >= c->ncls) return HMPC_ERR_ARG;
   const ClassCfg& k = c->cls[cls];
   out[0] = k.threads; out[1] = k.smem; out[2] = k.qmax; out[3] = k.grid_cap; out[4] = k.nb_cap;
-  out[5] = (k.variant == 2) ? 3 : 6;
+  out[5] = 6;  // sweep strip width (columns of the 6x6 register block)
   return HMPC_OK;
 }
 
