@@ -144,29 +144,38 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback (B200_PROFILING.md)"}
 
 
-def cpu_reference_leg(records, steps: int, warmup: int, sample_per_step: int):
+def cpu_reference_leg(records, steps: int, warmup: int, sample_per_step: int, budget_s: float = 150.0):
     """Times the reference's CPU implementation (oracle/_ref: restated solve_mpc + the reference's qpOASES)
     with one independent solver per host core (the reference is single-threaded and non-reentrant, so
-    cores are used as independent processes).  Returns (QP/s, cores, per-solve seconds array)."""
+    cores are used as independent processes).  Returns (QP/s, cores, per-solve seconds array, solves per step).
+    If the first (warm-up) step shows that warmup+steps steps would exceed `budget_s`, the per-step sample is
+    shrunk (never below 4 solves per core) so that the whole run stays within a few minutes."""
     import multiprocessing as mp
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    chunks = np.array_split(np.arange(sample_per_step), cores)
     ctx = mp.get_context("fork")
+
+    def make_jobs(n):
+        chunks = np.array_split(np.arange(n), cores)
+        return [(records[c % len(records)],) for c in chunks if len(c)]
+
     total_solves = 0
     lat = []
     t_total = 0.0
-    jobs = [(records[c % len(records)],) for c in chunks if len(c)]
+    jobs = make_jobs(sample_per_step)
     with ctx.Pool(cores) as pool:
         for it in range(warmup + steps):
             t0 = time.perf_counter()
             outs = pool.map(_cpu_worker, jobs, chunksize=1)
             dt = time.perf_counter() - t0
+            if it == 0 and dt * (warmup + steps) > budget_s:
+                sample_per_step = max(4 * cores, int(sample_per_step * budget_s / (dt * (warmup + steps))))
+                jobs = make_jobs(sample_per_step)
             if it >= warmup:
                 t_total += dt
                 total_solves += sum(len(o) for o in outs)
                 lat.extend(np.concatenate(outs).tolist())
-    return total_solves / t_total, cores, np.array(lat)
+    return total_solves / t_total, cores, np.array(lat), sample_per_step
 
 
 def cpu_sample_size() -> int:
@@ -197,14 +206,14 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref built without qpOASES (no /root/reference, no prebuilt .so)"}))
         return
     sample = cpu_sample_size()
-    qps, cores, lat = cpu_reference_leg(recs, args.steps, max(args.warmup, 1), sample)
+    qps, cores, lat, sample = cpu_reference_leg(recs, args.steps, max(args.warmup, 1), sample)
     line = {
-        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sample / qps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 assembly / f64 solve",
         "data": "synthetic", "config": {"workload": "configs[1]: batch=1024 Hector walking-gait states, horizon=10 (bounded sample per step)",
                                        "horizon": HORIZON, "sample_per_step": sample},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{sample} solves per step (64 per core, cycling through the 1024 records), one solver process per core",
+                         "sample": f"{sample} solves per step ({sample // cores} per core, cycling through the 1024 records), one solver process per core",
                          "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -439,7 +448,7 @@ def main():
 
             if O.has_qpoases():
                 sample = cpu_sample_size()
-                cq, cores, lat = cpu_reference_leg(recs, 3, 1, sample)
+                cq, cores, lat, sample = cpu_reference_leg(recs, 3, 1, sample)
                 line["cpu_baseline"] = {"value": cq, "unit": UNIT, "cores": cores, "kind": "reference",
                                         "sample": f"3 steps of {sample} solves (64 per core, cycling through the {B} records), one solver process per core (restated solve_mpc + the reference's qpOASES 3.2)",
                                         "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)}
