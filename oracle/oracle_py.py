@@ -5,8 +5,11 @@ import this module.  It wraps oracle/_ref/liboracle_mpc.so: the Eigen-free resta
 reference's ``solve_mpc`` (hector_control/ConvexMPC/SolverMPC.cpp:371-732) linked against the
 reference's own vendored qpOASES 3.2 built unchanged from /root/reference (oracle/Makefile).
 
-Formulation half: *parity unpinned* (the reference has no tests/golden vectors and needs Eigen,
-absent here — see the header of solve_mpc_oracle.cpp).  Solver half: the reference's own code.
+Parity status: the restatement is pinned against the reference's own formulation sources compiled
+unchanged against oracle/eigen_shim (oracle/_ref/libref_mpc.so, `ref_solve` below): in trig-as-compiled
+mode it reproduces them bit for bit (tests/test_reference_compiled.py).  What stays a restatement is the
+arithmetic of Eigen itself (absent here, unpinned by the reference) — see the header of
+solve_mpc_oracle.cpp.  Solver half: the reference's own code.
 """
 from __future__ import annotations
 
@@ -86,7 +89,12 @@ def _p(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def solve_batch(records: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False):
+def _mode(assembly_fp64: bool, trig_as_compiled: bool) -> ctypes.c_int:
+    """Bit mask of solve_mpc_oracle.cpp: 1 = formulation in double, 2 = trig as the reference's TU resolves it."""
+    return ctypes.c_int(int(bool(assembly_fp64)) | (2 if trig_as_compiled else 0))
+
+
+def solve_batch(records: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False, trig_as_compiled: bool = False):
     """-> (q_soln [n,12N] f64, info [n,4] i32 = {rc, nWSR, nv_red, nc_red})."""
     records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
     n = records.shape[0]
@@ -95,7 +103,7 @@ def solve_batch(records: np.ndarray, setup: np.ndarray, assembly_fp64: bool = Fa
     info = np.zeros((n, 4), dtype=np.int32)
     if not has_qpoases():
         raise RuntimeError("oracle was built without qpOASES (no /root/reference and no prebuilt oracle/_ref)")
-    lib().oracle_solve_batch(_p(records), ctypes.c_int(n), _p(setup), ctypes.c_int(int(assembly_fp64)), _p(q), _p(info))
+    lib().oracle_solve_batch(_p(records), ctypes.c_int(n), _p(setup), _mode(assembly_fp64, trig_as_compiled), _p(q), _p(info))
     return q, info
 
 
@@ -107,7 +115,7 @@ def time_solves(records: np.ndarray, setup: np.ndarray, total: int) -> np.ndarra
     return out
 
 
-def formulate_f32(record: np.ndarray, setup: np.ndarray) -> dict:
+def formulate_f32(record: np.ndarray, setup: np.ndarray, trig_as_compiled: bool = False) -> dict:
     """Un-reduced fp32 QP data + intermediates of ONE record (the reference's arithmetic)."""
     record = np.ascontiguousarray(record, dtype=UPDATE_DTYPE).reshape(1)
     N = int(setup["horizon"][0])
@@ -118,13 +126,13 @@ def formulate_f32(record: np.ndarray, setup: np.ndarray) -> dict:
         Acd=np.zeros((13, 13), np.float32), Bcd=np.zeros((13, 12), np.float32), Rfoot=np.zeros((2, 3, 3), np.float32),
         R=np.zeros((3, 3), np.float32), A_qp=np.zeros((13 * N, 13), np.float32),
     )
-    lib().oracle_formulate_f32(_p(record), _p(setup), _p(out["H"]), _p(out["g"]), _p(out["Fblk"]), _p(out["lb"]),
-                               _p(out["ub"]), _p(out["x0"]), _p(out["Acd"]), _p(out["Bcd"]), _p(out["Rfoot"]),
-                               _p(out["R"]), _p(out["A_qp"]))
+    lib().oracle_formulate_f32_mode(_p(record), _p(setup), _mode(False, trig_as_compiled), _p(out["H"]), _p(out["g"]), _p(out["Fblk"]), _p(out["lb"]),
+                                    _p(out["ub"]), _p(out["x0"]), _p(out["Acd"]), _p(out["Bcd"]), _p(out["Rfoot"]),
+                                    _p(out["R"]), _p(out["A_qp"]))
     return out
 
 
-def reduced_qp(record: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False) -> dict:
+def reduced_qp(record: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False, trig_as_compiled: bool = False) -> dict:
     """The reduced QP exactly as handed to qpOASES (SolverMPC.cpp:644-697), doubles."""
     record = np.ascontiguousarray(record, dtype=UPDATE_DTYPE).reshape(1)
     N = int(setup["horizon"][0])
@@ -133,7 +141,7 @@ def reduced_qp(record: np.ndarray, setup: np.ndarray, assembly_fp64: bool = Fals
     vi = np.zeros(n, np.int32); ci = np.zeros(m, np.int32); nc = ctypes.c_int(0)
     L = lib()
     L.oracle_reduced_qp.restype = ctypes.c_int
-    nv = L.oracle_reduced_qp(_p(record), _p(setup), ctypes.c_int(int(assembly_fp64)), _p(H), _p(g), _p(A), _p(lb), _p(ub),
+    nv = L.oracle_reduced_qp(_p(record), _p(setup), _mode(assembly_fp64, trig_as_compiled), _p(H), _p(g), _p(A), _p(lb), _p(ub),
                              _p(vi), _p(ci), ctypes.byref(nc))
     nc = nc.value
     return dict(H=H[: nv * nv].reshape(nv, nv).copy(), g=g[:nv].copy(), A=A[: nc * nv].reshape(nc, nv).copy(),
@@ -173,3 +181,65 @@ def swing_update(states: np.ndarray, loop: np.ndarray, phase: np.ndarray, swing:
     lib().oracle_swing_update(_p(states), _p(loop), _p(phase), _p(swing), ctypes.c_int(n), ctypes.c_int(n_iterations),
                               ctypes.c_double(dt), ctypes.c_double(dt_swing), _p(cmd))
     return cmd
+
+
+# ---- the reference's own formulation sources, compiled against oracle/eigen_shim (oracle/Makefile) ------------
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libref_mpc.so")
+_ref_lib = None
+
+
+def has_reference_build() -> bool:
+    """True when oracle/_ref/libref_mpc.so exists (built where /root/reference is present; it travels)."""
+    return os.path.exists(_REF_LIB_PATH)
+
+
+def ref_lib() -> ctypes.CDLL:
+    global _ref_lib
+    if _ref_lib is None:
+        L = ctypes.CDLL(_REF_LIB_PATH)
+        L.refshim_sizeof_update_data.restype = ctypes.c_size_t
+        assert L.refshim_sizeof_update_data() == UPDATE_DTYPE.itemsize
+        _ref_lib = L
+    return _ref_lib
+
+
+def ref_solve(records: np.ndarray, setup: np.ndarray, formulation: bool = False):
+    """The reference's `resize_qp_mats` + `solve_mpc` (SolverMPC.cpp, compiled unchanged) on each record.
+    The reference's c2qp loops are fixed at 10 (quirk Q1), so only horizon 10 is meaningful.
+    -> q_soln [n,12N] f64, and with formulation=True a dict of the reference's file-scope QP matrices per record."""
+    records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
+    n = records.shape[0]
+    N = int(setup["horizon"][0])
+    assert N == 10, "the reference formulation is hard-wired to horizon 10 (SolverMPC.cpp:148,161,180)"
+    nv, nc = 12 * N, 16 * N
+    q = np.zeros((n, nv))
+    out = None
+    if formulation:
+        out = dict(H=np.zeros((n, nv, nv), np.float32), g=np.zeros((n, nv), np.float32), A=np.zeros((n, nc, nv), np.float32),
+                   lb=np.zeros((n, nc), np.float32), ub=np.zeros((n, nc), np.float32), x0=np.zeros((n, 13), np.float32),
+                   A_qp=np.zeros((n, 13 * N, 13), np.float32), A_ct=np.zeros((n, 13, 13), np.float32),
+                   B_ct=np.zeros((n, 13, 12), np.float32))
+    L = ref_lib()
+    null = ctypes.c_void_p(0)
+    for i in range(n):
+        rec = records[i:i + 1]
+        if formulation:
+            L.refshim_solve(_p(rec), _p(setup), _p(q[i]), _p(out["H"][i]), _p(out["g"][i]), _p(out["A"][i]), _p(out["lb"][i]),
+                            _p(out["ub"][i]), _p(out["x0"][i]), _p(out["A_qp"][i]), _p(out["A_ct"][i]), _p(out["B_ct"][i]))
+        else:
+            L.refshim_solve(_p(rec), _p(setup), _p(q[i]), null, null, null, null, null, null, null, null, null)
+    return (q, out) if formulation else q
+
+
+def ref_boundary_solve(b: dict, horizon: int = 10, dt: float = 0.04, mu: float = 0.25, f_max: float = 500.0) -> np.ndarray:
+    """`setup_problem` + `update_problem_data` + `get_solution` of the compiled reference on one set of boundary
+    inputs (doubles, the dict layout of scenarios.boundary_inputs)."""
+    d = lambda k: np.ascontiguousarray(b[k], dtype=np.float64)
+    gait = np.ascontiguousarray(b["gait"], dtype=np.int32)
+    q = np.zeros(12 * horizon)
+    arrs = [d(k) for k in ("p", "v", "q", "w", "r", "joint_angles")]
+    w8, traj, alpha = d("weights"), d("state_trajectory"), d("Alpha_K")
+    ref_lib().refshim_boundary_solve(ctypes.c_double(dt), ctypes.c_int(horizon), ctypes.c_double(mu), ctypes.c_double(f_max),
+                                     *[_p(a) for a in arrs], ctypes.c_double(float(b["yaw"])), _p(w8), _p(traj), _p(alpha),
+                                     _p(gait), _p(q))
+    return q

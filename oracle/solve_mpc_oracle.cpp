@@ -13,14 +13,43 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this.  The product library (libhector_mpc_b200.so) never links or calls it.
  *
- * PARITY STATUS: *parity unpinned* for the formulation half.  The reference ships no tests or
- * golden vectors and its formulation needs Eigen, which is neither vendored nor
- * installed here, so SolverMPC.cpp cannot be compiled.  This file restates its arithmetic:
- * `float` wherever the reference uses `fpt`, products as plain sequential sums with separately
- * rounded multiply and add (the reference is built with -O3 and no -march, i.e. SSE2 without FMA,
- * hector_control/CMakeLists.txt:7; Eigen's GEBP / coefficient-based products accumulate
- * sequentially in k), 3x3 inverses by the cofactor formula Eigen uses, trig in double then
- * narrowed.  The QP-solve half IS the reference (qpOASES built from its own sources).
+ * PARITY STATUS: pinned against the reference's own source text; bit-level arithmetic of the absent
+ * third-party library (Eigen, version not pinned by the reference) restated.  The reference ships no
+ * tests or golden vectors and its formulation needs Eigen, which is neither vendored
+ * nor installed here.  Two things stand in for that:
+ *   1. oracle/_ref/libref_mpc.so — SolverMPC.cpp, RobotState.cpp and convexMPC_interface.cpp compiled
+ *      UNCHANGED from /root/reference against oracle/eigen_shim (an eager stand-in for the Eigen API
+ *      subset those files use; sequential-sum products, cofactor 3x3 inverse) and the reference's
+ *      qpOASES.  This restatement, in TRIG-AS-COMPILED mode, reproduces it bit for bit — qH, qg, fmat,
+ *      L_b, U_b, x_0, A_qp and the returned solution (tests/test_reference_compiled.py) — so every
+ *      index, sign, literal and quirk below is checked against the reference's text by the compiler,
+ *      not by reading.  Committed vectors: tests/golden/ref_compiled_h10.npz.
+ *   2. What remains a restatement is Eigen's own arithmetic: `float` wherever the reference uses
+ *      `fpt`, products as plain sequential sums with separately rounded multiply and add (the
+ *      reference is built with -O3 and no -march, i.e. SSE2 without FMA, hector_control/CMakeLists.txt:7;
+ *      Eigen's coefficient-based products accumulate sequentially in k, its blocked GEBP kernel may
+ *      group differently — a freedom the reference itself has, its Eigen version being unpinned),
+ *      3x3 inverses by the cofactor formula Eigen uses.  The QP-solve half IS the reference (qpOASES
+ *      built from its own sources).
+ *
+ * TRIG RESOLUTION (found by compiling the reference, not visible from reading it): SolverMPC.cpp
+ * includes <cmath> (:6) and then qpOASES.hpp (:8), whose Utils.ipp:36 includes <math.h>.  With
+ * libstdc++ (GCC >= 6) <math.h> brings std::sin/cos/asin(float) into the global namespace, so the
+ * unqualified calls on `fpt` arguments in euler_to_rotation (:73-85), quat_to_rpy (:340) and the
+ * foot-rotation literals (:428-433) resolve to libm's FLOAT functions, and products of two such
+ * values are rounded to float (terms led by the literal `1.0*` stay double); atan2(float, double)
+ * (:339,:341) and fmod(float, double) (:392) promote to double.  glibc's sinf/cosf/asinf differ from
+ * the correctly rounded value in 1.3 % / 1.3 % / 7 % of arguments and have CPU-dispatched variants,
+ * so those last bits are not reproducible across machines — let alone on a GPU.  Hence two modes:
+ *   mode 0, CANONICAL (default; what the CUDA kernel reproduces bit for bit and what the golden
+ *           cfg*.npz fixtures hold): every trig call in double, narrowed to float — the correctly
+ *           rounded version of the same expression;
+ *   mode 2, TRIG AS COMPILED: the overloads the reference's TU gets, for the bit-for-bit check
+ *           against libref_mpc.so.
+ * The two differ by last-bit perturbations of Rb and R_foot; measured on 256 robots of configs[2]:
+ * first-step wrench median 4e-9, worst 3.5e-5 relative (an fp64 referee on the canonical QP sits
+ * 2.3e-5 from the compiled reference at worst) — inside the 1e-4 contract, and the scale of the
+ * reference's own sensitivity to its libm.
  *
  * Build with -ffp-contract=off and WITHOUT -march=native so no FMA contraction can occur.
  *
@@ -107,32 +136,52 @@ void quat_to_R(const T* q, T* R)
 }
 
 // Foot rotation of one leg from its five (offset-corrected) joint angles: SolverMPC.cpp:428-433.
-// Same expression tree as the reference (double arithmetic, narrowed to T on store); written
-// with named sub-terms instead of one literal.
-template <class T>
+// Same expression tree as the reference, written with named sub-terms instead of one literal.
+// TR is the type the trig calls resolve to (see "trig resolution" in the header comment): with
+// TR = double every sub-term is double; with TR = float the C++ usual arithmetic conversions give
+// exactly the mixed float/double evaluation of the reference's literal (a product of two float
+// trig values is rounded to float; a term that starts with the literal `1.0*` is double).
+template <class T, class TR>
 void foot_rotation(const T* q, T* Rf)
 {
-  double s0 = sin((double)q[0]), c0 = cos((double)q[0]);
-  double s1 = sin((double)q[1]), c1 = cos((double)q[1]);
-  double s2 = sin((double)q[2]), c2 = cos((double)q[2]);
-  double s3 = sin((double)q[3]), c3 = cos((double)q[3]);
-  double s4 = sin((double)q[4]), c4 = cos((double)q[4]);
+  const TR s0 = std::sin((TR)q[0]), c0 = std::cos((TR)q[0]);
+  const TR s1 = std::sin((TR)q[1]), c1 = std::cos((TR)q[1]);
+  const TR s2 = std::sin((TR)q[2]), c2 = std::cos((TR)q[2]);
+  const TR s3 = std::sin((TR)q[3]), c3 = std::cos((TR)q[3]);
+  const TR s4 = std::sin((TR)q[4]), c4 = std::cos((TR)q[4]);
   // recurring brackets of the reference expression
-  double a = c0 * s2 + c2 * s0 * s1;        // (cos(q0)*sin(q2) + cos(q2)*sin(q0)*sin(q1))
-  double b = c0 * c2 - 1.0 * s0 * s1 * s2;  // (cos(q0)*cos(q2) - sin(q0)*sin(q1)*sin(q2))
-  double c = c2 * s0 + c0 * s1 * s2;        // (cos(q2)*sin(q0) + cos(q0)*sin(q1)*sin(q2))
-  double d = s0 * s2 - 1.0 * c0 * c2 * s1;  // (sin(q0)*sin(q2) - cos(q0)*cos(q2)*sin(q1))
+  const auto a = c0 * s2 + c2 * s0 * s1;        // (cos(q0)*sin(q2) + cos(q2)*sin(q0)*sin(q1))
+  const auto b = c0 * c2 - 1.0 * s0 * s1 * s2;  // (cos(q0)*cos(q2) - 1.0*sin(q0)*sin(q1)*sin(q2))
+  const auto c = c2 * s0 + c0 * s1 * s2;        // (cos(q2)*sin(q0) + cos(q0)*sin(q1)*sin(q2))
+  const auto d = s0 * s2 - 1.0 * c0 * c2 * s1;  // (sin(q0)*sin(q2) - 1.0*cos(q0)*cos(q2)*sin(q1))
   // the sum q2+q3+q4 is formed in the matrix scalar type (floats in the reference)
-  T q234 = q[2] + q[3] + q[4];
+  const T q234 = q[2] + q[3] + q[4];
   Rf[0] = (T)(-1.0 * s4 * (c3 * a + s3 * b) - c4 * (1.0 * s3 * a - c3 * b));
   Rf[1] = (T)(-1.0 * c1 * s0);
   Rf[2] = (T)(c4 * (c3 * a + s3 * b) - s4 * (1.0 * s3 * a - c3 * b));
   Rf[3] = (T)(c4 * (c3 * c - 1.0 * s3 * d) - 1.0 * s4 * (s3 * c + c3 * d));
   Rf[4] = (T)(c0 * c1);
   Rf[5] = (T)(c4 * (s3 * c + c3 * d) + s4 * (c3 * c - 1.0 * s3 * d));
-  Rf[6] = (T)(-1.0 * sin((double)q234) * c1);
+  Rf[6] = (T)(-1.0 * std::sin((TR)q234) * c1);
   Rf[7] = (T)(s1);
-  Rf[8] = (T)(cos((double)q234) * c1);
+  Rf[8] = (T)(std::cos((TR)q234) * c1);
+}
+
+// Pitch from its clamped sine (SolverMPC.cpp:340) in the trig type TR.
+template <class T, class TR>
+T pitch_from_sine(T as)
+{
+  return (T)std::asin((TR)as);
+}
+// The Euler-rate map whose inverse is Rb (SolverMPC.cpp:83-85) in the trig type TR: with TR = float,
+// `cos(y)*cos(p)` is a float product of two float cosines.
+template <class T, class TR>
+void euler_rate_map(T pitch, T yaw, T* Rbm)
+{
+  const TR p = (TR)pitch, y = (TR)yaw;
+  Rbm[0] = (T)(std::cos(y) * std::cos(p)); Rbm[1] = (T)(-std::sin(y)); Rbm[2] = (T)0;
+  Rbm[3] = (T)(std::sin(y) * std::cos(p)); Rbm[4] = (T)(std::cos(y));  Rbm[5] = (T)0;
+  Rbm[6] = (T)(-std::sin(p));              Rbm[7] = (T)0;              Rbm[8] = (T)1;
 }
 
 }  // namespace
@@ -161,7 +210,7 @@ struct Formulation {
 };
 
 template <class T>
-static void formulate(const update_data_t* u, const problem_setup* setup, Formulation<T>& F)
+static void formulate(const update_data_t* u, const problem_setup* setup, Formulation<T>& F, bool trig_as_compiled = false)
 {
   const int N = setup->horizon;
   const int nx = 13 * N, nu = 12 * N, nc = 16 * N;
@@ -194,15 +243,14 @@ static void formulate(const update_data_t* u, const problem_setup* setup, Formul
     if (!(as_d < .99999)) as_d = .99999;  // t_min(a,b): a<b ? a : b
     T as = (T)as_d;
     F.rpy[0] = (T)atan2((double)((T)2 * (qw * qx + qy * qz)), 1. - (double)((T)2 * (qx * qx + qy * qy)));
-    F.rpy[1] = (T)asin((double)as);
+    F.rpy[1] = trig_as_compiled ? pitch_from_sine<T, T>(as) : pitch_from_sine<T, double>(as);
     F.rpy[2] = (T)atan2((double)((T)2 * (qw * qz + qx * qy)), 1. - (double)((T)2 * (qy * qy + qz * qz)));
   }
   // ---- SolverMPC.cpp:65-89 euler_to_rotation (Rb = inverse of the rate map) --------------------
   {
-    double p = (double)F.rpy[1], y = (double)F.rpy[2];
-    T Rbm[9] = {(T)(cos(y) * cos(p)), (T)(-sin(y)), (T)0,
-                (T)(sin(y) * cos(p)), (T)(cos(y)),  (T)0,
-                (T)(-sin(p)),         (T)0,         (T)1};
+    T Rbm[9];
+    if (trig_as_compiled) euler_rate_map<T, T>(F.rpy[1], F.rpy[2], Rbm);
+    else euler_rate_map<T, double>(F.rpy[1], F.rpy[2], Rbm);
     inverse3(Rbm, F.Rb);
   }
   // ---- SolverMPC.cpp:420-421 --------------------------------------------------------------------
@@ -253,8 +301,10 @@ static void formulate(const update_data_t* u, const problem_setup* setup, Formul
     }
   }
   // ---- SolverMPC.cpp:426-433 foot rotations ----------------------------------------------------
-  foot_rotation(&F.q[0], F.Rfoot[0]);
-  foot_rotation(&F.q[5], F.Rfoot[1]);
+  for (int leg = 0; leg < 2; leg++) {
+    if (trig_as_compiled) foot_rotation<T, T>(&F.q[5 * leg], F.Rfoot[leg]);
+    else foot_rotation<T, double>(&F.q[5 * leg], F.Rfoot[leg]);
+  }
 
   // ---- SolverMPC.cpp:133-193 c2qp (forward Euler, re-powered blocks) ---------------------------
   {
@@ -456,10 +506,10 @@ static int solve_reduced(ReducedQP& Q, std::vector<double>& x, int* nwsr_out)
 }
 
 template <class T>
-static int solve_one(const update_data_t* u, const problem_setup* s, double* q_soln, int* info)
+static int solve_one(const update_data_t* u, const problem_setup* s, double* q_soln, int* info, bool trig_as_compiled = false)
 {
   Formulation<T> F;
-  formulate<T>(u, s, F);
+  formulate<T>(u, s, F, trig_as_compiled);
   ReducedQP Q;
   eliminate(F, Q);
   std::vector<double> x;
@@ -489,17 +539,21 @@ int oracle_has_qpoases(void)
 
 size_t oracle_sizeof_update_data(void) { return sizeof(update_data_t); }
 
-/* Solve `n` records.  assembly_fp64 = 0: the reference's arithmetic (fp32 formulation, fp64 solve);
- * 1: the same formulation carried in double (sensitivity probe, not the reference).
+/* Solve `n` records.  `mode` is a bit mask:
+ *   bit 0 (ORACLE_MODE_FP64)  the formulation carried in double (sensitivity probe, not the reference);
+ *                             0 = the reference's arithmetic (fp32 formulation, fp64 solve);
+ *   bit 1 (ORACLE_MODE_TRIG_AS_COMPILED)  trig calls resolve as in the reference's translation unit
+ *                             (float overloads, see "trig resolution" above); 0 = canonical double trig.
  * q_soln [n][12N]; info [n][4] = {return code, nWSR, reduced vars, reduced cons}. */
-int oracle_solve_batch(const update_data_t* u, int n, const problem_setup* s, int assembly_fp64,
+int oracle_solve_batch(const update_data_t* u, int n, const problem_setup* s, int mode,
                        double* q_soln, int* info)
 {
   int bad = 0;
   const int nu = 12 * s->horizon;
+  const bool tac = (mode & 2) != 0;
   for (int i = 0; i < n; i++) {
-    int rc = assembly_fp64 ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL)
-                           : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL);
+    int rc = (mode & 1) ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac)
+                        : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac);
     if (rc) bad++;
   }
   return bad;
@@ -530,12 +584,12 @@ int oracle_time_solves(const update_data_t* u, int n, const problem_setup* s, in
 /* Formulation only (fp32, the reference's arithmetic): full un-reduced QP data of one record.
  * H [n*n] row-major, g [n], Fblk [192], lb/ub [16N]; optional intermediates (may be NULL):
  * x0 [13], Acd [169], Bcd [156], Rfoot [18], Rmat [9], A_qp [13N*13]. */
-int oracle_formulate_f32(const update_data_t* u, const problem_setup* s, float* H, float* g, float* Fblk,
-                         float* lb, float* ub, float* x0, float* Acd, float* Bcd, float* Rfoot,
-                         float* Rmat, float* A_qp)
+int oracle_formulate_f32_mode(const update_data_t* u, const problem_setup* s, int mode, float* H, float* g,
+                              float* Fblk, float* lb, float* ub, float* x0, float* Acd, float* Bcd, float* Rfoot,
+                              float* Rmat, float* A_qp)
 {
   Formulation<float> F;
-  formulate<float>(u, s, F);
+  formulate<float>(u, s, F, (mode & 2) != 0);
   const int N = s->horizon, nu = 12 * N;
   if (H) memcpy(H, F.H.data(), sizeof(float) * (size_t)nu * nu);
   if (g) memcpy(g, F.g.data(), sizeof(float) * nu);
@@ -551,14 +605,22 @@ int oracle_formulate_f32(const update_data_t* u, const problem_setup* s, float* 
   return 0;
 }
 
+int oracle_formulate_f32(const update_data_t* u, const problem_setup* s, float* H, float* g, float* Fblk,
+                         float* lb, float* ub, float* x0, float* Acd, float* Bcd, float* Rfoot,
+                         float* Rmat, float* A_qp)
+{
+  return oracle_formulate_f32_mode(u, s, 0, H, g, Fblk, lb, ub, x0, Acd, Bcd, Rfoot, Rmat, A_qp);
+}
+
 /* The reduced QP exactly as handed to qpOASES (doubles), for independent QP cross-checks.
  * Buffers sized for the un-reduced problem.  Returns nv, writes nc. */
-int oracle_reduced_qp(const update_data_t* u, const problem_setup* s, int assembly_fp64, double* H,
+int oracle_reduced_qp(const update_data_t* u, const problem_setup* s, int mode, double* H,
                       double* g, double* A, double* lb, double* ub, int* var_ind, int* con_ind, int* nc_out)
 {
   ReducedQP Q;
-  if (assembly_fp64) { Formulation<double> F; formulate<double>(u, s, F); eliminate(F, Q); }
-  else { Formulation<float> F; formulate<float>(u, s, F); eliminate(F, Q); }
+  const bool tac = (mode & 2) != 0;
+  if (mode & 1) { Formulation<double> F; formulate<double>(u, s, F, tac); eliminate(F, Q); }
+  else { Formulation<float> F; formulate<float>(u, s, F, tac); eliminate(F, Q); }
   memcpy(H, Q.H.data(), sizeof(double) * Q.H.size());
   memcpy(g, Q.g.data(), sizeof(double) * Q.g.size());
   memcpy(A, Q.A.data(), sizeof(double) * Q.A.size());

@@ -12,8 +12,10 @@ hector_simulation_b200/scenarios.py) together with what the ORACLE returned for 
   H,g,Fblk,lb,ub  (first 4 records) the un-reduced fp32 QP data of the restated formulation
 
 The reference itself ships no tests or vectors, so these are outputs of the reference's
-solver on the restated formulation, generated here by this script; parity of the formulation half is
-therefore "unpinned" (oracle/solve_mpc_oracle.cpp header).
+solver on the restated formulation in its CANONICAL arithmetic (double trig narrowed to float — what the CUDA kernel
+reproduces bit for bit).  The restatement is pinned against the reference's own sources compiled unchanged
+(make_ref_compiled.py -> ref_compiled_h10.npz holds that build's outputs for the same records; oracle/solve_mpc_oracle.cpp
+header explains the two trig modes).
 """
 import os
 import sys
