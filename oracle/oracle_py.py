@@ -243,3 +243,70 @@ def ref_boundary_solve(b: dict, horizon: int = 10, dt: float = 0.04, mu: float =
                                      *[_p(a) for a in arrs], ctypes.c_double(float(b["yaw"])), _p(w8), _p(traj), _p(alpha),
                                      _p(gait), _p(q))
     return q
+
+
+# ---- the reference's controller tick (rows f-1..f-4), compiled against oracle/eigen_shim (oracle/Makefile) ----------
+_TICK_LIB_PATH = os.path.join(_HERE, "_ref", "libref_tick.so")
+_tick_lib = None
+
+# numpy mirror of `reftick_out_t` (oracle/ref_tick_probe.cpp)
+REFTICK_DTYPE = np.dtype(
+    [
+        ("rBody", "<f8", 9), ("rpy", "<f8", 3), ("leg_q", "<f8", 10), ("leg_p", "<f8", 6), ("J", "<f8", 60),
+        ("wpd_before", "<f8", 3), ("wpd_entry", "<f8", 3), ("wpd", "<f8", 3), ("phase", "<f8"), ("gait_iteration", "<i4"),
+        ("mpc_table", "<i4", 20), ("mpc_ran", "<i4"), ("iteration_counter", "<i4"), ("q_soln", "<f8", 120),
+        ("f_ff", "<f8", 12), ("swing_states", "<f8", 2), ("swing_times", "<f8", 2), ("first_swing", "<i4", 2),
+        ("p0", "<f8", 6), ("pf", "<f8", 6), ("q_des", "<f8", 10), ("p_des", "<f8", 6), ("v_des", "<f8", 6),
+        ("ff_cmd", "<f8", 12), ("tau", "<f8", 10), ("update_record", "u1", 3016),
+    ],
+    align=True,
+)
+
+
+def has_reference_tick() -> bool:
+    return os.path.exists(_TICK_LIB_PATH)
+
+
+def tick_lib() -> ctypes.CDLL:
+    global _tick_lib
+    if _tick_lib is None:
+        L = ctypes.CDLL(_TICK_LIB_PATH)
+        L.reftick_sizeof_out.restype = ctypes.c_size_t
+        L.reftick_create.restype = ctypes.c_void_p
+        assert L.reftick_sizeof_out() == REFTICK_DTYPE.itemsize, (L.reftick_sizeof_out(), REFTICK_DTYPE.itemsize)
+        _tick_lib = L
+    return _tick_lib
+
+
+class ReferenceController:
+    """One robot's walking controller of the reference (ConvexMPCLocomotion + LegController + swing-leg controller +
+    gait), ticked the way FSMState_Walking::run does.  State persists across ticks like the reference's objects;
+    the MPC itself is process-global in the reference (one controller solving at a time)."""
+
+    def __init__(self, dt: float = 0.001, iterations_between_mpc: int = 40):
+        self._L = tick_lib()
+        self._h = ctypes.c_void_p(self._L.reftick_create(ctypes.c_double(dt), ctypes.c_int(iterations_between_mpc)))
+        assert self._h.value, "reftick_create failed"
+
+    def run(self, gait_number, position, vWorld, orientation, omegaWorld, motor_q, motor_dq=None, v_des_body=(0.0, 0.0),
+            yaw_rate=0.0, roll=0.0, pitch=0.0) -> np.ndarray:
+        d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        position, vWorld, orientation, omegaWorld, vdb = d(position), d(vWorld), d(orientation), d(omegaWorld), d(v_des_body)
+        mq = np.ascontiguousarray(motor_q, dtype=np.float32)
+        mdq = np.zeros(10, np.float32) if motor_dq is None else np.ascontiguousarray(motor_dq, dtype=np.float32)
+        out = np.zeros(1, dtype=REFTICK_DTYPE)
+        self._L.reftick_run(self._h, ctypes.c_int(gait_number), _p(position), _p(vWorld), _p(orientation), _p(omegaWorld),
+                            _p(mq), _p(mdq), _p(vdb), ctypes.c_double(yaw_rate), ctypes.c_double(roll), ctypes.c_double(pitch),
+                            _p(out))
+        return out[0]
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._L.reftick_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

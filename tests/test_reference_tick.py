@@ -1,0 +1,214 @@
+"""CPU: the restatements of the widening rows pinned against the reference's OWN controller.
+
+oracle/_ref/libref_tick.so = the reference's ConvexMPCLocomotion, GaitGenerator, LegController, SwingLegController,
+FootSwingTrajectory and DesiredCommand translation units (plus the three formulation files and qpOASES) compiled unchanged
+against oracle/eigen_shim; oracle/ref_tick_probe.cpp ticks them the way FSMState_Walking::run does.  One simulated robot is
+walked through more than a full gait cycle with a smoothly varying pose, and on every tick
+
+  f-3  Gait::setIterations / mpc_gait          == scenarios.gait_phase / scenarios.mpc_gait
+  f-1  the `update_data_t` record the reference's updateMPCIfNeeded hands to solve_mpc
+                                              == csrc/locomotion_host.cpp hmpc_prepare_record, BYTE FOR BYTE (live fields)
+       the clamp write-back of world_position_desired                       == the host mirror's
+  a16  f_ff = -rBody [F; M]                    == hmpc_wrench_to_feedforward, bit for bit
+  f-2  J_force_moment and the joint torques    == oracle_leg_jacobian_fm / oracle_joint_torques
+  f-4  swingLegController (both calls per tick) == oracle_swing_update: controller memory, touch-down point, pDes, vDes bit for
+       bit; IK joint targets to 1e-12 rad
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from hector_simulation_b200 import scenarios
+from test_locomotion_host import Desired, LegData, StateEstimate, _host
+
+DT, ITER_MPC, N = 0.001, 40, 10
+DT_MPC = DT * ITER_MPC
+N_TICKS = 520
+COMMAND = dict(v_des=(0.3, 0.05), yaw_rate=0.2, roll=0.01, pitch=-0.02)
+FIXTURE = os.path.join(GOLDEN, "ref_tick_walk.npz")   # the same ticks, recorded by tests/golden/make_ref_tick.py
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    if not oracle.has_reference_tick():
+        pytest.skip("oracle/_ref/libref_tick.so not built (needs /root/reference at build time)")
+    return oracle
+
+
+def _pose(k, rng_phase):
+    """A smooth, deterministic pose sequence: forward drift, small body oscillations, moving joints."""
+    t = k * DT
+    a, b, c = rng_phase
+    rpy = np.array([0.04 * np.sin(7 * t + a), 0.05 * np.sin(5 * t + b), 0.3 * t + 0.02 * np.sin(3 * t + c)])
+    pos = np.array([0.25 * t + 0.01 * np.sin(9 * t), 0.02 * np.sin(4 * t + a), 0.55 + 0.01 * np.sin(6 * t + b)])
+    vel = np.array([0.25 + 0.09 * np.cos(9 * t), 0.08 * np.cos(4 * t + a), 0.06 * np.cos(6 * t + b)])
+    omega = np.array([0.28 * np.cos(7 * t + a), 0.25 * np.cos(5 * t + b), 0.3 + 0.06 * np.cos(3 * t + c)])
+    raw = np.array([0.05 * np.sin(11 * t + i) for i in range(10)]) + np.tile([0.0, 0.02, 0.1, -0.2, 0.1], 2)
+    return pos, rpy, vel, omega, raw.astype(np.float32)
+
+
+def _state_record(o, pos, vel, quat, omega, cmd5, horizon=N):
+    st = np.zeros((), dtype=scenarios.STATE_DTYPE)
+    st["position"], st["vWorld"], st["orientation"], st["omegaWorld"] = pos, vel, quat, omega
+    st["rpy"], st["leg_q"], st["leg_p"] = o["rpy"], o["leg_q"], o["leg_p"]
+    st["state_des"] = cmd5
+    st["world_position_desired"] = o["wpd_entry"][:2]
+    st["gait"][: 2 * horizon] = o["mpc_table"]
+    return st
+
+
+def reference_ticks(O):
+    """Tick the compiled reference controller through the pose sequence; yields its per-tick outputs."""
+    ctl = O.ReferenceController(DT, ITER_MPC)
+    for k in range(N_TICKS):
+        pos, rpy, vel, omega, raw = _pose(k, (0.3, 1.1, 2.0))
+        quat = scenarios.rpy_to_quat(rpy)
+        yield ctl.run(2, pos, vel, quat, omega, raw, v_des_body=COMMAND["v_des"], yaw_rate=COMMAND["yaw_rate"],
+                      roll=COMMAND["roll"], pitch=COMMAND["pitch"])
+    ctl.close()
+
+
+def committed_ticks(O):
+    return iter(np.load(FIXTURE)["ticks"].view(O.REFTICK_DTYPE).reshape(-1))
+
+
+@pytest.mark.parametrize("source", ["live", "committed"])
+def test_walking_ticks_match_the_reference_controller(oracle, source):
+    """live: libref_tick.so ticked here;  committed: the outputs it produced when the fixture was generated (runs on any
+    machine, also without /root/reference)."""
+    O = oracle
+    if source == "live":
+        if not O.has_reference_tick():
+            pytest.skip("oracle/_ref/libref_tick.so not built (needs /root/reference at build time)")
+        ticks = reference_ticks(O)
+    else:
+        ticks = committed_ticks(O)
+    H = _host()
+    swing = scenarios.make_swing(1)
+    loop = np.zeros(1, dtype=scenarios.ROLLOUT_DTYPE)
+    loop["gait_offset"], loop["gait_duration"] = (0, 5), (5, 5)
+    v_des, yaw_rate, roll, pitch = COMMAND["v_des"], COMMAND["yaw_rate"], COMMAND["roll"], COMMAND["pitch"]
+    cmd5 = np.array([roll, pitch, v_des[0], v_des[1], yaw_rate])
+    n_ticks, n_mpc, n_swing_checked, worst_ik = N_TICKS, 0, 0, 0.0
+    for k, o in enumerate(ticks):
+        pos, rpy, vel, omega, raw = _pose(k, (0.3, 1.1, 2.0))
+        quat = scenarios.rpy_to_quat(rpy)
+        assert o["iteration_counter"] == k + 1
+
+        # ---- f-3: gait ------------------------------------------------------------------------------------------
+        it, ph = (k // ITER_MPC) % N, float(scenarios.gait_phase(k, ITER_MPC, N))
+        assert o["gait_iteration"] == it and o["phase"] == ph
+        assert np.array_equal(o["mpc_table"], scenarios.mpc_gait(N, (0, 5), (5, 5), it).reshape(-1))
+
+        # ---- the state estimate the probe wrote == what the restatements derive from the quaternion ---------------
+        assert np.array_equal(o["rBody"].reshape(3, 3), _rbody_from_quat(quat))
+
+        # ---- f-2: leg Jacobian ------------------------------------------------------------------------------------
+        for leg in range(2):
+            J = O.leg_jacobian_fm(o["leg_q"][5 * leg: 5 * leg + 5], leg)
+            assert np.abs(J - o["J"][30 * leg: 30 * leg + 30].reshape(6, 5)).max() < 1e-15
+
+        # ---- f-1 / a16: on the ticks the reference solves ------------------------------------------------------------
+        assert o["mpc_ran"] == (k % 5 == 0)
+        if o["mpc_ran"]:
+            n_mpc += 1
+            st = _state_record(o, pos, vel, quat, omega, cmd5)
+            rec = _host_record(H, st, o["rBody"])
+            ref_rec = np.frombuffer(o["update_record"].tobytes(), dtype=scenarios.UPDATE_DTYPE)[0]
+            for f in ("p", "v", "q", "w", "r", "joint_angles", "yaw", "weights", "Alpha_K"):
+                assert rec[f].tobytes() == ref_rec[f].tobytes(), (k, f)
+            assert rec["traj"][: 12 * N].tobytes() == ref_rec["traj"][: 12 * N].tobytes(), k
+            assert np.array_equal(rec["gait"][: 2 * N], ref_rec["gait"][: 2 * N])
+            # clamp write-back (ConvexMPCLocomotion.cpp:338-346)
+            w = o["wpd_entry"].copy()
+            for a in range(2):
+                if w[a] - pos[a] > 0.05:
+                    w[a] = pos[a] + 0.05
+                if pos[a] - w[a] > 0.05:
+                    w[a] = pos[a] - 0.05
+            assert np.array_equal(w[:2], o["wpd"][:2])
+            # f_ff = -rBody [F; M]
+            ff = (ctypes.c_double * 12)()
+            H.hmpc_wrench_to_feedforward(_dp(o["rBody"]), _dp(o["q_soln"][:12].copy()), ff)
+            assert np.array_equal(np.array(ff[:]), o["f_ff"])
+            # f-2: joint torques of the stance legs on this tick (J^T f_ff), the reference's own command path
+            contact = np.array([[1 if np.any(o["ff_cmd"][6 * leg: 6 * leg + 6] != 0) else 0 for leg in range(2)]], np.int32)
+            tau = O.joint_torques(o["q_soln"][:12], o["rBody"], o["leg_q"], contact)[0]
+            assert np.allclose(tau, o["tau"], rtol=2e-6, atol=1e-5), (k, tau, o["tau"])   # lowCmd holds floats
+        else:
+            assert np.array_equal(o["wpd"], o["wpd_entry"])
+
+        # ---- f-4: swing-leg controller, called once per foot by run() (ConvexMPCLocomotion.cpp:218) ------------------
+        st = _state_record(o, pos, vel, quat, omega, cmd5)
+        states = np.array([st])
+        for _ in range(2):
+            cmd = O.swing_update(states, loop, np.array([o["phase"]]), swing, N, dt=DT, dt_swing=DT_MPC)
+        assert np.array_equal(swing["swing_time"][0], o["swing_times"]), k
+        assert np.array_equal(swing["first_swing"][0], o["first_swing"]), k
+        assert np.array_equal(cmd["pf"][0], o["pf"]), k
+        for leg in range(2):
+            sl = slice(3 * leg, 3 * leg + 3)
+            if o["swing_states"][leg] > 0:
+                n_swing_checked += 1
+                assert cmd["swing"][0][leg] == 1
+                assert np.array_equal(swing["p0"][0][sl], o["p0"][sl]), k
+                assert np.array_equal(cmd["p_des"][0][sl], o["p_des"][sl]), k
+                assert np.array_equal(cmd["v_des"][0][sl], o["v_des"][sl]), k
+                d = np.abs(cmd["q_des"][0][5 * leg: 5 * leg + 5] - o["q_des"][5 * leg: 5 * leg + 5]).max()
+                worst_ik = max(worst_ik, d)
+            else:
+                assert cmd["swing"][0][leg] == 0
+    assert n_mpc == n_ticks // 5 and n_swing_checked > 300
+    assert worst_ik < 1e-12, worst_ik
+
+
+def test_standing_tick_is_the_physically_sane_stand(ref):
+    """configs[0] through the reference's whole controller: Fz = 47.84 N per foot."""
+    b = scenarios.stand_inputs(N)
+    ctl = ref.ReferenceController(DT, ITER_MPC)
+    o = ctl.run(1, b["p"], b["v"], b["q"], b["w"], np.zeros(10, np.float32))
+    ctl.close()
+    assert o["mpc_ran"] == 1
+    assert abs(o["q_soln"][2] - 47.84) < 0.05 and abs(o["q_soln"][5] - 47.84) < 0.05
+    assert np.allclose(o["leg_q"], b["q_leg"], atol=1e-6) and np.allclose(o["leg_p"], b["leg_p"].reshape(-1), atol=1e-9)
+    rec = np.frombuffer(o["update_record"].tobytes(), dtype=scenarios.UPDATE_DTYPE)[0]
+    mine = scenarios.to_record(b, N)
+    for f in ("p", "v", "q", "w", "joint_angles", "weights", "Alpha_K", "yaw"):
+        assert np.array_equal(rec[f], mine[f]), f
+    assert np.allclose(rec["r"], mine["r"], atol=1e-7) and np.allclose(rec["traj"][:120], mine["traj"][:120], atol=1e-6)
+
+
+# ---- helpers -----------------------------------------------------------------------------------------------------
+def _dp(a):
+    return np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _rbody_from_quat(q):
+    """orientation_tools.h:182-200, the expression order of the reference (R, then transposed)."""
+    e0, e1, e2, e3 = (float(x) for x in q)
+    R = np.array([[1 - 2 * (e2 * e2 + e3 * e3), 2 * (e1 * e2 - e0 * e3), 2 * (e1 * e3 + e0 * e2)],
+                  [2 * (e1 * e2 + e0 * e3), 1 - 2 * (e1 * e1 + e3 * e3), 2 * (e2 * e3 - e0 * e1)],
+                  [2 * (e1 * e3 - e0 * e2), 2 * (e2 * e3 + e0 * e1), 1 - 2 * (e1 * e1 + e2 * e2)]])
+    return R.T
+
+
+def _host_record(H, st, rBody):
+    se = StateEstimate()
+    se.position[:] = st["position"]; se.orientation[:] = st["orientation"]; se.rpy[:] = st["rpy"]
+    se.rBody[:] = np.asarray(rBody).reshape(-1)
+    se.omegaWorld[:] = st["omegaWorld"]; se.vWorld[:] = st["vWorld"]
+    legs = (LegData * 2)()
+    for leg in range(2):
+        legs[leg].q[:] = st["leg_q"][5 * leg: 5 * leg + 5]
+        legs[leg].p[:] = st["leg_p"][3 * leg: 3 * leg + 3]
+    cmd = Desired()
+    cmd.stateDes[3], cmd.stateDes[4], cmd.stateDes[6], cmd.stateDes[7], cmd.stateDes[11] = st["state_des"]
+    wpd = (ctypes.c_double * 2)(*st["world_position_desired"])
+    table = st["gait"][: 2 * N].astype(np.int32)
+    rec = np.zeros(1, dtype=scenarios.UPDATE_DTYPE)
+    H.hmpc_prepare_record(ctypes.byref(se), legs, ctypes.byref(cmd), wpd, table.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                          ctypes.c_int(N), ctypes.c_double(DT_MPC), rec.ctypes.data_as(ctypes.c_void_p), None)
+    return rec[0]
