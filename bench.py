@@ -214,6 +214,7 @@ def run_reference(args):
                                        "horizon": HORIZON, "sample_per_step": sample},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": f"{sample} solves per step ({sample // cores} per core, cycling through the 1024 records), one solver process per core",
+                         "what": "oracle/_ref/liboracle_mpc.so: solve_mpc restated without Eigen (bit-identical to the reference's own sources compiled against a stand-in, tests/test_reference_compiled.py) + the reference's qpOASES 3.2 compiled unchanged",
                          "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -257,7 +257,7 @@ REFTICK_DTYPE = np.dtype(
         ("mpc_table", "<i4", 20), ("mpc_ran", "<i4"), ("iteration_counter", "<i4"), ("q_soln", "<f8", 120),
         ("f_ff", "<f8", 12), ("swing_states", "<f8", 2), ("swing_times", "<f8", 2), ("first_swing", "<i4", 2),
         ("p0", "<f8", 6), ("pf", "<f8", 6), ("q_des", "<f8", 10), ("p_des", "<f8", 6), ("v_des", "<f8", 6),
-        ("ff_cmd", "<f8", 12), ("tau", "<f8", 10), ("update_record", "u1", 3016),
+        ("ff_cmd", "<f8", 12), ("cmpc_pf", "<f8", 6), ("tau", "<f8", 10), ("update_record", "u1", 3016),
     ],
     align=True,
 )

@@ -126,6 +126,7 @@ struct reftick_out_t {
   double p0[6], pf[6];      /* swing.footSwingTrajectory[leg]._p0 / _pf */
   double q_des[10], p_des[6], v_des[6];   /* commands[leg].qDes / pDes / vDes after run */
   double ff_cmd[12];        /* commands[leg].feedforwardForce after run */
+  double cmpc_pf[6];        /* cmpc.footSwingTrajectories[leg]._pf: run()'s own touch-down heuristic (ConvexMPCLocomotion.cpp:119-160) */
   /* after LegController::updateCommand */
   double tau[10];           /* lowCmd.motorCmd[].tau */
   unsigned char update_record[sizeof(update_data_t)]; /* the global `update` record (valid when mpc_ran) */
@@ -220,6 +221,7 @@ void reftick_run(void* h, int gait_number, const double* position, const double*
     for (int k = 0; k < 3; k++) {
       out->p0[3 * leg + k] = t.cmpc.swing.footSwingTrajectory[leg]._p0[k];
       out->pf[3 * leg + k] = t.cmpc.swing.footSwingTrajectory[leg]._pf[k];
+      out->cmpc_pf[3 * leg + k] = t.cmpc.footSwingTrajectories[leg]._pf[k];
       out->p_des[3 * leg + k] = t.legs.commands[leg].pDes(k);
       out->v_des[3 * leg + k] = t.legs.commands[leg].vDes(k);
     }

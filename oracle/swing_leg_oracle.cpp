@@ -12,8 +12,13 @@
  *   hector_control/src/common/SwingLegController.cpp:160-193  computeIK
  * on the record layouts of include/hector_mpc_b200.h (hmpc_state_t, hmpc_rollout_t, hmpc_swing_t, hmpc_swing_cmd_t).
  *
- * PARITY STATUS: *parity unpinned* — the reference has no tests or vectors for this controller and its sources need
- * Eigen/ROS, absent here; the arithmetic is restated expression by expression (including the float clamp of the
+ * PARITY STATUS: pinned against the reference's own sources.  The reference has no tests or vectors for this
+ * controller, and its sources need Eigen (absent here); oracle/Makefile compiles SwingLegController.cpp,
+ * FootSwingTrajectory.cpp, GaitGenerator.cpp, LegController.cpp and ConvexMPCLocomotion.cpp UNCHANGED against
+ * oracle/eigen_shim into oracle/_ref/libref_tick.so, and tests/test_reference_tick.py requires this restatement to
+ * reproduce that controller tick by tick (520 ticks of walking, two updateSwingLeg calls per tick as
+ * ConvexMPCLocomotion::run makes them): controller memory, touch-down point, pDes and vDes bit for bit, the IK joint
+ * targets within 1e-12 rad.  The arithmetic is restated expression by expression (including the float clamp of the
  * placement offsets, fminf/fmaxf at :117-118, and M_PI in the joint offsets at :190-192).
  */
 #include <algorithm>

@@ -6,6 +6,7 @@ against oracle/eigen_shim; oracle/ref_tick_probe.cpp ticks them the way FSMState
 walked through more than a full gait cycle with a smoothly varying pose, and on every tick
 
   f-3  Gait::setIterations / mpc_gait          == scenarios.gait_phase / scenarios.mpc_gait
+       run()'s touch-down heuristic            == the formula the closed-loop harness places feet with
   f-1  the `update_data_t` record the reference's updateMPCIfNeeded hands to solve_mpc
                                               == csrc/locomotion_host.cpp hmpc_prepare_record, BYTE FOR BYTE (live fields)
        the clamp write-back of world_position_desired                       == the host mirror's
@@ -140,6 +141,18 @@ def test_walking_ticks_match_the_reference_controller(oracle, source):
             assert np.allclose(tau, o["tau"], rtol=2e-6, atol=1e-5), (k, tau, o["tau"])   # lowCmd holds floats
         else:
             assert np.array_equal(o["wpd"], o["wpd_entry"])
+
+        # ---- f-3: the touch-down heuristic of run() (ConvexMPCLocomotion.cpp:119-160) the closed-loop harness places feet
+        #      with: hip projection + v * (remaining swing time) + clamp(0.5 v T_stance + 0.02 (v - v_des), +-0.4), z = 0.
+        #      (run() never clears its firstSwing flags, so the remaining swing time stays dtMPC * _swing.)
+        R = o["rBody"].reshape(3, 3).T
+        vdw = R @ np.array([v_des[0], v_des[1], 0.0])
+        for leg in range(2):
+            rel = np.clip(vel[:2] * 0.5 * 5 * DT_MPC + 0.02 * (vel[:2] - vdw[:2]), -0.4, 0.4).astype(np.float32)
+            want = pos + R @ scenarios.hip_yaw_location(leg) + vel * (DT_MPC * 5)
+            want[:2] += rel
+            want[2] = -0.0
+            assert np.abs(want - o["cmpc_pf"][3 * leg: 3 * leg + 3]).max() < 1e-7   # the reference clamps through floats (:152-153)
 
         # ---- f-4: swing-leg controller, called once per foot by run() (ConvexMPCLocomotion.cpp:218) ------------------
         st = _state_record(o, pos, vel, quat, omega, cmd5)
