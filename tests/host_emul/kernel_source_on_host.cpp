@@ -1,0 +1,211 @@
+// tests/host_emul/kernel_source_on_host.cpp — TEST INFRASTRUCTURE (CPU suite only), see fake_cuda/cuda_runtime.h.
+//
+// Includes the product's device header through the fake CUDA prelude and runs, on the host,
+//   * the one-thread-per-robot kernels  hmpc_prepare_kernel (row f-1), hmpc_advance_kernel (f-3), hmpc_swing_kernel (f-4)
+//     — one call per robot with threadIdx/blockIdx set the way a launch would set them;
+//   * the stage-1 device functions of the solve kernel (role_leg / role_state / role_inertia: SRBD linearisation, foot
+//     rotations, constraint rows) and the joint-torque epilogue function (leg_torque, f-2).
+//   * the classification kernel and the solve kernel itself (all stages), one OS thread per CUDA thread of one CTA at a
+//     time, launched the way hmpc_capi.cu's enqueue_solve launches them (classification -> class 0 -> class 1 -> class 2
+//     with working-set-overflow escalation through the lists)
+// so that tests/test_kernel_source_on_host.py can hold the kernels' SOURCE to the oracle / to the reference's compiled
+// controller without a GPU.
+#include <cstring>
+#include <thread>
+#include <vector>
+
+// HMPC_DEVICE_HEADER: hector_simulation_b200/csrc/hmpc_device.cuh after the test's build step (test_kernel_source_on_host.py,
+// `_host_buildable`) has made the handful of substitutions a host compiler needs, each asserted to hit exactly once:
+//   - the four PTX helper bodies (mbar_init / mbar_expect_tx / mbar_wait / bulk_g2s) -> calls to hmpc_emul_* (cuda_runtime.h)
+//   - the `rcp.approx.ftz.f64` seed of fast_rcp -> `1.0 / x` (the Newton steps that follow are kept)
+//   - the dynamic shared-memory declaration -> a pointer to the emulated CTA's buffer
+//   - every other `asm volatile(...)` (fences, griddepcontrol: no arithmetic) -> nothing
+// Everything else is the product's source, byte for byte.
+#include HMPC_DEVICE_HEADER
+
+thread_local hmpc_emul_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local hmpc_emul::Cta* hmpc_emul_cta = nullptr;
+
+namespace hmpc_emul {
+unsigned char* cta_smem()
+{
+  alignas(16) static unsigned char buf[256 * 1024];
+  return buf;
+}
+}  // namespace hmpc_emul
+
+namespace {
+// run `fn()` on NT OS threads as the NT CUDA threads of the single CTA of a 1-CTA grid
+template <class F>
+void run_cta(int NT, F fn)
+{
+  hmpc_emul::Cta* cta = new hmpc_emul::Cta;
+  cta->bar.count = NT;
+  for (int w = 0; w < 32; w++) cta->warps[w].bar.count = 32;
+  std::vector<std::thread> th;
+  th.reserve(NT);
+  for (int t = 0; t < NT; t++)
+    th.emplace_back([=] {
+      threadIdx = {(unsigned)t, 0, 0};
+      blockIdx = {0, 0, 0};
+      blockDim = {(unsigned)NT, 1, 1};
+      gridDim = {1, 1, 1};
+      hmpc_emul_cta = cta;
+      fn();
+      hmpc_emul_cta = nullptr;
+    });
+  for (auto& x : th) x.join();
+  delete cta;
+}
+
+// the kernel variants of hmpc_capi.cu (HMPC_FOR_VARIANT): <threads, min CTAs/SM, strip, fixed horizon, class>
+void launch_variant(int variant, const hmpc::KernelArgs& ka)
+{
+  switch (variant) {
+    case 0: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 6, 10, 0>(ka); }); break;
+    case 1: run_cta(224, [=] { hmpc::hmpc_solve_kernel<224, 2, 6, 10, 1>(ka); }); break;
+    case 3: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 6, 0, 0>(ka); }); break;
+    case 4: run_cta(224, [=] { hmpc::hmpc_solve_kernel<224, 2, 6, 0, 0>(ka); }); break;
+    case 5: run_cta(544, [=] { hmpc::hmpc_solve_kernel<544, 1, 6, 0, 0>(ka); }); break;
+    case 6: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 6, 0, 1>(ka); }); break;
+    case 7: run_cta(224, [=] { hmpc::hmpc_solve_kernel<224, 2, 6, 0, 1>(ka); }); break;
+    default: run_cta(544, [=] { hmpc::hmpc_solve_kernel<544, 1, 6, 0, 1>(ka); }); break;
+  }
+}
+struct ClassCfg {
+  int variant, nb_cap, qmax;
+  hmpc::Layout L;
+};
+// hmpc_capi.cu build_classes, minus the CUDA occupancy calls
+int build_classes(int N, ClassCfg* cls)
+{
+  const int rs = hmpc::record_stride(N);
+  int ncls = 3;
+  for (int i = 0; i < 2; i++) {
+    ClassCfg& k = cls[i];
+    k.nb_cap = hmpc::class_nb_cap(N, i);
+    const int n = 6 * k.nb_cap, nbt = k.nb_cap * (k.nb_cap + 1) / 2, need = nbt > n ? nbt : n;
+    const int bucket = need <= 64 ? 0 : (need <= 224 ? 1 : 2);
+    k.variant = (N == 10) ? i : 3 + 3 * i + bucket;
+    k.qmax = hmpc::class_qmax(N, i);
+    k.L = hmpc::class_layout(N, i);
+  }
+  {
+    ClassCfg& k = cls[2];
+    k = cls[1];
+    const int n = 6 * k.nb_cap;
+    k.qmax = n;
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs);
+    while (k.L.total > 226 * 1024 && k.qmax > cls[1].qmax) {
+      k.qmax -= 4;
+      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs);
+    }
+    if (k.qmax <= cls[1].qmax) ncls = 2;
+    const int nbt = k.nb_cap * (k.nb_cap + 1) / 2, need = nbt > n ? nbt : n;
+    k.variant = 6 + (need <= 64 ? 0 : (need <= 224 ? 1 : 2));
+  }
+  return ncls;
+}
+const unsigned kBlock = 128;
+inline void set_thread(int i)
+{
+  blockDim = {kBlock, 1, 1};
+  blockIdx = {(unsigned)i / kBlock, 0, 0};
+  threadIdx = {(unsigned)i % kBlock, 0, 0};
+  gridDim = {1u << 20, 1, 1};
+}
+}  // namespace
+
+extern "C" {
+
+int emul_record_stride(int N) { return hmpc::record_stride(N); }
+
+void emul_prepare(const unsigned char* states, int batch, int N, double dtMPC, unsigned char* records)
+{
+  for (int i = 0; i < batch; i++) {
+    set_thread(i);
+    hmpc::hmpc_prepare_kernel(states, batch, N, dtMPC, records, hmpc::record_stride(N));
+  }
+}
+
+void emul_advance(unsigned char* states, unsigned char* loop, int batch, int N, double dtMPC, const float* wrench,
+                  const int* status)
+{
+  for (int i = 0; i < batch; i++) {
+    set_thread(i);
+    hmpc::hmpc_advance_kernel(states, loop, batch, N, dtMPC, wrench, status, nullptr);
+  }
+}
+
+void emul_swing(const unsigned char* states, const unsigned char* loop, const double* phase, unsigned char* swing, int batch,
+                int n_iterations, double dt, double dtSwing, unsigned char* cmd)
+{
+  for (int i = 0; i < batch; i++) {
+    set_thread(i);
+    hmpc::hmpc_swing_kernel(states, loop, phase, swing, batch, n_iterations, dt, dtSwing, cmd);
+  }
+}
+
+/* stage 1 of the solve kernel on one packed record's floats `rf` (layout: hmpc_device.cuh, "record floats"):
+ * Fblk [192] (both legs' constraint rows), x0 [13], Acd [169], Bcd [156] — pre-zeroed as the kernel does. */
+void emul_stage1(const float* rf, float dt, float* Fblk, float* x0, float* Acd, float* Bcd)
+{
+  memset(Fblk, 0, 192 * sizeof(float));
+  memset(Acd, 0, 169 * sizeof(float));
+  memset(Bcd, 0, 156 * sizeof(float));
+  float x0f[16] = {0};
+  hmpc::role_leg(rf, 0, Fblk);
+  hmpc::role_leg(rf, 1, Fblk);
+  hmpc::role_state(rf, dt, x0f, Acd);
+  hmpc::role_inertia(rf, dt, Bcd);
+  memcpy(x0, x0f, 13 * sizeof(float));
+}
+
+/* The device-resident solve path of hmpc_capi.cu (enqueue_solve): classification kernel, then one launch per size class
+ * with escalation lists; B <= 1024 packed records.  Outputs: wrench [B][12N] floats, status [B], tau [B][10] or NULL,
+ * launched[3] = instances each class processed (NULL to skip).  Optional assembly dump (all NULL, or all given):
+ * H [B][n*n], g [B][n], Fblk [B][192], lb/ub [B][16N]. */
+int emul_solve(const unsigned char* records, int B, int N, float dt, float f_max, int max_iter, float* wrench, int* status,
+               float* tau, int* launched, float* dH, float* dg, float* dF, float* dlb, float* dub)
+{
+  if (B < 1 || B > 1024) return 1;
+  ClassCfg cls[3];
+  const int ncls = build_classes(N, cls);
+  std::vector<int> block(4 + 3 * (size_t)B, 0);
+  int* counts = block.data();
+  int* lists = counts + 4;
+  const int rs = hmpc::record_stride(N);
+  const int nb_hi0 = cls[0].nb_cap;
+  run_cta((B + 31) / 32 * 32, [=] { hmpc::hmpc_classify1_kernel(records, rs, B, N, f_max, nb_hi0, counts, lists, B); });
+  for (int i = 0; i < ncls; i++) {
+    if (launched) launched[i] = counts[i];
+    if (counts[i] == 0) continue;
+    hmpc::KernelArgs ka{};
+    ka.records = records;
+    ka.rec_stride = rs;
+    ka.batch = B;
+    ka.horizon = N;
+    ka.dt = dt;
+    ka.f_max = f_max;
+    ka.max_iter = max_iter;
+    ka.wrench = wrench;
+    ka.status = status;
+    ka.tau = tau;
+    ka.warm_start = 0;
+    ka.list = lists + (size_t)i * B;
+    ka.counts = counts;
+    ka.cls = i;
+    ka.esc_list = (i + 1 < ncls) ? lists + (size_t)(i + 1) * B : nullptr;
+    ka.nb_cap = cls[i].nb_cap;
+    ka.qmax = cls[i].qmax;
+    ka.L = cls[i].L;
+    ka.dbg_H = dH; ka.dbg_g = dg; ka.dbg_F = dF; ka.dbg_lb = dlb; ka.dbg_ub = dub;
+    launch_variant(cls[i].variant, ka);
+  }
+  return 0;
+}
+
+/* the torque epilogue's per-joint function: tau_j = column j of J_force_moment(q5, leg) . f6 */
+double emul_leg_torque(const double* q5, int leg, int j, const double* f6) { return hmpc::leg_torque(q5, leg, j, f6); }
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+"""CPU: the SOURCE of the product's device code, compiled for the host through a fake CUDA prelude and held to the oracle
+and to the reference's compiled controller — without a GPU.
+
+tests/host_emul/ builds hector_simulation_b200/csrc/hmpc_device.cuh (inline PTX blanked, nothing else changed) into a
+throw-away host library and runs the one-thread-per-robot kernels (data preparation f-1, closed-loop advance f-3,
+swing-leg controller f-4) plus the stage-1 device functions of the solve kernel (SRBD linearisation, foot rotations,
+constraint rows, a5-a11) and the torque epilogue function (f-2).  This is test infrastructure: the product has no CPU path
+(test_capi_cpu.py asserts that), and the cooperative stages of the solve kernel are covered by the -m gpu tests only.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from hector_simulation_b200 import interface, scenarios
+
+HERE = os.path.join(ROOT, "tests", "host_emul")
+BUILD = os.path.join(HERE, "_build")
+DEVICE_HEADER = os.path.join(ROOT, "hector_simulation_b200", "csrc", "hmpc_device.cuh")
+
+
+def _blank_inline_ptx(text: str):
+    """Replace every `asm volatile( ... );` statement by a comment, matching parentheses outside string literals."""
+    out, i, n = [], 0, 0
+    key = "asm volatile("
+    while True:
+        j = text.find(key, i)
+        if j < 0:
+            out.append(text[i:])
+            return "".join(out), n
+        out.append(text[i:j])
+        k, depth, in_str = j + len(key), 1, False
+        while depth:
+            c = text[k]
+            if in_str:
+                if c == "\\":
+                    k += 1
+                elif c == '"':
+                    in_str = False
+            elif c == '"':
+                in_str = True
+            elif c == "(":
+                depth += 1
+            elif c == ")":
+                depth -= 1
+            k += 1
+        assert text[k] == ";", text[j:k + 20]
+        out.append("/* inline PTX blanked for the host build */")
+        i, n = k, n + 1
+
+
+def _replace_body(text: str, signature: str, body: str) -> str:
+    """Swap the body of the (unique) function whose definition starts with `signature`."""
+    assert text.count(signature) == 1, signature
+    j = text.index(signature) + len(signature)
+    k = text.index("{", j)
+    depth, e = 1, k + 1
+    while depth:
+        depth += {"{": 1, "}": -1}.get(text[e], 0)
+        e += 1
+    return text[:k] + "{ " + body + " }" + text[e:]
+
+
+def _host_buildable(src: str) -> str:
+    """The substitutions a host compiler needs (documented in tests/host_emul/kernel_source_on_host.cpp)."""
+    src = _replace_body(src, "void mbar_init(uint64_t* bar, int count)", "(void)count; hmpc_emul_mbar_init(bar);")
+    src = _replace_body(src, "void mbar_expect_tx(uint64_t* bar, uint32_t bytes)", "(void)bar; (void)bytes;")
+    src = _replace_body(src, "void mbar_wait(uint64_t* bar, uint32_t phase)", "hmpc_emul_mbar_wait(bar, phase);")
+    src = _replace_body(src, "void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)",
+                        "hmpc_emul_bulk_g2s(dst, src, bytes, bar);")
+    rcp = 'asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));'
+    assert src.count(rcp) == 1
+    src = src.replace(rcp, "r = 1.0 / x;  /* host build: exact seed instead of MUFU.RCP64H */")
+    smem = "extern __shared__ __align__(16) unsigned char smem[];"
+    assert src.count(smem) == 1
+    src = src.replace(smem, "unsigned char* const smem = hmpc_emul::cta_smem();")
+    src, n = _blank_inline_ptx(src)
+    assert n == 4, n   # pdl_trigger, pdl_wait, fence.mbarrier_init, fence.proxy.async
+    assert "asm" not in src.replace("/* inline PTX blanked", "")
+    return src
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(BUILD, exist_ok=True)
+    hdr = os.path.join(BUILD, "hmpc_device_host.cuh")
+    with open(hdr, "w") as f:
+        f.write(_host_buildable(open(DEVICE_HEADER).read()))
+    lib = os.path.join(BUILD, "libkernel_source_on_host.so")
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread",
+           "-I" + os.path.join(HERE, "fake_cuda"), "-I" + os.path.join(ROOT, "include"),
+           '-DHMPC_DEVICE_HEADER="%s"' % hdr, os.path.join(HERE, "kernel_source_on_host.cpp"), "-o", lib,
+           "-l:libstdc++.so.6"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(lib)
+    L.emul_leg_torque.restype = ctypes.c_double
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _prepare(L, states, N, dt_mpc=0.04):
+    B = len(states)
+    stride = L.emul_record_stride(N)
+    assert stride == interface.record_bytes(N)
+    out = np.full((B, stride), 0xAB, np.uint8)
+    st = np.ascontiguousarray(states)
+    L.emul_prepare(_p(st), B, N, ctypes.c_double(dt_mpc), _p(out))
+    return out
+
+
+# ---- f-1 ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("horizon,cfg,batch", [(10, 3, 96), (5, 4, 32), (16, 4, 32), (10, 1, 4)])
+def test_prepare_kernel_source_equals_host_mirror(emul, horizon, cfg, batch):
+    from test_state_prepare import _host_prepared
+
+    _, inputs = scenarios.make_batch(cfg, batch, horizon=horizon)
+    states = scenarios.make_states(inputs, horizon)
+    want = interface.pack_records(_host_prepared(states, horizon), horizon)
+    got = _prepare(emul, states, horizon)
+    assert np.array_equal(got, want)
+
+
+def test_prepare_kernel_source_reproduces_the_reference_controllers_records(emul, oracle):
+    from test_reference_tick import DT_MPC, FIXTURE, N, _pose, _state_record
+
+    ticks = np.load(FIXTURE)["ticks"].view(oracle.REFTICK_DTYPE).reshape(-1)
+    which = np.nonzero(ticks["mpc_ran"])[0]
+    cmd5 = np.array([0.01, -0.02, 0.3, 0.05, 0.2])
+    states = np.zeros(len(which), dtype=scenarios.STATE_DTYPE)
+    for n, k in enumerate(which):
+        pos, rpy, vel, omega, _ = _pose(int(k), (0.3, 1.1, 2.0))
+        states[n] = _state_record(ticks[k], pos, vel, scenarios.rpy_to_quat(rpy), omega, cmd5)
+    ref = np.array([np.frombuffer(ticks[k]["update_record"].tobytes(), dtype=scenarios.UPDATE_DTYPE)[0] for k in which])
+    assert np.array_equal(_prepare(emul, states, N, DT_MPC), interface.pack_records(ref, N))
+
+
+# ---- f-4 ------------------------------------------------------------------------------------------------------------
+def test_swing_kernel_source_follows_the_reference_controller(emul, oracle):
+    from test_reference_tick import DT, DT_MPC, FIXTURE, N, _pose, _state_record
+
+    ticks = np.load(FIXTURE)["ticks"].view(oracle.REFTICK_DTYPE).reshape(-1)
+    cmd5 = np.array([0.01, -0.02, 0.3, 0.05, 0.2])
+    loop = np.zeros(1, dtype=scenarios.ROLLOUT_DTYPE)
+    loop["gait_offset"], loop["gait_duration"] = (0, 5), (5, 5)
+    sw = scenarios.make_swing(1)
+    cmd = np.zeros(1, dtype=scenarios.SWING_CMD_DTYPE)
+    checked, worst_q = 0, 0.0
+    for k, o in enumerate(ticks):
+        pos, rpy, vel, omega, _ = _pose(k, (0.3, 1.1, 2.0))
+        st = np.array([_state_record(o, pos, vel, scenarios.rpy_to_quat(rpy), omega, cmd5)])
+        ph = np.array([o["phase"]])
+        for _ in range(2):
+            emul.emul_swing(_p(st), _p(loop), _p(ph), _p(sw), 1, N, ctypes.c_double(DT), ctypes.c_double(DT_MPC), _p(cmd))
+        assert np.array_equal(sw["swing_time"][0], o["swing_times"]) and np.array_equal(sw["first_swing"][0], o["first_swing"]), k
+        assert np.array_equal(cmd["pf"][0], o["pf"]), k
+        for leg in range(2):
+            s3, s5 = slice(3 * leg, 3 * leg + 3), slice(5 * leg, 5 * leg + 5)
+            if o["swing_states"][leg] > 0:
+                checked += 1
+                assert cmd["swing"][0][leg] == 1
+                assert np.array_equal(sw["p0"][0][s3], o["p0"][s3]), k
+                assert np.array_equal(cmd["p_des"][0][s3], o["p_des"][s3]) and np.array_equal(cmd["v_des"][0][s3], o["v_des"][s3]), k
+                worst_q = max(worst_q, float(np.abs(cmd["q_des"][0][s5] - o["q_des"][s5]).max()))
+            else:
+                assert cmd["swing"][0][leg] == 0 and not cmd["q_des"][0][s5].any()
+    assert checked > 300 and worst_q < 1e-12
+
+
+# ---- f-3 ------------------------------------------------------------------------------------------------------------
+def test_advance_kernel_source_equals_numpy_mirror(emul):
+    N, B = 10, 48
+    _, inputs = scenarios.make_batch(2, B, horizon=N, seed=11)
+    states, loop = scenarios.make_rollout(inputs, N)
+    s_k, l_k = states.copy(), loop.copy()
+    rng = np.random.default_rng(3)
+    for tick in range(12):
+        wrench = np.zeros((B, 12 * N), np.float32)
+        wrench[:, 2] = wrench[:, 5] = 45.0
+        wrench[:, :12] += rng.normal(0, 2.0, (B, 12)).astype(np.float32)
+        status = (rng.integers(0, 15, B) << 8).astype(np.int32)
+        scenarios.advance_numpy(states, loop, wrench, status, N)
+        emul.emul_advance(_p(s_k), _p(l_k), B, N, ctypes.c_double(0.04), _p(wrench), _p(status))
+        for f in ("position", "vWorld", "orientation", "omegaWorld", "rpy", "leg_p", "world_position_desired"):
+            assert np.abs(s_k[f] - states[f]).max() < 1e-12, (tick, f)
+        assert np.array_equal(s_k["gait"], states["gait"])
+        assert np.abs(l_k["feet_world"] - loop["feet_world"]).max() < 1e-12
+        for f in ("iteration", "failures", "iters_total", "ticks"):
+            assert np.array_equal(l_k[f], loop[f]), f
+
+
+# ---- a5-a11: stage 1 of the solve kernel ------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [2, 3])
+def test_stage1_source_is_bit_exact_against_the_oracle(emul, oracle, cfg):
+    N, B = 10, 64
+    recs, _ = scenarios.make_batch(cfg, B, horizon=N, seed=5 + cfg)
+    setup = oracle.make_setup(N)
+    packed = interface.pack_records(recs, N)
+    for i in range(B):
+        rf = np.ascontiguousarray(packed[i, : 54 * 4].view(np.float32))
+        Fblk, x0 = np.zeros(192, np.float32), np.zeros(13, np.float32)
+        Acd, Bcd = np.zeros(169, np.float32), np.zeros(156, np.float32)
+        emul.emul_stage1(_p(rf), ctypes.c_float(0.04), _p(Fblk), _p(x0), _p(Acd), _p(Bcd))
+        F = oracle.formulate_f32(recs[i], setup)
+        assert np.array_equal(Fblk.reshape(16, 12), F["Fblk"]), i
+        assert np.array_equal(x0, F["x0"]), i
+        assert np.array_equal(Acd.reshape(13, 13), F["Acd"]), i
+        assert np.array_equal(Bcd.reshape(13, 12), F["Bcd"]), i
+
+
+# ---- f-2: torque epilogue function -------------------------------------------------------------------------------------
+def test_leg_torque_source_equals_jacobian_transpose(emul, oracle):
+    rng = np.random.default_rng(2)
+    for _ in range(40):
+        q5, f6 = rng.normal(0, 0.8, 5), rng.normal(0, 30, 6)
+        for leg in (0, 1):
+            J = oracle.leg_jacobian_fm(q5, leg)
+            want = J.T @ f6
+            got = np.array([emul.emul_leg_torque(_p(q5), leg, j, _p(f6)) for j in range(5)])
+            assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+# ---- the solve kernel itself, all stages, one OS thread per CUDA thread ------------------------------------------------
+def _solve(L, records, N, dump=False, tau=True):
+    """The device-resident path of hmpc_capi.cu (classification + class launches + escalation) on the host."""
+    B = len(records)
+    packed = np.ascontiguousarray(interface.pack_records(records, N))
+    n = 12 * N
+    w = np.zeros((B, n), np.float32)
+    st = np.full(B, -1, np.int32)
+    t = np.zeros((B, 10), np.float32)
+    launched = np.zeros(3, np.int32)
+    d = None
+    if dump:
+        d = dict(H=np.zeros((B, n, n), np.float32), g=np.zeros((B, n), np.float32), Fblk=np.zeros((B, 16, 12), np.float32),
+                 lb=np.zeros((B, 16 * N), np.float32), ub=np.zeros((B, 16 * N), np.float32))
+    ptrs = [_p(d[k]) for k in ("H", "g", "Fblk", "lb", "ub")] if dump else [None] * 5
+    rc = L.emul_solve(_p(packed), B, N, ctypes.c_float(0.04), ctypes.c_float(500.0), 500, _p(w), _p(st), _p(t) if tau else None,
+                      _p(launched), *ptrs)
+    assert rc == 0
+    return w.astype(np.float64), st, t.astype(np.float64), launched, d
+
+
+def test_solve_kernel_source_assembly_is_bit_exact(emul):
+    """Stages 0-3 of the kernel source (TMA staging, SRBD linearisation, powers/Toeplitz blocks, prefix-chain Hessian, swing
+    elimination), through the kernel's own assembly-dump mode, against the golden fp32 QP data — the bar the -m gpu suite
+    holds the GPU to, here for the source executed on the host."""
+    from conftest import load_golden
+
+    for name in ("cfg2_h10", "cfg3_h10", "cfg4_h5"):
+        g = load_golden(name)
+        N, nf = g["horizon"], g["H"].shape[0]
+        _, _, _, _, d = _solve(emul, g["records"][:nf], N, dump=True)
+        iu = np.triu_indices(12 * N)
+        for i in range(nf):
+            assert np.array_equal(d["H"][i][iu].view(np.uint32), g["H"][i][iu].view(np.uint32)), (name, i)
+            assert np.array_equal(d["H"][i], d["H"][i].T)
+            for k in ("g", "lb", "ub", "Fblk"):
+                assert np.array_equal(d[k][i].view(np.uint32), g[k][i].view(np.uint32)), (name, i, k)
+
+
+def test_solve_kernel_source_single_support_class(emul, oracle):
+    """Class 0 (64 threads per CTA, compile-time horizon-10 layout): walking-gait robots of configs[1]."""
+    from conftest import load_golden, rel_err
+
+    g = load_golden("cfg2_h10")
+    B = 6
+    w, st, tau, launched, _ = _solve(emul, g["records"][:B], 10)
+    assert launched.tolist() == [B, 0, 0]
+    assert (interface.status_code(st) == 0).all()
+    assert rel_err(w, g["q_soln"][:B], 12).max() < 5e-6 and rel_err(w, g["q_soln"][:B]).max() < 5e-5
+    assert (w[g["q_soln"][:B] == 0.0] == 0.0).all()
+    assert np.array_equal(interface.status_iters(st), g["info"][:B, 1])       # same number of working-set changes as qpOASES
+    # torque epilogue (row f-2) of the same launch
+    _, inputs = scenarios.make_batch(2, 64, horizon=10)
+    rB = np.array([b["rBody"] for b in inputs[:B]]); ql = np.array([b["q_leg"] for b in inputs[:B]])
+    contact = np.array([b["gait"][:2] for b in inputs[:B]])
+    ref_tau = oracle.joint_torques(g["q_soln"][:B, :12], rB, ql, contact)
+    assert rel_err(tau, ref_tau).max() < 1e-4
+
+
+def test_solve_kernel_source_double_support_class(emul):
+    """Class 1 (224 threads per CTA, 120 variables): the stand of configs[0] and the standing robots of configs[2]."""
+    from conftest import load_golden, rel_err
+
+    g1, g3 = load_golden("cfg1_h10"), load_golden("cfg3_h10")
+    stand = np.nonzero(g3["info"][:, 2] == 120)[0][:2]
+    recs = np.concatenate([g1["records"][:1], g3["records"][stand]])
+    want = np.concatenate([g1["q_soln"][:1], g3["q_soln"][stand]])
+    w, st, _, launched, _ = _solve(emul, recs, 10, tau=False)
+    assert launched.tolist() == [0, len(recs), 0]
+    assert (interface.status_code(st) == 0).all()
+    assert rel_err(w, want, 12).max() < 5e-5 and rel_err(w, want).max() < 5e-5
+    assert abs(w[0, 2] - 47.84) < 0.05 and abs(w[0, 5] - 47.84) < 0.05
+
+
+def test_solve_kernel_source_runtime_horizon(emul):
+    """The runtime-layout instantiations (horizon 5): mixed contact schedules, both classes."""
+    from conftest import load_golden, rel_err
+
+    g = load_golden("cfg4_h5")
+    B = 8
+    w, st, _, launched, _ = _solve(emul, g["records"][:B], 5, tau=False)
+    assert launched[:2].sum() == B and launched[2] == 0
+    assert (interface.status_code(st) == 0).all()
+    assert rel_err(w, g["q_soln"][:B], 12).max() < 5e-6 and rel_err(w, g["q_soln"][:B]).max() < 5e-5
+    assert (w[g["q_soln"][:B] == 0.0] == 0.0).all()
+
+
+def test_solve_kernel_source_escalates_a_degenerate_optimum(emul):
+    """Working-set overflow: class 1 hands the falling robot to class 2 through the escalation list (the kernel appends to
+    the next class's list itself), which still returns a KKT point on the fp64 referee's optimum."""
+    from conftest import load_golden
+
+    g = load_golden("degenerate_zero_force_h10")
+    w, st, _, launched, _ = _solve(emul, g["records"], 10, tau=False)
+    assert launched.tolist() == [0, 1, 1]
+    assert (interface.status_code(st) == 0).all(), st
+    assert interface.status_nactive(st).max() > 64
+    assert np.abs(w - g["q_soln"]).max() < 5e-3
+    assert np.abs(w - g["q_referee"]).max() < 2e-5
+    assert np.abs(w[:, :6]).max() < 1e-3
+
+
+def test_solve_kernel_source_against_the_compiled_reference(emul):
+    """The kernel source against outputs of the reference's own solve_mpc (tests/golden/ref_compiled_h10.npz): the 1e-4
+    contract, no restatement in between."""
+    from conftest import GOLDEN, load_golden, rel_err
+
+    z = np.load(os.path.join(GOLDEN, "ref_compiled_h10.npz"))
+    g = load_golden("cfg3_h10")
+    B = 8
+    w, st, _, _, _ = _solve(emul, g["records"][:B], 10, tau=False)
+    assert (interface.status_code(st) == 0).all()
+    assert rel_err(w, z["cfg3_q"][:B], 12).max() < 1e-4 and rel_err(w, z["cfg3_q"][:B]).max() < 1e-4
