@@ -339,3 +339,29 @@ def test_solve_kernel_source_against_the_compiled_reference(emul):
     w, st, _, _, _ = _solve(emul, g["records"][:B], 10, tau=False)
     assert (interface.status_code(st) == 0).all()
     assert rel_err(w, z["cfg3_q"][:B], 12).max() < 1e-4 and rel_err(w, z["cfg3_q"][:B]).max() < 1e-4
+
+
+# ---- race check of the kernel source (ThreadSanitizer on the emulated CTA) ----------------------------------------------
+def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
+    """Every CUDA thread is an OS thread and every barrier / warp primitive real synchronisation, so ThreadSanitizer sees
+    any two conflicting accesses the kernel does not order (removing a single __syncwarp from the active-set loop makes it
+    report within one QP).  Paths: class 0, class 1, class 1 -> class 2 escalation, runtime-horizon variants."""
+    from conftest import load_golden
+
+    exe = os.path.join(BUILD, "race_driver_tsan")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=thread", "-w", "-pthread",
+           "-I" + os.path.join(HERE, "fake_cuda"), "-I" + os.path.join(ROOT, "include"),
+           '-DHMPC_DEVICE_HEADER="%s"' % os.path.join(BUILD, "hmpc_device_host.cuh"),
+           os.path.join(HERE, "kernel_source_on_host.cpp"), os.path.join(HERE, "race_driver.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime with this toolchain: " + r.stderr[-300:])
+    cases = [("cfg2_h10", [0, 1, 2]), ("cfg1_h10", [0]), ("degenerate_zero_force_h10", [0]), ("cfg4_h5", [0, 1, 2, 3])]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66")
+    for name, idx in cases:
+        g = load_golden(name)
+        f = tmp_path / (name + ".bin")
+        np.ascontiguousarray(interface.pack_records(g["records"][idx], g["horizon"])).tofile(f)
+        r = subprocess.run([exe, str(f), str(g["horizon"])], capture_output=True, text=True, env=env, timeout=900)
+        assert "ThreadSanitizer" not in r.stderr, (name, r.stderr[:3000])
+        assert r.returncode == 0, (name, r.returncode, r.stdout, r.stderr[-500:])
