@@ -27,6 +27,15 @@ def main():
     ticks = np.array(list(T.reference_ticks(O)), dtype=O.REFTICK_DTYPE)
     np.savez_compressed(os.path.join(HERE, "ref_tick_walk.npz"), ticks=ticks.view(np.uint8).reshape(len(ticks), -1))
     print(len(ticks), "ticks,", int(ticks["mpc_ran"].sum()), "MPC solves")
+    # ref_tick_cases.npz: the shorter cases of test_reference_tick.CASES (zero command under the walking gait, standing gait)
+    more = {}
+    for case in T.CASES:
+        if case == "walk":
+            continue
+        t = np.array(list(T.reference_ticks(O, case)), dtype=O.REFTICK_DTYPE)
+        more[case] = t.view(np.uint8).reshape(len(t), -1)
+        print(case, len(t), "ticks,", int(t["mpc_ran"].sum()), "MPC solves")
+    np.savez_compressed(os.path.join(HERE, "ref_tick_cases.npz"), **more)
 
 
 if __name__ == "__main__":

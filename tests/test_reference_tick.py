@@ -61,48 +61,67 @@ def _state_record(o, pos, vel, quat, omega, cmd5, horizon=N):
     return st
 
 
-def reference_ticks(O):
+# further cases (fixture ref_tick_cases.npz): the zero-command branches of the reference trajectory
+# (ConvexMPCLocomotion.cpp:380-397 `== 0` tests) under the walking gait, and the standing gait
+CASES = {
+    "walk": dict(gait=2, n_ticks=N_TICKS, command=COMMAND, offsets=(0, 5), durations=(5, 5), pose=(0.3, 1.1, 2.0)),
+    "walk_zero_command": dict(gait=2, n_ticks=200, command=dict(v_des=(0.0, 0.0), yaw_rate=0.0, roll=0.0, pitch=0.0),
+                              offsets=(0, 5), durations=(5, 5), pose=(1.3, 0.2, 0.7)),
+    "stand": dict(gait=1, n_ticks=100, command=dict(v_des=(0.0, 0.0), yaw_rate=0.0, roll=0.0, pitch=0.0),
+                  offsets=(0, 0), durations=(10, 10), pose=(2.1, 0.9, 0.1)),
+}
+CASES_FIXTURE = os.path.join(GOLDEN, "ref_tick_cases.npz")
+
+
+def reference_ticks(O, case="walk"):
     """Tick the compiled reference controller through the pose sequence; yields its per-tick outputs."""
+    c = CASES[case]
     ctl = O.ReferenceController(DT, ITER_MPC)
-    for k in range(N_TICKS):
-        pos, rpy, vel, omega, raw = _pose(k, (0.3, 1.1, 2.0))
+    for k in range(c["n_ticks"]):
+        pos, rpy, vel, omega, raw = _pose(k, c["pose"])
         quat = scenarios.rpy_to_quat(rpy)
-        yield ctl.run(2, pos, vel, quat, omega, raw, v_des_body=COMMAND["v_des"], yaw_rate=COMMAND["yaw_rate"],
-                      roll=COMMAND["roll"], pitch=COMMAND["pitch"])
+        yield ctl.run(c["gait"], pos, vel, quat, omega, raw, v_des_body=c["command"]["v_des"], yaw_rate=c["command"]["yaw_rate"],
+                      roll=c["command"]["roll"], pitch=c["command"]["pitch"])
     ctl.close()
 
 
-def committed_ticks(O):
-    return iter(np.load(FIXTURE)["ticks"].view(O.REFTICK_DTYPE).reshape(-1))
+def committed_ticks(O, case="walk"):
+    if case == "walk":
+        return iter(np.load(FIXTURE)["ticks"].view(O.REFTICK_DTYPE).reshape(-1))
+    return iter(np.load(CASES_FIXTURE)[case].view(O.REFTICK_DTYPE).reshape(-1))
 
 
+@pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("source", ["live", "committed"])
-def test_walking_ticks_match_the_reference_controller(oracle, source):
+def test_walking_ticks_match_the_reference_controller(oracle, source, case):
     """live: libref_tick.so ticked here;  committed: the outputs it produced when the fixture was generated (runs on any
     machine, also without /root/reference)."""
     O = oracle
+    C = CASES[case]
     if source == "live":
         if not O.has_reference_tick():
             pytest.skip("oracle/_ref/libref_tick.so not built (needs /root/reference at build time)")
-        ticks = reference_ticks(O)
+        ticks = reference_ticks(O, case)
     else:
-        ticks = committed_ticks(O)
+        ticks = committed_ticks(O, case)
     H = _host()
     swing = scenarios.make_swing(1)
     loop = np.zeros(1, dtype=scenarios.ROLLOUT_DTYPE)
-    loop["gait_offset"], loop["gait_duration"] = (0, 5), (5, 5)
-    v_des, yaw_rate, roll, pitch = COMMAND["v_des"], COMMAND["yaw_rate"], COMMAND["roll"], COMMAND["pitch"]
+    loop["gait_offset"], loop["gait_duration"] = C["offsets"], C["durations"]
+    cmdd = C["command"]
+    v_des, yaw_rate, roll, pitch = cmdd["v_des"], cmdd["yaw_rate"], cmdd["roll"], cmdd["pitch"]
     cmd5 = np.array([roll, pitch, v_des[0], v_des[1], yaw_rate])
-    n_ticks, n_mpc, n_swing_checked, worst_ik = N_TICKS, 0, 0, 0.0
+    n_ticks, n_mpc, n_swing_checked, worst_ik = C["n_ticks"], 0, 0, 0.0
+    g_stance, g_swing = C["durations"][0], N - C["durations"][0]          # Gait::_stance / _swing (GaitGenerator.cpp:13-14)
     for k, o in enumerate(ticks):
-        pos, rpy, vel, omega, raw = _pose(k, (0.3, 1.1, 2.0))
+        pos, rpy, vel, omega, raw = _pose(k, C["pose"])
         quat = scenarios.rpy_to_quat(rpy)
         assert o["iteration_counter"] == k + 1
 
         # ---- f-3: gait ------------------------------------------------------------------------------------------
         it, ph = (k // ITER_MPC) % N, float(scenarios.gait_phase(k, ITER_MPC, N))
         assert o["gait_iteration"] == it and o["phase"] == ph
-        assert np.array_equal(o["mpc_table"], scenarios.mpc_gait(N, (0, 5), (5, 5), it).reshape(-1))
+        assert np.array_equal(o["mpc_table"], scenarios.mpc_gait(N, C["offsets"], C["durations"], it).reshape(-1))
 
         # ---- the state estimate the probe wrote == what the restatements derive from the quaternion ---------------
         assert np.array_equal(o["rBody"].reshape(3, 3), _rbody_from_quat(quat))
@@ -148,8 +167,8 @@ def test_walking_ticks_match_the_reference_controller(oracle, source):
         R = o["rBody"].reshape(3, 3).T
         vdw = R @ np.array([v_des[0], v_des[1], 0.0])
         for leg in range(2):
-            rel = np.clip(vel[:2] * 0.5 * 5 * DT_MPC + 0.02 * (vel[:2] - vdw[:2]), -0.4, 0.4).astype(np.float32)
-            want = pos + R @ scenarios.hip_yaw_location(leg) + vel * (DT_MPC * 5)
+            rel = np.clip(vel[:2] * 0.5 * g_stance * DT_MPC + 0.02 * (vel[:2] - vdw[:2]), -0.4, 0.4).astype(np.float32)
+            want = pos + R @ scenarios.hip_yaw_location(leg) + vel * (DT_MPC * g_swing)
             want[:2] += rel
             want[2] = -0.0
             assert np.abs(want - o["cmpc_pf"][3 * leg: 3 * leg + 3]).max() < 1e-7   # the reference clamps through floats (:152-153)
@@ -174,7 +193,9 @@ def test_walking_ticks_match_the_reference_controller(oracle, source):
                 worst_ik = max(worst_ik, d)
             else:
                 assert cmd["swing"][0][leg] == 0
-    assert n_mpc == n_ticks // 5 and n_swing_checked > 300
+    assert n_mpc == n_ticks // 5 and n_swing_checked > (300 if case == "walk" else (100 if g_swing else -1))
+    if not g_swing:
+        assert n_swing_checked == 0
     assert worst_ik < 1e-12, worst_ik
 
 
