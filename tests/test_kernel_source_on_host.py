@@ -365,3 +365,30 @@ def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
         r = subprocess.run([exe, str(f), str(g["horizon"])], capture_output=True, text=True, env=env, timeout=900)
         assert "ThreadSanitizer" not in r.stderr, (name, r.stderr[:3000])
         assert r.returncode == 0, (name, r.returncode, r.stdout, r.stderr[-500:])
+
+
+def test_solve_kernel_source_edge_cases(emul, oracle):
+    """The contact-schedule edge cases of the -m gpu suite on the kernel source: no foot in contact over the whole horizon
+    (everything eliminated), flight then double support, and arbitrary ragged schedules against the live oracle."""
+    from conftest import rel_err
+
+    N = 10
+    b = scenarios.stand_inputs(N)
+    b["gait"][:] = 0
+    b2 = scenarios.stand_inputs(N)
+    b2["gait"][:8] = 0
+    rng = np.random.default_rng(5)
+    recs = [scenarios.to_record(b, N), scenarios.to_record(b2, N)]
+    for _ in range(6):
+        table = (rng.random(2 * N) < 0.6).astype(np.int32)
+        recs.append(scenarios.to_record(scenarios._random_state(rng, N, table, moving=True), N))
+    recs = np.array(recs)
+    w, st, _, _, _ = _solve(emul, recs, N, tau=False)
+    assert (interface.status_code(st) == 0).all()
+    assert (w[0] == 0).all()
+    assert (w[1, :48] == 0).all() and np.abs(w[1, 48:]).max() > 1
+    if oracle.has_qpoases():
+        ref, info = oracle.solve_batch(recs, oracle.make_setup(N))
+        assert (info[:, 0] == 0).all()
+        assert rel_err(w[1:], ref[1:]).max() < 5e-5
+        assert (w[ref == 0.0] == 0.0).all()
