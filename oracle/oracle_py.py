@@ -263,8 +263,28 @@ REFTICK_DTYPE = np.dtype(
 )
 
 
+_TICK_DROPIN_LIB_PATH = os.path.join(_HERE, "_ref", "libref_tick_b200.so")
+_tick_dropin_lib = None
+
+
 def has_reference_tick() -> bool:
     return os.path.exists(_TICK_LIB_PATH)
+
+
+def has_reference_tick_dropin() -> bool:
+    """oracle/_ref/libref_tick_b200.so: the reference's controller objects linked against the product library."""
+    return os.path.exists(_TICK_DROPIN_LIB_PATH)
+
+
+def tick_dropin_lib() -> ctypes.CDLL:
+    global _tick_dropin_lib
+    if _tick_dropin_lib is None:
+        L = ctypes.CDLL(_TICK_DROPIN_LIB_PATH)
+        L.reftick_sizeof_out.restype = ctypes.c_size_t
+        L.reftick_create.restype = ctypes.c_void_p
+        assert L.reftick_sizeof_out() == REFTICK_DTYPE.itemsize
+        _tick_dropin_lib = L
+    return _tick_dropin_lib
 
 
 def tick_lib() -> ctypes.CDLL:
@@ -283,8 +303,10 @@ class ReferenceController:
     gait), ticked the way FSMState_Walking::run does.  State persists across ticks like the reference's objects;
     the MPC itself is process-global in the reference (one controller solving at a time)."""
 
-    def __init__(self, dt: float = 0.001, iterations_between_mpc: int = 40):
-        self._L = tick_lib()
+    def __init__(self, dt: float = 0.001, iterations_between_mpc: int = 40, drop_in: bool = False):
+        """drop_in=True: the same controller objects with libhector_mpc_b200.so behind setup_problem /
+        update_problem_data / get_solution (needs a GPU to run; `update_record` stays zero)."""
+        self._L = tick_dropin_lib() if drop_in else tick_lib()
         self._h = ctypes.c_void_p(self._L.reftick_create(ctypes.c_double(dt), ctypes.c_int(iterations_between_mpc)))
         assert self._h.value, "reftick_create failed"
 

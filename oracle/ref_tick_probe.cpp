@@ -8,6 +8,11 @@
  * UNCHANGED from /root/reference against oracle/eigen_shim (stand-ins for Eigen and, declaration-only, for the
  * LCM/boost headers the unitree SDK headers name) and the reference's qpOASES -> oracle/_ref/libref_tick.so.
  *
+ * Drop-in build (-DREFTICK_DROP_IN -> oracle/_ref/libref_tick_b200.so): the same controller objects, but the three MPC
+ * files and qpOASES are LEFT OUT and the link is completed by hector_simulation_b200/libhector_mpc_b200.so — the
+ * maintainer's change of INTEGRATION.md carried out on the reference's own objects.  Used by the -m gpu suite to tick the
+ * reference's controller with the GPU library behind its unchanged setup_problem/update_problem_data/get_solution calls.
+ *
  * A tick here is what FSMState_Walking::run does (src/FSM/FSMState_Walking.cpp:25-40):
  *   LegController::updateData -> [state estimate] -> DesiredStateCommand::setStateCommands ->
  *   ConvexMPCLocomotion::run (gait, swing-leg controller, updateMPCIfNeeded -> setup_problem/update_problem_data)
@@ -44,9 +49,12 @@
 #undef private
 #undef protected
 
-// file-scope objects of convexMPC_interface.cpp:12-17 (external linkage there)
+// file-scope objects of convexMPC_interface.cpp:12-17 (external linkage there).  Not available in the drop-in build
+// (REFTICK_DROP_IN: the controller objects linked against libhector_mpc_b200.so instead of the reference's MPC files).
+#ifndef REFTICK_DROP_IN
 extern update_data_t update;
 extern problem_setup problem_configuration;
+#endif
 
 namespace {
 struct QuietStdout {
@@ -227,7 +235,9 @@ void reftick_run(void* h, int gait_number, const double* position, const double*
     }
     for (int k = 0; k < 5; k++) out->q_des[5 * leg + k] = t.legs.commands[leg].qDes(k);
   }
+#ifndef REFTICK_DROP_IN
   memcpy(out->update_record, &update, sizeof(update_data_t));
+#endif
 
   t.legs.updateCommand(&t.lowCmd);
   for (int i = 0; i < 10; i++) out->tau[i] = t.lowCmd.motorCmd[i].tau;

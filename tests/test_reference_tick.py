@@ -215,6 +215,27 @@ def test_standing_tick_is_the_physically_sane_stand(ref):
     assert np.allclose(rec["r"], mine["r"], atol=1e-7) and np.allclose(rec["traj"][:120], mine["traj"][:120], atol=1e-6)
 
 
+def test_reference_controller_links_against_the_product_library(oracle):
+    """INTEGRATION.md's claim at link level: the reference's controller objects (ConvexMPCLocomotion.cpp & co., compiled
+    unchanged) link with --no-undefined against libhector_mpc_b200.so in place of convexMPC_interface.cpp + SolverMPC.cpp +
+    RobotState.cpp + qpOASES, importing exactly the boundary symbols of convexMPC_interface.h:39-43.  (Ticking it needs a
+    GPU: tests/test_zz_device_vs_reference_vectors.py.)"""
+    import shutil
+    import subprocess
+
+    if not oracle.has_reference_tick_dropin():
+        pytest.skip("oracle/_ref/libref_tick_b200.so not built (needs /root/reference at build time)")
+    L = oracle.tick_dropin_lib()           # loads libhector_mpc_b200.so through its RUNPATH
+    for sym in ("reftick_create", "reftick_run", "reftick_destroy"):
+        assert hasattr(L, sym)
+    if shutil.which("nm"):
+        und = subprocess.run(["nm", "-D", "--undefined-only", oracle._TICK_DROPIN_LIB_PATH], capture_output=True, text=True).stdout
+        boundary = {l.split()[-1] for l in und.splitlines() if l.split()[-1] in
+                    ("setup_problem", "update_problem_data", "get_solution", "update_solver_settings")}
+        assert boundary == {"setup_problem", "update_problem_data", "get_solution"}   # what ConvexMPCLocomotion.cpp calls
+        assert "solve_mpc" not in und and "qpOASES" not in und
+
+
 # ---- helpers -----------------------------------------------------------------------------------------------------
 def _dp(a):
     return np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))

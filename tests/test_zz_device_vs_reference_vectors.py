@@ -122,3 +122,40 @@ def test_device_solve_and_torques_follow_the_reference_controller():
     # the reference's torques pass through float motor commands; ours start from the float-narrowed record
     err = np.linalg.norm(got - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1.0)
     assert err.max() < 5e-4, err.max()
+
+
+def test_reference_controller_runs_on_the_gpu_library():
+    """The drop-in, end to end: the reference's OWN controller objects (ConvexMPCLocomotion, LegController, swing-leg
+    controller, gait — compiled unchanged) linked against libhector_mpc_b200.so instead of their MPC files, ticked through
+    the walking sequence, against what the same controller produced with the reference's own solve_mpc + qpOASES."""
+    from oracle import oracle_py as O   # loader of the test-side library only; no oracle arithmetic runs
+
+    if not O.has_reference_tick_dropin():
+        pytest.skip("oracle/_ref/libref_tick_b200.so not built (needs /root/reference at build time)")
+    from test_reference_tick import CASES
+
+    ticks = _ticks()
+    c = CASES["walk"]
+    ctl = O.ReferenceController(DT, ITER_MPC, drop_in=True)
+    worst = dict(wrench=0.0, f_ff=0.0, tau=0.0)
+    n_mpc = 0
+    for k in range(len(ticks)):
+        want = ticks[k]
+        pos, rpy, vel, omega, raw = _pose(k, c["pose"])
+        o = ctl.run(c["gait"], pos, vel, scenarios.rpy_to_quat(rpy), omega, raw, v_des_body=c["command"]["v_des"],
+                    yaw_rate=c["command"]["yaw_rate"], roll=c["command"]["roll"], pitch=c["command"]["pitch"])
+        # everything around the solver is the same machine code: identical
+        for f in ("leg_q", "leg_p", "J", "wpd", "phase", "mpc_table", "swing_states", "swing_times", "first_swing", "p0", "pf",
+                  "q_des", "cmpc_pf", "iteration_counter", "mpc_ran"):
+            assert np.array_equal(o[f], want[f]), (k, f)
+        if want["mpc_ran"]:
+            n_mpc += 1
+            scale = np.linalg.norm(want["q_soln"][:12])
+            worst["wrench"] = max(worst["wrench"], float(np.linalg.norm(o["q_soln"][:12] - want["q_soln"][:12]) / scale))
+            worst["f_ff"] = max(worst["f_ff"], float(np.linalg.norm(o["f_ff"] - want["f_ff"]) / np.linalg.norm(want["f_ff"])))
+        nt = max(np.linalg.norm(want["tau"]), 1.0)
+        worst["tau"] = max(worst["tau"], float(np.linalg.norm(o["tau"] - want["tau"]) / nt))
+    ctl.close()
+    print("reference controller on the GPU library vs on its own solver, worst relative gaps:", worst, "MPC ticks:", n_mpc)
+    assert n_mpc == len(ticks) // 5
+    assert worst["wrench"] < 1e-4 and worst["f_ff"] < 1e-4 and worst["tau"] < 1e-4
