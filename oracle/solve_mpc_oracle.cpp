@@ -30,7 +30,9 @@
  *      Eigen's coefficient-based products accumulate sequentially in k, its blocked GEBP kernel may
  *      group differently — a freedom the reference itself has, its Eigen version being unpinned),
  *      3x3 inverses by the cofactor formula Eigen uses.  The QP-solve half IS the reference (qpOASES
- *      built from its own sources).
+ *      built from its own sources).  Measured sensitivity to that freedom (mode bit 2, the two gemv's of
+ *      :570 grouped four columns at a time like Eigen 3.3's kernel): first-step wrench median 1e-6,
+ *      worst 3.7e-5 relative on 256 robots of configs[2] — inside the contract.
  *
  * TRIG RESOLUTION (found by compiling the reference, not visible from reading it): SolverMPC.cpp
  * includes <cmath> (:6) and then qpOASES.hpp (:8), whose Utils.ipp:36 includes <math.h>.  With
@@ -210,7 +212,8 @@ struct Formulation {
 };
 
 template <class T>
-static void formulate(const update_data_t* u, const problem_setup* setup, Formulation<T>& F, bool trig_as_compiled = false)
+static void formulate(const update_data_t* u, const problem_setup* setup, Formulation<T>& F, bool trig_as_compiled = false,
+                      bool gemv_by4 = false)
 {
   const int N = setup->horizon;
   const int nx = 13 * N, nu = 12 * N, nc = 16 * N;
@@ -409,18 +412,28 @@ static void formulate(const update_data_t* u, const problem_setup* setup, Formul
         F.H[(size_t)i * nu + j] = (T)2 * (acc + alpha);
       }
     // d = A_qp * x0 - X_d ; g = (2*B^T*S) * d
+    // gemv_by4 (sensitivity probe, see "what stays a restatement" in the header): the two matrix-vector products summed
+    // the way Eigen 3.3's column-major gemv kernel groups them — four columns at a time, pairwise inside the group,
+    // res += (a0 x0 + a1 x1) + (a2 x2 + a3 x3), leftover columns one by one — instead of one sequential sum.
+    auto gemv_row = [gemv_by4](int n, auto coef, auto vec) {
+      if (!gemv_by4) {
+        T acc = coef(0) * vec(0);
+        for (int k = 1; k < n; k++) acc = acc + coef(k) * vec(k);
+        return acc;
+      }
+      T res = (T)0;
+      int k = 0;
+      for (; k + 4 <= n; k += 4)
+        res = res + ((coef(k) * vec(k) + coef(k + 1) * vec(k + 1)) + (coef(k + 2) * vec(k + 2) + coef(k + 3) * vec(k + 3)));
+      for (; k < n; k++) res = res + coef(k) * vec(k);
+      return res;
+    };
     std::vector<T> d(nx);
-    for (int r = 0; r < nx; r++) {
-      T acc = F.A_qp[(size_t)r * 13] * F.x0[0];
-      for (int c = 1; c < 13; c++) acc = acc + F.A_qp[(size_t)r * 13 + c] * F.x0[c];
-      d[r] = acc - Xd[r];
-    }
+    for (int r = 0; r < nx; r++)
+      d[r] = gemv_row(13, [&](int c) { return F.A_qp[(size_t)r * 13 + c]; }, [&](int c) { return F.x0[c]; }) - Xd[r];
     F.g.assign(nu, (T)0);
-    for (int i = 0; i < nu; i++) {
-      T acc = (T1[(size_t)i * nx] * (T)2) * d[0];
-      for (int k = 1; k < nx; k++) acc = acc + (T1[(size_t)i * nx + k] * (T)2) * d[k];
-      F.g[i] = acc;
-    }
+    for (int i = 0; i < nu; i++)
+      F.g[i] = gemv_row(nx, [&](int k) { return T1[(size_t)i * nx + k] * (T)2; }, [&](int k) { return d[k]; });
   }
 }
 
@@ -506,10 +519,11 @@ static int solve_reduced(ReducedQP& Q, std::vector<double>& x, int* nwsr_out)
 }
 
 template <class T>
-static int solve_one(const update_data_t* u, const problem_setup* s, double* q_soln, int* info, bool trig_as_compiled = false)
+static int solve_one(const update_data_t* u, const problem_setup* s, double* q_soln, int* info, bool trig_as_compiled = false,
+                     bool gemv_by4 = false)
 {
   Formulation<T> F;
-  formulate<T>(u, s, F, trig_as_compiled);
+  formulate<T>(u, s, F, trig_as_compiled, gemv_by4);
   ReducedQP Q;
   eliminate(F, Q);
   std::vector<double> x;
@@ -544,16 +558,18 @@ size_t oracle_sizeof_update_data(void) { return sizeof(update_data_t); }
  *                             0 = the reference's arithmetic (fp32 formulation, fp64 solve);
  *   bit 1 (ORACLE_MODE_TRIG_AS_COMPILED)  trig calls resolve as in the reference's translation unit
  *                             (float overloads, see "trig resolution" above); 0 = canonical double trig.
+ *   bit 2 (ORACLE_MODE_GEMV_BY4)  sensitivity probe: the two matrix-vector products of :570 summed the way Eigen 3.3's
+ *                             column-major gemv kernel groups them (four columns at a time) instead of sequentially.
  * q_soln [n][12N]; info [n][4] = {return code, nWSR, reduced vars, reduced cons}. */
 int oracle_solve_batch(const update_data_t* u, int n, const problem_setup* s, int mode,
                        double* q_soln, int* info)
 {
   int bad = 0;
   const int nu = 12 * s->horizon;
-  const bool tac = (mode & 2) != 0;
+  const bool tac = (mode & 2) != 0, by4 = (mode & 4) != 0;
   for (int i = 0; i < n; i++) {
-    int rc = (mode & 1) ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac)
-                        : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac);
+    int rc = (mode & 1) ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac, by4)
+                        : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac, by4);
     if (rc) bad++;
   }
   return bad;

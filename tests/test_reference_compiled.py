@@ -87,6 +87,22 @@ def test_canonical_arithmetic_is_within_contract_of_compiled_reference(compiled)
     assert r1.max() < 1e-4 and rh.max() < 1e-4
 
 
+def test_sensitivity_to_the_summation_order_eigen_is_free_to_choose(oracle):
+    """The one piece that stays a restatement is the order in which Eigen sums its products.  Probe: the two matrix-vector
+    products of SolverMPC.cpp:570 grouped four columns at a time (Eigen 3.3's column-major gemv kernel) instead of
+    sequentially.  The optimum moves by ~1e-6 typically and stays inside the 1e-4 contract — the same scale as the
+    reference's sensitivity to its libm."""
+    if not oracle.has_qpoases():
+        pytest.skip("oracle built without qpOASES")
+    setup = oracle.make_setup(N)
+    recs, _ = scenarios.make_batch(3, 192, horizon=N, seed=123)
+    q_seq, _ = oracle.solve_batch(recs, setup)
+    q_by4, info = oracle.solve_batch(recs, setup, gemv_by4=True)
+    assert (info[:, 0] == 0).all()
+    r = rel_err(q_by4, q_seq, 12)
+    assert 0 < np.median(r) < 1e-5 and r.max() < 1e-4 and rel_err(q_by4, q_seq).max() < 1e-4
+
+
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
 def test_committed_vectors_of_compiled_reference(oracle, name):
     """Runs everywhere (no libref needed): the restatement against vectors the compiled reference produced."""
