@@ -15,6 +15,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built libraries (they are git-ignored): build them once, the way the driver's build() does.
+    On the GPU box the libraries travel with the snapshot, so nothing happens there."""
+    lib = os.path.join(ROOT, "hector_simulation_b200", "libhector_mpc_b200.so")
+    if os.path.exists(lib):
+        return
+    try:
+        import __graft_entry__
+
+        __graft_entry__.build()
+    except Exception as e:  # the tests that need the library then fail with their own, more specific message
+        print("conftest: __graft_entry__.build() failed: %r" % (e,))
+
+
 def load_golden(name):
     from hector_simulation_b200.scenarios import UPDATE_DTYPE
 
