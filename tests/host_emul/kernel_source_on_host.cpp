@@ -161,27 +161,48 @@ void emul_stage1(const float* rf, float dt, float* Fblk, float* x0, float* Acd, 
   memcpy(x0, x0f, 13 * sizeof(float));
 }
 
-/* The device-resident solve path of hmpc_capi.cu (enqueue_solve): classification kernel, then one launch per size class
- * with escalation lists; B <= 1024 packed records.  Outputs: wrench [B][12N] floats, status [B], tau [B][10] or NULL,
- * launched[3] = instances each class processed (NULL to skip).  Optional assembly dump (all NULL, or all given):
- * H [B][n*n], g [B][n], Fblk [B][192], lb/ub [B][16N]. */
-int emul_solve(const unsigned char* records, int B, int N, float dt, float f_max, int max_iter, float* wrench, int* status,
-               float* tau, int* launched, float* dH, float* dg, float* dF, float* dlb, float* dub)
+/* The solve paths of hmpc_capi.cu on B <= 1024 robots.
+ *   records != NULL: the device-resident path (enqueue_solve): classification kernel, then one launch per size class with
+ *                    escalation lists, reading packed records.
+ *   raw != NULL    : the in-place host-buffer path (enqueue_solve_hostlists): class lists built on the host from the contact
+ *                    tables, kernels gather the live bytes of the caller's update_data_t records (3016-byte stride), no
+ *                    escalation (the caller retries overflow through the first path).
+ * Outputs: wrench [B][12N] floats and/or wrench64 [B][12N] doubles, status [B], tau [B][10] or NULL, launched[3] =
+ * instances each class processed (NULL to skip).  warm_start: KernelArgs::warm_start.  Optional assembly dump (all NULL,
+ * or all given): H [B][n*n], g [B][n], Fblk [B][192], lb/ub [B][16N]. */
+int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B, int N, float dt, float f_max, int max_iter,
+                  int warm_start, float* wrench, double* wrench64, int* status, float* tau, int* launched, float* dH, float* dg,
+                  float* dF, float* dlb, float* dub)
 {
-  if (B < 1 || B > 1024) return 1;
+  if (B < 1 || B > 1024 || (!records && !raw)) return 1;
   ClassCfg cls[3];
-  const int ncls = build_classes(N, cls);
+  int ncls = build_classes(N, cls);
   std::vector<int> block(4 + 3 * (size_t)B, 0);
   int* counts = block.data();
   int* lists = counts + 4;
   const int rs = hmpc::record_stride(N);
   const int nb_hi0 = cls[0].nb_cap;
-  run_cta((B + 31) / 32 * 32, [=] { hmpc::hmpc_classify1_kernel(records, rs, B, N, f_max, nb_hi0, counts, lists, B); });
+  if (raw) {
+    // hmpc_capi.cu classify_host: gait bytes at offsetof(update_data_t, gait) = 1944
+    for (int i = 0; i < B; i++) {
+      int k = 0;
+      for (int e = 0; e < 2 * N; e++) {
+        const float ub = f_max * (float)raw[(size_t)i * 3016 + 1944 + e];
+        k += !(ub < 0.0001f && ub > -0.0001f);
+      }
+      const int cl = (k <= nb_hi0) ? 0 : 1;
+      lists[(size_t)cl * B + counts[cl]++] = i;
+    }
+    ncls = 2;
+  } else {
+    run_cta((B + 31) / 32 * 32, [=] { hmpc::hmpc_classify1_kernel(records, rs, B, N, f_max, nb_hi0, counts, lists, B); });
+  }
   for (int i = 0; i < ncls; i++) {
     if (launched) launched[i] = counts[i];
     if (counts[i] == 0) continue;
     hmpc::KernelArgs ka{};
     ka.records = records;
+    ka.raw_records = raw;
     ka.rec_stride = rs;
     ka.batch = B;
     ka.horizon = N;
@@ -189,13 +210,14 @@ int emul_solve(const unsigned char* records, int B, int N, float dt, float f_max
     ka.f_max = f_max;
     ka.max_iter = max_iter;
     ka.wrench = wrench;
+    ka.wrench64 = wrench64;
     ka.status = status;
     ka.tau = tau;
-    ka.warm_start = 0;
+    ka.warm_start = warm_start;
     ka.list = lists + (size_t)i * B;
     ka.counts = counts;
     ka.cls = i;
-    ka.esc_list = (i + 1 < ncls) ? lists + (size_t)(i + 1) * B : nullptr;
+    ka.esc_list = (!raw && i + 1 < ncls) ? lists + (size_t)(i + 1) * B : nullptr;
     ka.nb_cap = cls[i].nb_cap;
     ka.qmax = cls[i].qmax;
     ka.L = cls[i].L;
@@ -203,6 +225,12 @@ int emul_solve(const unsigned char* records, int B, int N, float dt, float f_max
     launch_variant(cls[i].variant, ka);
   }
   return 0;
+}
+
+int emul_solve(const unsigned char* records, int B, int N, float dt, float f_max, int max_iter, float* wrench, int* status,
+               float* tau, int* launched, float* dH, float* dg, float* dF, float* dlb, float* dub)
+{
+  return emul_solve_ex(records, nullptr, B, N, dt, f_max, max_iter, 0, wrench, nullptr, status, tau, launched, dH, dg, dF, dlb, dub);
 }
 
 /* the torque epilogue's per-joint function: tau_j = column j of J_force_moment(q5, leg) . f6 */

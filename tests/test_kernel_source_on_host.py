@@ -356,15 +356,21 @@ def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("no ThreadSanitizer runtime with this toolchain: " + r.stderr[-300:])
-    cases = [("cfg2_h10", [0, 1, 2]), ("cfg1_h10", [0]), ("degenerate_zero_force_h10", [0]), ("cfg4_h5", [0, 1, 2, 3])]
+    cases = [("cfg2_h10", [0, 1, 2], ()), ("cfg1_h10", [0], ()), ("degenerate_zero_force_h10", [0], ()),
+             ("cfg4_h5", [0, 1, 2, 3], ()),
+             ("cfg3_h10", [0, 1], ("raw",)),          # in-place gather of update_data_t records, double results
+             ("cfg2_h10", [3, 4], ("warm",))]         # S-pair warm start
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66")
-    for name, idx in cases:
+    for name, idx, flags in cases:
         g = load_golden(name)
-        f = tmp_path / (name + ".bin")
-        np.ascontiguousarray(interface.pack_records(g["records"][idx], g["horizon"])).tofile(f)
-        r = subprocess.run([exe, str(f), str(g["horizon"])], capture_output=True, text=True, env=env, timeout=900)
-        assert "ThreadSanitizer" not in r.stderr, (name, r.stderr[:3000])
-        assert r.returncode == 0, (name, r.returncode, r.stdout, r.stderr[-500:])
+        f = tmp_path / (name + "".join(flags) + ".bin")
+        if "raw" in flags:
+            np.ascontiguousarray(g["records"][idx]).tofile(f)
+        else:
+            np.ascontiguousarray(interface.pack_records(g["records"][idx], g["horizon"])).tofile(f)
+        r = subprocess.run([exe, str(f), str(g["horizon"]), *flags], capture_output=True, text=True, env=env, timeout=900)
+        assert "ThreadSanitizer" not in r.stderr, (name, flags, r.stderr[:3000])
+        assert r.returncode == 0, (name, flags, r.returncode, r.stdout, r.stderr[-500:])
 
 
 def test_solve_kernel_source_edge_cases(emul, oracle):
@@ -392,3 +398,30 @@ def test_solve_kernel_source_edge_cases(emul, oracle):
         assert (info[:, 0] == 0).all()
         assert rel_err(w[1:], ref[1:]).max() < 5e-5
         assert (w[ref == 0.0] == 0.0).all()
+
+
+def test_solve_kernel_source_in_place_and_warm_start_modes(emul):
+    """The other modes of the same kernel: gathering the live bytes of the caller's update_data_t records in place (the
+    host-buffer path's in-place mode), double-precision result stores, and the optional S-pair warm start."""
+    from conftest import load_golden, rel_err
+
+    g = load_golden("cfg3_h10")
+    N, B = 10, 6
+    recs = np.ascontiguousarray(g["records"][:B])
+    w0, st0, tau0, _, _ = _solve(emul, recs, N)
+    w = np.zeros((B, 12 * N), np.float32)
+    w64 = np.zeros((B, 12 * N), np.float64)
+    st = np.full(B, -1, np.int32)
+    tau = np.zeros((B, 10), np.float32)
+    rc = emul.emul_solve_ex(None, _p(recs), B, N, ctypes.c_float(0.04), ctypes.c_float(500.0), 500, 0, _p(w), _p(w64), _p(st), _p(tau),
+                            None, None, None, None, None, None)
+    assert rc == 0
+    assert np.array_equal(w.astype(np.float64), w0) and np.array_equal(st, st0) and np.array_equal(tau.astype(np.float64), tau0)
+    assert np.array_equal(w64, w0)                     # the double store is the float-rounded solution, widened
+    packed = np.ascontiguousarray(interface.pack_records(recs, N))
+    ww = np.zeros((B, 12 * N), np.float32)
+    sw = np.full(B, -1, np.int32)
+    rc = emul.emul_solve_ex(_p(packed), None, B, N, ctypes.c_float(0.04), ctypes.c_float(500.0), 500, 1, _p(ww), None, _p(sw), None,
+                            None, None, None, None, None, None)
+    assert rc == 0 and (interface.status_code(sw) == 0).all()
+    assert rel_err(ww.astype(np.float64), g["q_soln"][:B]).max() < 5e-5
