@@ -130,6 +130,8 @@ def test_walking_ticks_match_the_reference_controller(oracle, source, case):
         for leg in range(2):
             J = O.leg_jacobian_fm(o["leg_q"][5 * leg: 5 * leg + 5], leg)
             assert np.abs(J - o["J"][30 * leg: 30 * leg + 30].reshape(6, 5)).max() < 1e-15
+            # the forward kinematics the scenario generator uses (LegController.cpp:190-194) on the same angles
+            assert np.abs(scenarios.leg_fk(o["leg_q"][5 * leg: 5 * leg + 5], leg) - o["leg_p"][3 * leg: 3 * leg + 3]).max() < 1e-14
 
         # ---- f-1 / a16: on the ticks the reference solves ------------------------------------------------------------
         assert o["mpc_ran"] == (k % 5 == 0)
