@@ -253,9 +253,9 @@ def test_solve_kernel_source_assembly_is_bit_exact(emul):
     holds the GPU to, here for the source executed on the host."""
     from conftest import load_golden
 
-    for name in ("cfg2_h10", "cfg3_h10", "cfg4_h5"):
+    for name in ("cfg2_h10", "cfg3_h10", "cfg4_h5", "cfg4_h16"):
         g = load_golden(name)
-        N, nf = g["horizon"], g["H"].shape[0]
+        N, nf = g["horizon"], min(g["H"].shape[0], 2 if name == "cfg4_h16" else 4)
         _, _, _, _, d = _solve(emul, g["records"][:nf], N, dump=True)
         iu = np.triu_indices(12 * N)
         for i in range(nf):
@@ -300,17 +300,20 @@ def test_solve_kernel_source_double_support_class(emul):
     assert abs(w[0, 2] - 47.84) < 0.05 and abs(w[0, 5] - 47.84) < 0.05
 
 
-def test_solve_kernel_source_runtime_horizon(emul):
-    """The runtime-layout instantiations (horizon 5): mixed contact schedules, both classes."""
+@pytest.mark.parametrize("name,B", [("cfg4_h5", 8), ("cfg4_h16", 3)])
+def test_solve_kernel_source_runtime_horizon(emul, name, B):
+    """The runtime-layout instantiations: horizon 5 (64 / 224 threads) and the horizon-16 extension (224 / 544 threads),
+    mixed contact schedules, both classes."""
     from conftest import load_golden, rel_err
 
-    g = load_golden("cfg4_h5")
-    B = 8
-    w, st, _, launched, _ = _solve(emul, g["records"][:B], 5, tau=False)
-    assert launched[:2].sum() == B and launched[2] == 0
+    g = load_golden(name)
+    N = g["horizon"]
+    w, st, _, launched, _ = _solve(emul, g["records"][:B], N, tau=False)
+    assert launched[:2].sum() == B and launched[2] == 0 and (launched[:2] > 0).all()
     assert (interface.status_code(st) == 0).all()
     assert rel_err(w, g["q_soln"][:B], 12).max() < 5e-6 and rel_err(w, g["q_soln"][:B]).max() < 5e-5
     assert (w[g["q_soln"][:B] == 0.0] == 0.0).all()
+    assert np.array_equal(interface.status_iters(st), g["info"][:B, 1])
 
 
 def test_solve_kernel_source_escalates_a_degenerate_optimum(emul):
