@@ -428,3 +428,47 @@ def test_solve_kernel_source_in_place_and_warm_start_modes(emul):
                             None, None, None, None, None, None)
     assert rc == 0 and (interface.status_code(sw) == 0).all()
     assert rel_err(ww.astype(np.float64), g["q_soln"][:B]).max() < 5e-5
+
+
+def test_closed_loop_of_kernel_sources(emul, oracle):
+    """hmpc_rollout_device's tick — data-preparation kernel -> classification + solve kernels -> advance kernel — with all
+    three kernels' sources chained on the host, against the same loop driven from the host (host mirror of the preparation,
+    the same solve, numpy mirror of the advance step: the comparison tests/test_rollout.py makes on the GPU), with qpOASES
+    checking every tick's wrench."""
+    if not oracle.has_qpoases():
+        pytest.skip("oracle/_ref without qpOASES")
+    from conftest import rel_err
+    from test_rollout import _host_prepared, _walkers
+
+    N, B, T = 10, 3, 8
+    states, loop = _walkers(B)
+    s_k, l_k = states.copy(), loop.copy()
+    setup = oracle.make_setup(N)
+    stride = interface.record_bytes(N)
+
+    def solve(packed):
+        w = np.zeros((B, 12 * N), np.float32)
+        st = np.full(B, -1, np.int32)
+        assert emul.emul_solve(_p(packed), B, N, ctypes.c_float(0.04), ctypes.c_float(500.0), 500, _p(w), _p(st), None, None,
+                               None, None, None, None, None) == 0
+        assert (interface.status_code(st) == 0).all()
+        return w, st
+
+    for t in range(T):
+        # host-driven loop
+        recs = _host_prepared(states, N)
+        w_h, st_h = solve(np.ascontiguousarray(interface.pack_records(recs, N)))
+        q, info = oracle.solve_batch(recs, setup)
+        assert (info[:, 0] == 0).all() and rel_err(w_h.astype(np.float64), q, 12).max() < 5e-5
+        scenarios.advance_numpy(states, loop, w_h, st_h, N)
+        # the kernels' loop
+        packed = np.zeros((B, stride), np.uint8)
+        emul.emul_prepare(_p(s_k), B, N, ctypes.c_double(0.04), _p(packed))
+        w_k, st_k = solve(packed)
+        emul.emul_advance(_p(s_k), _p(l_k), B, N, ctypes.c_double(0.04), _p(w_k), _p(st_k))
+        for f in ("position", "vWorld", "orientation", "omegaWorld", "rpy", "leg_p", "world_position_desired"):
+            assert np.abs(s_k[f] - states[f]).max() < 1e-9, (t, f, np.abs(s_k[f] - states[f]).max())
+        assert np.array_equal(s_k["gait"], states["gait"])
+        assert np.abs(l_k["feet_world"] - loop["feet_world"]).max() < 1e-9
+    assert (l_k["failures"] == 0).all() and np.array_equal(l_k["ticks"], np.full(B, T))
+    assert np.array_equal(l_k["iters_total"], loop["iters_total"])
