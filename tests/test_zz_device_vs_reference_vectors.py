@@ -7,12 +7,10 @@ of the host restatements against the same vectors).  Nothing here needs oracle/_
   f-4  hmpc_swing_device     == the reference's swing-leg controller, tick by tick (two calls per tick, as run() makes them)
   f-2  hmpc_solve_batch_ex   == the reference's first-step wrench (1e-4 contract) and the joint torques it commanded
 """
-import os
-
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, rel_err
+from conftest import rel_err
 from hector_simulation_b200 import interface, scenarios
 from test_reference_tick import COMMAND, DT, DT_MPC, FIXTURE, ITER_MPC, N, _pose, _state_record
 

@@ -10,7 +10,7 @@ import sys, ctypes, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
-from hector_simulation_b200 import interface, scenarios
+from hector_simulation_b200 import interface
 import test_kernel_source_on_host as KS
 
 L = ctypes.CDLL(os.path.join(KS.BUILD, "libkernel_source_on_host.so"))
