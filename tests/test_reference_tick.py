@@ -67,6 +67,10 @@ CASES = {
     "walk": dict(gait=2, n_ticks=N_TICKS, command=COMMAND, offsets=(0, 5), durations=(5, 5), pose=(0.3, 1.1, 2.0)),
     "walk_zero_command": dict(gait=2, n_ticks=200, command=dict(v_des=(0.0, 0.0), yaw_rate=0.0, roll=0.0, pitch=0.0),
                               offsets=(0, 5), durations=(5, 5), pose=(1.3, 0.2, 0.7)),
+    # a command far from the motion: the set-point clamp (+-0.05 m, :338-346) engages within 100 ticks and the swing-leg
+    # placement saturates at its FLOAT +-0.3 (fminf/fmaxf on doubles, SwingLegController.cpp:117-118)
+    "walk_saturated": dict(gait=2, n_ticks=240, command=dict(v_des=(3.5, -3.2), yaw_rate=0.5, roll=0.0, pitch=0.03),
+                           offsets=(0, 5), durations=(5, 5), pose=(0.9, 2.4, 1.6)),
     "stand": dict(gait=1, n_ticks=100, command=dict(v_des=(0.0, 0.0), yaw_rate=0.0, roll=0.0, pitch=0.0),
                   offsets=(0, 0), durations=(10, 10), pose=(2.1, 0.9, 0.1)),
 }
@@ -112,6 +116,7 @@ def test_walking_ticks_match_the_reference_controller(oracle, source, case):
     v_des, yaw_rate, roll, pitch = cmdd["v_des"], cmdd["yaw_rate"], cmdd["roll"], cmdd["pitch"]
     cmd5 = np.array([roll, pitch, v_des[0], v_des[1], yaw_rate])
     n_ticks, n_mpc, n_swing_checked, worst_ik = C["n_ticks"], 0, 0, 0.0
+    n_clamped_setpoint = n_saturated_placement = 0
     g_stance, g_swing = C["durations"][0], N - C["durations"][0]          # Gait::_stance / _swing (GaitGenerator.cpp:13-14)
     for k, o in enumerate(ticks):
         pos, rpy, vel, omega, raw = _pose(k, C["pose"])
@@ -152,6 +157,7 @@ def test_walking_ticks_match_the_reference_controller(oracle, source, case):
                 if pos[a] - w[a] > 0.05:
                     w[a] = pos[a] - 0.05
             assert np.array_equal(w[:2], o["wpd"][:2])
+            n_clamped_setpoint += int(not np.array_equal(w[:2], o["wpd_entry"][:2]))
             # f_ff = -rBody [F; M]
             ff = (ctypes.c_double * 12)()
             H.hmpc_wrench_to_feedforward(_dp(o["rBody"]), _dp(o["q_soln"][:12].copy()), ff)
@@ -183,6 +189,8 @@ def test_walking_ticks_match_the_reference_controller(oracle, source, case):
         assert np.array_equal(swing["swing_time"][0], o["swing_times"]), k
         assert np.array_equal(swing["first_swing"][0], o["first_swing"]), k
         assert np.array_equal(cmd["pf"][0], o["pf"]), k
+        hipw = pos + o["rBody"].reshape(3, 3).T @ scenarios.hip_yaw_location(0) + vel * o["swing_times"][0]
+        n_saturated_placement += int(abs(abs(o["pf"][0] - hipw[0]) - np.float32(0.3)) < 1e-12)
         for leg in range(2):
             sl = slice(3 * leg, 3 * leg + 3)
             if o["swing_states"][leg] > 0:
@@ -196,6 +204,8 @@ def test_walking_ticks_match_the_reference_controller(oracle, source, case):
             else:
                 assert cmd["swing"][0][leg] == 0
     assert n_mpc == n_ticks // 5 and n_swing_checked > (300 if case == "walk" else (100 if g_swing else -1))
+    if case == "walk_saturated":
+        assert n_clamped_setpoint > 20 and n_saturated_placement > 50
     if not g_swing:
         assert n_swing_checked == 0
     assert worst_ik < 1e-12, worst_ik
