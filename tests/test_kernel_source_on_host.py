@@ -127,33 +127,43 @@ def test_prepare_kernel_source_equals_host_mirror(emul, horizon, cfg, batch):
     assert np.array_equal(got, want)
 
 
-def test_prepare_kernel_source_reproduces_the_reference_controllers_records(emul, oracle):
-    from test_reference_tick import DT_MPC, FIXTURE, N, _pose, _state_record
+def _case_ticks(oracle, case):
+    from test_reference_tick import CASES, committed_ticks
 
-    ticks = np.load(FIXTURE)["ticks"].view(oracle.REFTICK_DTYPE).reshape(-1)
-    which = np.nonzero(ticks["mpc_ran"])[0]
-    cmd5 = np.array([0.01, -0.02, 0.3, 0.05, 0.2])
+    C = CASES[case]
+    c = C["command"]
+    cmd5 = np.array([c["roll"], c["pitch"], c["v_des"][0], c["v_des"][1], c["yaw_rate"]])
+    return C, cmd5, list(committed_ticks(oracle, case))
+
+
+@pytest.mark.parametrize("case", ["walk", "walk_zero_command", "walk_saturated", "stand"])
+def test_prepare_kernel_source_reproduces_the_reference_controllers_records(emul, oracle, case):
+    """Including the zero-command branches of the reference trajectory, the engaged set-point clamp and the standing gait."""
+    from test_reference_tick import DT_MPC, N, _pose, _state_record
+
+    C, cmd5, ticks = _case_ticks(oracle, case)
+    which = [k for k, o in enumerate(ticks) if o["mpc_ran"]]
     states = np.zeros(len(which), dtype=scenarios.STATE_DTYPE)
     for n, k in enumerate(which):
-        pos, rpy, vel, omega, _ = _pose(int(k), (0.3, 1.1, 2.0))
+        pos, rpy, vel, omega, _ = _pose(int(k), C["pose"])
         states[n] = _state_record(ticks[k], pos, vel, scenarios.rpy_to_quat(rpy), omega, cmd5)
     ref = np.array([np.frombuffer(ticks[k]["update_record"].tobytes(), dtype=scenarios.UPDATE_DTYPE)[0] for k in which])
     assert np.array_equal(_prepare(emul, states, N, DT_MPC), interface.pack_records(ref, N))
 
 
 # ---- f-4 ------------------------------------------------------------------------------------------------------------
-def test_swing_kernel_source_follows_the_reference_controller(emul, oracle):
-    from test_reference_tick import DT, DT_MPC, FIXTURE, N, _pose, _state_record
+@pytest.mark.parametrize("case", ["walk", "walk_saturated", "stand"])
+def test_swing_kernel_source_follows_the_reference_controller(emul, oracle, case):
+    from test_reference_tick import DT, DT_MPC, N, _pose, _state_record
 
-    ticks = np.load(FIXTURE)["ticks"].view(oracle.REFTICK_DTYPE).reshape(-1)
-    cmd5 = np.array([0.01, -0.02, 0.3, 0.05, 0.2])
+    C, cmd5, ticks = _case_ticks(oracle, case)
     loop = np.zeros(1, dtype=scenarios.ROLLOUT_DTYPE)
-    loop["gait_offset"], loop["gait_duration"] = (0, 5), (5, 5)
+    loop["gait_offset"], loop["gait_duration"] = C["offsets"], C["durations"]
     sw = scenarios.make_swing(1)
     cmd = np.zeros(1, dtype=scenarios.SWING_CMD_DTYPE)
     checked, worst_q = 0, 0.0
     for k, o in enumerate(ticks):
-        pos, rpy, vel, omega, _ = _pose(k, (0.3, 1.1, 2.0))
+        pos, rpy, vel, omega, _ = _pose(k, C["pose"])
         st = np.array([_state_record(o, pos, vel, scenarios.rpy_to_quat(rpy), omega, cmd5)])
         ph = np.array([o["phase"]])
         for _ in range(2):
@@ -170,7 +180,7 @@ def test_swing_kernel_source_follows_the_reference_controller(emul, oracle):
                 worst_q = max(worst_q, float(np.abs(cmd["q_des"][0][s5] - o["q_des"][s5]).max()))
             else:
                 assert cmd["swing"][0][leg] == 0 and not cmd["q_des"][0][s5].any()
-    assert checked > 300 and worst_q < 1e-12
+    assert checked > (300 if case == "walk" else (100 if case == "walk_saturated" else -1)) and worst_q < 1e-12
 
 
 # ---- f-3 ------------------------------------------------------------------------------------------------------------
