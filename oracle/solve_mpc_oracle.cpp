@@ -41,7 +41,7 @@
  * foot-rotation literals (:428-433) resolve to libm's FLOAT functions, and products of two such
  * values are rounded to float (terms led by the literal `1.0*` stay double); atan2(float, double)
  * (:339,:341) and fmod(float, double) (:392) promote to double.  glibc's sinf/cosf/asinf differ from
- * the correctly rounded value in 1.3 % / 1.3 % / 7 % of arguments and have CPU-dispatched variants,
+ * the correctly rounded value in 1.3 % / 1.3 % / 7 % of arguments and (sinf, cosf) come in CPU-dispatched FMA variants,
  * so those last bits are not reproducible across machines — let alone on a GPU.  Hence two modes:
  *   mode 0, CANONICAL (default; what the CUDA kernel reproduces bit for bit and what the golden
  *           cfg*.npz fixtures hold): every trig call in double, narrowed to float — the correctly
