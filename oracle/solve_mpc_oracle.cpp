@@ -78,17 +78,23 @@ const double kBigNumber = 5e10;  // SolverMPC.cpp:16
 
 // ---- tiny dense helpers, sequential accumulation, no FMA (file is built -ffp-contract=off) ----
 
-// C(rxc) = A(rxk) * B(kxc), row-major, sum over the inner index in increasing order starting
-// from the first product (Eigen: res = a0*b0; res += a1*b1; ...).
+// C(rxc) = A(rxk) * B(kxc), row-major.  Every coefficient is the sum over the inner index in increasing order
+// starting from the first product (Eigen: res = a0*b0; res += a1*b1; ...).  The loops run row of C by row of B so that
+// the compiler can keep a whole row of accumulators in SSE registers — the order of additions per coefficient, hence
+// every bit of the result, is that of the textbook triple loop.
 template <class T>
 void matmul(const T* A, const T* B, T* C, int r, int k, int c)
 {
-  for (int i = 0; i < r; i++)
-    for (int j = 0; j < c; j++) {
-      T acc = A[i * k + 0] * B[0 * c + j];
-      for (int t = 1; t < k; t++) acc = acc + A[i * k + t] * B[t * c + j];
-      C[i * c + j] = acc;
+  for (int i = 0; i < r; i++) {
+    T* Ci = C + (size_t)i * c;
+    const T a0 = A[(size_t)i * k];
+    for (int j = 0; j < c; j++) Ci[j] = a0 * B[j];
+    for (int t = 1; t < k; t++) {
+      const T at = A[(size_t)i * k + t];
+      const T* Bt = B + (size_t)t * c;
+      for (int j = 0; j < c; j++) Ci[j] = Ci[j] + at * Bt[j];
     }
+  }
 }
 
 // Eigen's 3x3 inverse (Eigen/src/LU/InverseImpl.h, compute_inverse<...,3>): cofactors, det from
@@ -316,19 +322,29 @@ static void formulate(const update_data_t* u, const problem_setup* setup, Formul
     for (int i = 0; i < 156; i++) F.Bcd[i] = dt * F.B_ct[i];
     F.A_qp.assign((size_t)nx * 13, (T)0);
     F.B_qp.assign((size_t)nx * nu, (T)0);
-    // powers P_k = (((I*Acd)*Acd)*...)  (Acdm *= Acd, k times).  I*Acd == Acd exactly.
-    std::vector<T> P((size_t)(N + 1) * 169);
-    for (int i = 0; i < 169; i++) P[i] = (i / 13 == i % 13) ? (T)1 : (T)0;
-    for (int k = 1; k <= N; k++) matmul(&P[(size_t)(k - 1) * 169], F.Acd, &P[(size_t)k * 169], 13, 13, 13);
-    for (int i = 0; i < N; i++) memcpy(&F.A_qp[(size_t)i * 169], &P[(size_t)(i + 1) * 169], 169 * sizeof(T));
-    // B_qp(i,j) = P_{i-j} * Bcd for j <= i.  (P_0 * Bcd == Bcd exactly: 1*x + 0*y sums are exact.)
-    std::vector<T> M((size_t)N * 156);
-    for (int d = 0; d < N; d++) matmul(&P[(size_t)d * 169], F.Bcd, &M[(size_t)d * 156], 13, 13, 12);
+    // The reference re-powers from the identity for every block (SolverMPC.cpp:148-177: `Acdm *= Acd` i+1 times per
+    // A_qp block, i-j times per B_qp block — 220 13x13 products at N = 10); so does this restatement, so that the CPU
+    // baseline timed from it does the reference's floating-point work, not less.  P_k = (((I*Acd)*Acd)*...).
+    T Ident[169], Pa[169], Pb[169];
+    for (int i = 0; i < 169; i++) Ident[i] = (i / 13 == i % 13) ? (T)1 : (T)0;
+    auto power = [&](int k, T* out) {  // out = I * Acd^k by k successive right-multiplications
+      memcpy(out, Ident, sizeof(Ident));
+      for (int t = 0; t < k; t++) {
+        matmul(out, F.Acd, Pb, 13, 13, 13);
+        memcpy(out, Pb, sizeof(Pb));
+      }
+    };
+    for (int i = 0; i < N; i++) {
+      power(i + 1, Pa);
+      memcpy(&F.A_qp[(size_t)i * 169], Pa, 169 * sizeof(T));
+    }
+    T blk[156];
     for (int i = 0; i < N; i++)
-      for (int j = 0; j <= i; j++)
-        for (int r = 0; r < 13; r++)
-          for (int c = 0; c < 12; c++)
-            F.B_qp[(size_t)(13 * i + r) * nu + 12 * j + c] = M[(size_t)(i - j) * 156 + r * 12 + c];
+      for (int j = 0; j <= i; j++) {
+        power(i - j, Pa);
+        matmul(Pa, F.Bcd, blk, 13, 13, 12);
+        for (int r = 0; r < 13; r++) memcpy(&F.B_qp[(size_t)(13 * i + r) * nu + 12 * j], &blk[r * 12], 12 * sizeof(T));
+      }
   }
 
   // ---- SolverMPC.cpp:466-482 bounds -------------------------------------------------------------
@@ -399,17 +415,22 @@ static void formulate(const update_data_t* u, const problem_setup* setup, Formul
       }
       wdiag[13 * i + 12] = (T)0;
     }
-    // T1 = B^T * S  (S diagonal stored dense: every other product is an exact zero)
-    std::vector<T> T1((size_t)nu * nx);
-    for (int i = 0; i < nu; i++)
-      for (int k = 0; k < nx; k++) T1[(size_t)i * nx + k] = F.B_qp[(size_t)k * nu + i] * wdiag[k];
+    // qH = 2 * ((B^T * S) * B + Alpha_rep) with S and Alpha_rep DENSE like the reference's (SolverMPC.cpp:31,45,454,566):
+    // the products with their zeros are carried out (exact, so the bits equal a diagonal scaling), because this function
+    // is also what the CPU baseline times.
+    std::vector<T> Bt((size_t)nu * nx), Sd((size_t)nx * nx, (T)0), T1((size_t)nu * nx);
+    for (int k = 0; k < nx; k++) {
+      Sd[(size_t)k * nx + k] = wdiag[k];
+      for (int i = 0; i < nu; i++) Bt[(size_t)i * nx + k] = F.B_qp[(size_t)k * nu + i];
+    }
+    matmul(Bt.data(), Sd.data(), T1.data(), nu, nx, nx);
+    std::vector<T> BSB((size_t)nu * nu);
+    matmul(T1.data(), F.B_qp.data(), BSB.data(), nu, nx, nu);
     F.H.assign((size_t)nu * nu, (T)0);
     for (int i = 0; i < nu; i++)
       for (int j = 0; j < nu; j++) {
-        T acc = T1[(size_t)i * nx] * F.B_qp[j];
-        for (int k = 1; k < nx; k++) acc = acc + T1[(size_t)i * nx + k] * F.B_qp[(size_t)k * nu + j];
-        T alpha = (i == j) ? (T)u->Alpha_K[i % 12] : (T)0;
-        F.H[(size_t)i * nu + j] = (T)2 * (acc + alpha);
+        const T alpha = (i == j) ? (T)u->Alpha_K[i % 12] : (T)0;
+        F.H[(size_t)i * nu + j] = (T)2 * (BSB[(size_t)i * nu + j] + alpha);
       }
     // d = A_qp * x0 - X_d ; g = (2*B^T*S) * d
     // gemv_by4 (sensitivity probe, see "what stays a restatement" in the header): the two matrix-vector products summed
