@@ -127,7 +127,7 @@ def test_config5_200_ticks_on_device():
     disp = (st["position"][:, 0] - x0)[straight]
     want = cmd[straight] * T * scenarios.DT_MPC
     # the reference's weights/clamped position set-point track ~76 % of the commanded speed in steady state (the same
-    # ratio with qpOASES in the loop, tools/rollout_cpu_sim.py); initial-velocity transients move it by a few cm
+    # ratio with qpOASES in the loop, tests/tools/rollout_cpu_sim.py); initial-velocity transients move it by a few cm
     fast = np.abs(want) > 1.0
     ratio = disp[fast] / want[fast]
     dev = np.abs(disp - 0.76 * want)

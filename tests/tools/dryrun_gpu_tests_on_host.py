@@ -4,10 +4,10 @@ names, shapes, tolerances — before a test meets a GPU.  Not part of any test r
 BatchedMPC below lives in this script only).
 
     python -m pytest tests/test_kernel_source_on_host.py -q -k prepare     # builds tests/host_emul/_build/
-    python tools/dryrun_gpu_tests_on_host.py
+    python tests/tools/dryrun_gpu_tests_on_host.py
 """
 import sys, ctypes, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from hector_simulation_b200 import interface
