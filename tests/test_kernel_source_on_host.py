@@ -358,7 +358,8 @@ def test_solve_kernel_source_against_the_compiled_reference(emul):
 def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
     """Every CUDA thread is an OS thread and every barrier / warp primitive real synchronisation, so ThreadSanitizer sees
     any two conflicting accesses the kernel does not order (removing a single __syncwarp from the active-set loop makes it
-    report within one QP).  Paths: class 0, class 1, class 1 -> class 2 escalation, runtime-horizon variants."""
+    report within one QP).  Paths: class 0, class 1, class 1 -> class 2 escalation, runtime-horizon variants (up to 544
+    threads), the in-place gather mode with double stores, the warm start."""
     from conftest import load_golden
 
     exe = os.path.join(BUILD, "race_driver_tsan")
@@ -370,7 +371,7 @@ def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
     if r.returncode != 0:
         pytest.skip("no ThreadSanitizer runtime with this toolchain: " + r.stderr[-300:])
     cases = [("cfg2_h10", [0, 1, 2], ()), ("cfg1_h10", [0], ()), ("degenerate_zero_force_h10", [0], ()),
-             ("cfg4_h5", [0, 1, 2, 3], ()),
+             ("cfg4_h5", [0, 1, 2, 3], ()), ("cfg4_h16", [0, 1, 2], ()),       # runtime horizons: 64/224 and 224/544 threads
              ("cfg3_h10", [0, 1], ("raw",)),          # in-place gather of update_data_t records, double results
              ("cfg2_h10", [3, 4], ("warm",))]         # S-pair warm start
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66")
