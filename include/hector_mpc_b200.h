@@ -236,7 +236,10 @@ struct hmpc_swing_cmd_t
   double q_des[10];      /* commands[leg].qDes from computeIK */
   int swing[2];          /* swingStates[leg] > 0 */
 };
-/* dt = the controller's own period (0.001, SwingLegController.h:79), dtSwing = dtMPC (ConvexMPCLocomotion.cpp:70). */
+/* dt = the controller's own period (0.001, SwingLegController.h:79), dtSwing = dtMPC (ConvexMPCLocomotion.cpp:70).
+ * One call = one updateSwingLeg.  Note that the reference's ConvexMPCLocomotion::run calls updateSwingLeg inside its
+ * per-foot loop (ConvexMPCLocomotion.cpp:218), i.e. TWICE per control tick, so its swing-time countdown runs at 2*dt per
+ * tick; a caller reproducing that controller calls this function twice per tick (tests/test_reference_tick.py does). */
 HMPC_EXTERNC int hmpc_swing_device(hmpc_ctx* ctx, const struct hmpc_state_t* d_states, const struct hmpc_rollout_t* d_loop,
                                    const double* d_phase, struct hmpc_swing_t* d_swing, int B, double dt, double dtSwing,
                                    struct hmpc_swing_cmd_t* d_cmd, void* stream);
