@@ -141,10 +141,6 @@ struct hmpc_ctx {
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
-  // working-set warm start (S-pair guess at the unconstrained minimiser): measured SLOWER than the cold start on
-  // B200 (its Schur-factor build costs more instructions than the ~10 iterations it saves), so off unless
-  // HMPC_WARM_START=1; -1 = only for batches beyond one resident wave
-  int warm_mode = 0;
   // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
   // reference records from them and write results to them in place (no packing, no staging copies, no widening)
   struct Pin { char* base; size_t bytes; };   // what the caller asked for
@@ -162,28 +158,36 @@ struct hmpc_ctx {
 
 namespace {
 
-// kernel variants <threads, min CTAs/SM, sweep strip width, fixed horizon (0 = runtime), size class>
-//   0/1: horizon 10 fixed at compile time (class 0 / class 1)
-//   3..8: runtime horizon, 64 / 224 / 544 threads for class 0 and class 1
-#define HMPC_FOR_VARIANT(V, X)                      \
-  switch (V) {                                      \
-    case 0: X(64, 8, 6, 10, 0); break;              \
-    case 1: X(224, 2, 6, 10, 1); break;             \
-    case 3: X(64, 8, 6, 0, 0); break;               \
-    case 4: X(224, 2, 6, 0, 0); break;              \
-    case 5: X(544, 1, 6, 0, 0); break;              \
-    case 6: X(64, 8, 6, 0, 1); break;               \
-    case 7: X(224, 2, 6, 0, 1); break;              \
-    default: X(544, 1, 6, 0, 1); break;             \
+// kernel variants <threads, min CTAs/SM, fixed horizon (0 = runtime), size class>
+//   0/1: horizon 10 fixed at compile time (class 0: 4 warps, class 1: 8 warps)
+//   10 + 5*cls + b: runtime horizon, b-th entry of {64, 128, 192, 256, 384} threads
+#define HMPC_FOR_VARIANT(V, X)                   \
+  switch (V) {                                   \
+    case 0: X(128, 7, 10, 0); break;             \
+    case 1: X(256, 2, 10, 1); break;             \
+    case 10: X(64, 8, 0, 0); break;              \
+    case 11: X(128, 6, 0, 0); break;             \
+    case 12: X(192, 3, 0, 0); break;             \
+    case 13: X(256, 2, 0, 0); break;             \
+    case 14: X(384, 1, 0, 0); break;             \
+    case 15: X(64, 8, 0, 1); break;              \
+    case 16: X(128, 6, 0, 1); break;             \
+    case 17: X(192, 3, 0, 1); break;             \
+    case 18: X(256, 2, 0, 1); break;             \
+    default: X(384, 1, 0, 1); break;             \
   }
+const int kBucketThreads[5] = {64, 128, 192, 256, 384};
 
 cudaError_t prep_class(ClassCfg& c, int* occ)
 {
   cudaError_t e = cudaSuccess;
-#define HMPC_PREP(NT, MB, BW, NF, CL)                                                                  \
+  // The attribute is per kernel instantiation and process-wide, and several contexts (other horizons, the
+  // reference-style global context) share the runtime-horizon instantiations: always raise it to the device's opt-in
+  // maximum instead of this context's carve-up, so no context can lower it under another's launches.
+#define HMPC_PREP(NT, MB, NF, CL)                                                                       \
   {                                                                                                    \
-    auto k = hmpc::hmpc_solve_kernel<NT, MB, BW, NF, CL>;                                              \
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);                  \
+    auto k = hmpc::hmpc_solve_kernel<NT, MB, NF, CL>;                                                  \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);              \
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, NT, c.smem);       \
   }
   HMPC_FOR_VARIANT(c.variant, HMPC_PREP)
@@ -219,8 +223,8 @@ cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
 cudaError_t launch_class(const ClassCfg& c, const hmpc::KernelArgs& ka, int grid, cudaStream_t st, bool pdl = false)
 {
   cudaError_t e = cudaSuccess;
-#define HMPC_LAUNCH(NT, MB, BW, NF, CL) \
-  e = launch_chain(hmpc::hmpc_solve_kernel<NT, MB, BW, NF, CL>, dim3(grid), dim3(NT), (size_t)c.smem, st, pdl, ka);
+#define HMPC_LAUNCH(NT, MB, NF, CL) \
+  e = launch_chain(hmpc::hmpc_solve_kernel<NT, MB, NF, CL>, dim3(grid), dim3(NT), (size_t)c.smem, st, pdl, ka);
   HMPC_FOR_VARIANT(c.variant, HMPC_LAUNCH)
 #undef HMPC_LAUNCH
   return e != cudaSuccess ? e : cudaGetLastError();
@@ -231,8 +235,8 @@ int build_classes(hmpc_ctx* c)
   const int N = c->horizon;
   // class 0: at most N blocks of 6 variables (e.g. any single-support schedule); class 1: up to 2N.
   // Working-set overflow in class 0 escalates to class 1.
-  // class 2 = class 1's size with a working set as large as the variable count (1 CTA/SM): reached only by
-  // escalation from class 1 (massively degenerate optima, e.g. all contact forces at zero).
+  // class 2 = class 1's size with as many working-set slots as one SM's shared memory holds (1 CTA/SM): reached only
+  // by escalation from class 1 (massively degenerate optima, e.g. all contact forces at zero).
   c->ncls = 3;
   for (int i = 0; i < 3; i++) {
     ClassCfg& k = c->cls[i];
@@ -240,18 +244,17 @@ int build_classes(hmpc_ctx* c)
       k = c->cls[1];
       const int n = 6 * k.nb_cap;
       k.qmax = n;
-      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
-      while (k.L.total > 226 * 1024 && k.qmax > c->cls[1].qmax) {  // long horizons: as much as one SM's smem allows
+      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32);
+      while (k.L.total > 226 * 1024 && k.qmax > c->cls[1].qmax) {
         k.qmax -= 4;
-        k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride);
+        k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32);
       }
       if (k.qmax <= c->cls[1].qmax) { c->ncls = 2; break; }
       k.smem = k.L.total;
-      const int nbt = k.nb_cap * (k.nb_cap + 1) / 2;
-      const int need = nbt > n ? nbt : n;
-      const int bucket = need <= 64 ? 0 : (need <= 224 ? 1 : 2);
-      k.variant = 6 + bucket;  // runtime-layout class-1 instantiation
-      k.threads = bucket == 0 ? 64 : (bucket == 1 ? 224 : 544);
+      if (N == 10) {  // the runtime-layout instantiation of the same shape (the fixed one folds class 1's layout)
+        k.variant = 18;
+        k.threads = 256;
+      }
       int occ = 0;
       if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (class 2)")) return HMPC_ERR_CUDA;
       if (occ < 1) { g_err = "class-2 kernel does not fit on this device"; return HMPC_ERR_CUDA; }
@@ -260,20 +263,19 @@ int build_classes(hmpc_ctx* c)
     }
     k.nb_cap = hmpc::class_nb_cap(N, i);
     k.nb_hi = k.nb_cap;
-    const int n = 6 * k.nb_cap;
-    const int nbt = k.nb_cap * (k.nb_cap + 1) / 2;
-    const int need = nbt > n ? nbt : n;
-    const int bucket = need <= 64 ? 0 : (need <= 224 ? 1 : 2);
-    static const int bucket_threads[3] = {64, 224, 544};
+    const int warps = hmpc::class_warps(N, i);
+    int bucket = 0;
+    while (bucket < 4 && kBucketThreads[bucket] < 32 * warps) bucket++;
+    if (kBucketThreads[bucket] < 32 * warps) { g_err = "horizon too long for the built kernel variants"; return HMPC_ERR_ARG; }
     if (N == 10) {
       k.variant = i;
-      k.threads = (i == 0) ? 64 : 224;
+      k.threads = (i == 0) ? 128 : 256;
     } else {
-      k.variant = 3 + 3 * i + bucket;
-      k.threads = bucket_threads[bucket];
+      k.variant = 10 + 5 * i + bucket;
+      k.threads = kBucketThreads[bucket];
     }
     k.qmax = hmpc::class_qmax(N, i);
-    k.L = hmpc::class_layout(N, i);
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32);
     k.smem = k.L.total;
     int occ = 0;
     if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (is this an sm_100a device?)")) return HMPC_ERR_CUDA;
@@ -410,10 +412,6 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMallocHost(&c->h_cls, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMallocHost lists") ||
           build_classes(c) != HMPC_OK;
   }
-  if (!bad) {
-    const char* wm = getenv("HMPC_WARM_START");
-    if (wm) c->warm_mode = atoi(wm);
-  }
   if (!bad && max_batch >= 256) {
     const char* e = getenv("HMPC_HOST_THREADS");
     int nt = e ? atoi(e) : 4;
@@ -465,7 +463,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
     ka.tau = d_tau;
-    ka.warm_start = (c->warm_mode < 0) ? (B > c->cls[0].grid_cap ? 1 : 0) : c->warm_mode;
+    ka.warm_start = 0;
     ka.list = lists + (size_t)i * c->max_batch;
     ka.counts = counts;
     ka.cls = i;
@@ -523,7 +521,7 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
     ka.raw_records = reinterpret_cast<const unsigned char*>(raw);
     ka.wrench64 = wrench64;
     ka.tau = d_tau;
-    ka.warm_start = (c->warm_mode < 0) ? (nb > c->cls[0].grid_cap ? 1 : 0) : c->warm_mode;
+    ka.warm_start = 0;
     ka.list = d_block + 4 + (size_t)i * c->max_batch;
     ka.counts = d_block;
     ka.cls = i;
@@ -551,7 +549,7 @@ HMPC_EXTERNC int hmpc_class_config(const hmpc_ctx* c, int cls, int* out)
   if (!c || !out || cls < 0 || cls >= c->ncls) return HMPC_ERR_ARG;
   const ClassCfg& k = c->cls[cls];
   out[0] = k.threads; out[1] = k.smem; out[2] = k.qmax; out[3] = k.grid_cap; out[4] = k.nb_cap;
-  out[5] = 6;  // sweep strip width (columns of the 6x6 register block)
+  out[5] = 8;  // sweep tile edge (8x8 mma.m8n8k4.f64 accumulator tiles)
   return HMPC_OK;
 }
 

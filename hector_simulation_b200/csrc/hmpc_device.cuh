@@ -5,7 +5,8 @@
 //   stage 1  SRBD linearisation + foot rotations + constraint rows      (SolverMPC.cpp:374-433, 463-548)
 //   stage 2  forward-Euler discretisation, powers, Toeplitz blocks       (SolverMPC.cpp:133-193)
 //   stage 3  Hessian / gradient of the condensed QP, swing-leg removal   (SolverMPC.cpp:450-461, 557-570, 589-697)
-//   stage 4  in-register symmetric sweep inversion of H (fp64, one 6xBW block per thread)
+//   stage 4  blocked symmetric sweep inversion of H on the fp64 tensor pipe: 8x8 tiles in mma.sync.m8n8k4.f64
+//            accumulator fragments, one barrier per 8-pivot block step
 //   stage 5  dual active-set iterations on the explicit inverse           (replaces qpOASES, SolverMPC.cpp:702-712)
 //   stage 6  scatter of the optimal wrenches, eliminated entries = 0     (SolverMPC.cpp:720-732)
 //
@@ -34,41 +35,50 @@ enum : int { ST_OK = 0, ST_ITER_CAP = 1, ST_WS_CAP = 2, ST_INFEASIBLE = 3, ST_NO
 // shared-memory carve-up (byte offsets), computed once on the host and passed by value
 // ------------------------------------------------------------------------------------------------
 struct Layout {
-  int H, gq, x0, x, HA, nrm, rhs, blk, keep, misc, uni;
+  int H, gq, x0, nrm, fz, blk, keep, misc, uni;
   // solver view of the union
-  int Li, lam, dv, yv, rv, Wc, act;
+  int T, Sv, lam, dv, rr, wsl, zb;
+  // sweep view of the union
+  int Pb, Ws;
   // assembly view of the union
-  int rec, x0f, Acd, Bcd, P, M, dd, fbl;
+  int rec, x0f, Acd, Bcd, P, M, dd, fbl, comb;
   int total;
 };
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride)
+// H and H^-1 live in shared memory as the lower 8x8 tiles of the symmetric matrix (diagonal tiles complete): tile
+// (I,J), J <= I, at (I(I+1)/2 + J) * 64 elements, row-major inside.  During assembly the elements are the reference's
+// float32 values; the sweep leaves float64 there.
+__host__ __device__ constexpr int toff(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
+
+__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride, int nwarps)
 {
   Layout L{};
-  const int nbt = nb_cap * (nb_cap + 1) / 2;
-  const int n = 6 * nb_cap, m = 10 * nb_cap;
+  const int n = 6 * nb_cap;
+  const int nt8 = (n + 7) / 8, ntile = nt8 * (nt8 + 1) / 2;
   int o = 0;
-  L.H = o;    o += nbt * 36 * 8;
-  L.gq = o;   o += n * 8;
-  L.x0 = o;   o += n * 8;
-  L.x = o;    o += n * 8;   // doubles as sweep pivot-column buffer 0
-  L.HA = o;   o += n * 8;   // doubles as sweep pivot-column buffer 1
-  L.nrm = o;  o += 2 * 10 * 6 * 8;
-  L.rhs = o;  o += m * 8;
+  L.H = o;    o += ntile * 64 * 8;
+  L.gq = o;   o += nt8 * 8 * 8;       // gradient, zero-padded to whole tiles
+  L.x0 = o;   o += n * 8;             // unconstrained minimiser
+  L.nrm = o;  o += 2 * 10 * 6 * 8;    // the 20 distinct constraint normals
+  L.fz = o;   o += align16(nb_cap * 8);  // per block: f_max * gait (right-hand side of the Fz upper bound)
   L.blk = o;  o += align16((nb_cap + 2 * N) * 4);  // block -> (step,leg) and (step,leg) -> block
   L.keep = o; o += 64;     // joint angles + quaternion survive the union's reuse (torque epilogue)
   L.misc = o; o += 512;
   L.uni = o;
-  int s = L.uni;  // solver view
-  L.Li = s;   s += (qmax + 1) * (qmax + 2) / 2 * 8;
-  L.lam = s;  s += (qmax + 2) * 8;
-  L.dv = s;   s += (qmax + 2) * 8;
-  L.yv = s;   s += (qmax + 2) * 8;
-  L.rv = s;   s += (qmax + 2) * 8;
-  L.Wc = s;   s += align16((qmax + 2) * 4);
-  L.act = s;  s += align16(m);
+  int s = L.uni;  // solver view; one slot more than the capacity: the entering row needs one while a blocking row leaves
+  const int ns = qmax + 1;
+  L.T = s;    s += ns * n * 8;                      // H^-1 a_j of every working-set slot
+  L.Sv = s;   s += ns * (ns + 1) / 2 * 8;           // (A_W H^-1 A_W')^-1, packed lower rows
+  L.lam = s;  s += ns * 8;
+  L.dv = s;   s += ns * 8;
+  L.rr = s;   s += ns * 8;
+  L.wsl = s;  s += align16(ns * 4);
+  L.zb = s;   s += n * 8;
+  int w = L.uni;  // sweep view
+  L.Pb = w;   w += 2 * nt8 * 64 * 8;                // pivot panel, double-buffered
+  L.Ws = w;   w += nwarps * 64 * 8;                 // per-warp fragment-layout scratch
   int a = L.uni;  // assembly view
   L.rec = a;  a += align16(rec_stride);
   L.x0f = a;  a += 16 * 4;
@@ -78,29 +88,36 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.M = a;    a += align16(N * 72 * 4);
   L.dd = a;   a += align16(12 * N * 4);
   L.fbl = a;  a += 192 * 4;
-  L.total = align16(s > a ? s : a);
+  L.comb = a; a += align16(4 * N * 4);
+  int m = s > a ? s : a;
+  m = m > w ? m : w;
+  L.total = align16(m);
   return L;
 }
 
 // packed record stride (include/hector_mpc_b200.h: hmpc_record_bytes)
 __host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12 * N) * 4 + 2 * N); }
 
-// size classes: class 0 holds at most N blocks of 6 variables, class 1 up to 2N.  The working-set capacity is
-// the largest that still fits under the assembly staging area (class 1: at least min(n, 96)).
+// size classes: class 0 holds at most N blocks of 6 variables, class 1 up to 2N.  Working-set capacity: N + 5 rows for
+// class 0 (a walking gait ends with about one active row per stance step; 15 at N = 10), 32 for class 1; an instance that needs more
+// escalates to the next class (class 2 = class 1's size with as many slots as shared memory holds).
 __host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
 __host__ __device__ constexpr int class_qmax(int N, int cls)
 {
-  const int nb = class_nb_cap(N, cls), n = 6 * nb, rs = record_stride(N);
-  int q = n < 24 ? n : 24;
-  const int base = make_layout(N, nb, q, rs).total;
-  while (q < n && q < 250 && make_layout(N, nb, q + 1, rs).total <= base) q++;
-  const int floor1 = n < 96 ? n : 96;
-  if (cls == 1 && q < floor1) q = floor1;
-  return q;
+  const int n = 6 * class_nb_cap(N, cls);
+  const int q = cls == 0 ? N + 5 : 32;
+  return q < n ? q : n;
 }
-__host__ __device__ constexpr Layout class_layout(int N, int cls)
+// warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (10 per block)
+__host__ __device__ constexpr int class_warps(int N, int cls)
 {
-  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N));
+  const int nb = class_nb_cap(N, cls), n = 6 * nb, nt8 = (n + 7) / 8;
+  const int w_sweep = (nt8 + 1) / 2, w_rows = (10 * nb + 31) / 32;
+  return w_sweep > w_rows ? w_sweep : w_rows;
+}
+__host__ __device__ constexpr Layout class_layout(int N, int cls, int nwarps)
+{
+  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N), nwarps);
 }
 
 struct KernelArgs {
@@ -119,7 +136,8 @@ struct KernelArgs {
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
-  int warm_start;                // 1: guess the working set at the unconstrained minimiser (S-pair start)
+  int warm_start;                // 1: start from the working set in `ws_state` (previous tick), write it back
+  int* ws_state;                 // [batch][WS_STATE_INTS] persistent working sets (closed loop), or nullptr
   float* wrench;                 // [batch][12N] float results, or nullptr
   double* wrench64;              // [batch][12N] double results, or nullptr
   int* status;                   // [batch]
@@ -176,30 +194,65 @@ __device__ __forceinline__ int leg_of(int c12) { return (c12 / 3) & 1; }        
 __device__ __forceinline__ int loc_of(int c12) { return (c12 % 3) + (c12 >= 6 ? 3 : 0); }  // -> slot in [F(3) M(3)]
 __device__ __forceinline__ int col12_of(int leg, int loc) { return (loc < 3) ? 3 * leg + loc : 6 + 3 * leg + (loc - 3); }
 
-// symmetric matrix stored as lower 6x6 blocks: block (ib,jb), jb <= ib, at (ib(ib+1)/2+jb)*36, row-major inside
-__device__ __forceinline__ int blk_off(int ib, int jb) { return (ib * (ib + 1) / 2 + jb) * 36; }
-
-// dot of row (6*ib + r) of the symmetric matrix, restricted to block column kb, with a 6-vector
-__device__ __forceinline__ double hrow6(const double* H, int ib, int r, int kb, const double* v)
+// store element (i,j), i >= j, of the symmetric float32 Hessian into the tile layout (both triangles of a diagonal tile)
+__device__ __forceinline__ void hput(float* Hf, int i, int j, float v)
 {
-  double acc;
-  if (ib >= kb) {
-    const double2* p = reinterpret_cast<const double2*>(H + blk_off(ib, kb) + r * 6);
-    const double2 a = p[0], b = p[1], c = p[2];
-    acc = a.x * v[0];
-    acc = fma(a.y, v[1], acc);
-    acc = fma(b.x, v[2], acc);
-    acc = fma(b.y, v[3], acc);
-    acc = fma(c.x, v[4], acc);
-    acc = fma(c.y, v[5], acc);
-  } else {
-    const double* p = H + blk_off(kb, ib) + r;
-    acc = p[0] * v[0];
+  const int I = i >> 3, J = j >> 3;
+  Hf[toff(I, J) + ((i & 7) << 3) + (j & 7)] = v;
+  if (I == J) Hf[toff(I, I) + ((j & 7) << 3) + (i & 7)] = v;
+}
+
+// sum_c Hinv(i, j0 + c) * v[c], c < 6, j0 a multiple of 6: the six columns touch at most two tiles
+__device__ __forceinline__ double hinv_dot6(const double* Hi, int i, int j0, const double* v)
+{
+  const int I = i >> 3, ir = i & 7;
+  const int J0 = j0 >> 3, c0 = j0 & 7, J1 = J0 + 1;
+  const int sA = (I >= J0) ? 1 : 8, sB = (I >= J1) ? 1 : 8;
+  const double* pA = Hi + ((I >= J0) ? toff(I, J0) + ir * 8 + c0 : toff(J0, I) + c0 * 8 + ir);
+  const double* pB = Hi + ((I >= J1) ? toff(I, J1) + ir * 8 : toff(J1, I) + ir) - (8 - c0) * sB;
+  double acc = 0.0;
 #pragma unroll
-    for (int c = 1; c < 6; c++) acc = fma(p[6 * c], v[c], acc);
-  }
+  for (int c = 0; c < 6; c++) acc = fma((c0 + c < 8) ? pA[c * sA] : pB[c * sB], v[c], acc);
   return acc;
 }
+
+// row i of the symmetric tile-stored matrix times a vector padded to whole tiles
+__device__ __forceinline__ double hinv_rowdot(const double* Hi, int i, int nt8, const double* v)
+{
+  const int I = i >> 3, ir = i & 7;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int J = 0; J < nt8; J++) {
+    const double* p = Hi + ((J <= I) ? toff(I, J) + ir * 8 : toff(J, I) + ir);
+    const int st = (J <= I) ? 1 : 8;
+    const double* vv = v + 8 * J;
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      acc0 = fma(p[c * st], vv[c], acc0);
+      acc1 = fma(p[(c + 1) * st], vv[c + 1], acc1);
+    }
+  }
+  return acc0 + acc1;
+}
+
+__device__ __forceinline__ double dot6(const double* a, const double* b)
+{
+  double acc = a[0] * b[0];
+#pragma unroll
+  for (int c = 1; c < 6; c++) acc = fma(a[c], b[c], acc);
+  return acc;
+}
+
+// fp64 tensor-core MMA (SASS: DMMA.884): C[8x8] += A[8x4] * B[4x8].  Lane l = 4g + t holds A[g][t], B[t][g] and
+// C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Pivot-panel tiles are kept in "fragment order": element (r,c) at (c>>2)*32 + r*4 + (c&3), so that the A/B operand
+// fragment of k-half h is the contiguous run [h*32 + lane] and the accumulator pair of lane 4g+t is one 16-byte word.
+__device__ __forceinline__ int frag_pair(int lane) { return ((lane & 2) << 4) + ((lane >> 2) << 2) + ((lane & 1) << 1); }
+__device__ __forceinline__ int frag_elem(int r, int c) { return ((c >> 2) << 5) + (r << 2) + (c & 3); }
 
 // Eigen 3x3 inverse restated (oracle: inverse3)
 __device__ __forceinline__ float cof3(const float* m, int i, int j)
@@ -459,68 +512,47 @@ __device__ __forceinline__ unsigned fkey(float f)
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// block argmin of a float key with ONE barrier: REDUX per warp, partials to smem, every thread folds them.
-// Ties go to the smaller index.  `redk`/`redi` hold one entry per warp.
-__device__ __forceinline__ int block_argmin32(float v, int idx, unsigned* redk, int* redi, int nwarps)
+// Inverse of a symmetric positive definite 8x8 tile held in accumulator-fragment layout (lane 4g+t: a[g][2t], a[g][2t+1]),
+// by eight in-register sweeps; the reciprocal of pivot p+1 is predicted while pivot p is applied, so the dependent chain
+// per pivot is one reciprocal plus two multiply-adds.  Returns true if a pivot was not positive.
+__device__ __forceinline__ bool tile_inverse_spd(double& a0, double& a1, int lane)
 {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned key = fkey(v);
-  const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-  const int imin = __reduce_min_sync(0xffffffffu, key == kmin ? idx : 0x7fffffff);
-  if (lane == 0) { redk[wid] = kmin; redi[wid] = imin; }
-  __syncthreads();
-  unsigned k = redk[0];
-  int i = redi[0];
-  for (int w = 1; w < nwarps; w++) {
-    const unsigned ok = redk[w];
-    const int oi = redi[w];
-    if (ok < k || (ok == k && oi < i)) { k = ok; i = oi; }
-  }
-  return i;
-}
-
-// Inverse Cholesky factor P (P'P = S^-1, packed lower rows) without row/column l: rotate row l against every later
-// row so that column l of those rows vanishes (Givens on rows (l,i), i > l, keeps rows i lower triangular; row l
-// collects the direction that is projected out and is discarded), compacting the rows on the way.  Warp-collective;
-// `scratch` holds q doubles.
-__device__ __forceinline__ void li_downdate(double* Li, double* scratch, int l, int q, int lane)
-{
-  for (int j = lane; j < q; j += 32) scratch[j] = (j <= l) ? Li[l * (l + 1) / 2 + j] : 0.0;
-  double alpha = Li[l * (l + 1) / 2 + l];
-  __syncwarp();
-  for (int i = l + 1; i < q; i++) {
-    const double* ri_ = Li + i * (i + 1) / 2;
-    const double bq = ri_[l];
-    const double rr = sqrt(fma(bq, bq, alpha * alpha));
-    const double ir = fast_rcp(rr);
-    const double cg = alpha * ir, sg = bq * ir;
-    double* rnew = Li + (i - 1) * i / 2;  // ends exactly where the old row i begins
-    for (int j = lane; j <= i; j += 32) {
-      const double rl = scratch[j], rv_ = ri_[j];
-      scratch[j] = fma(cg, rl, sg * rv_);
-      const double ni = fma(-sg, rl, cg * rv_);
-      if (j != l) rnew[j < l ? j : j - 1] = ni;
+  const int g = lane >> 2, t4 = lane & 3;
+  bool bad = false;
+  double inv = fast_rcp(__shfl_sync(0xffffffffu, a0, 0));
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const double selp = (p & 1) ? a1 : a0;  // the element whose column has p's parity
+    const double colp = __shfl_sync(0xffffffffu, selp, 4 * g + (p >> 1));  // a[g][p]
+    const double r0 = __shfl_sync(0xffffffffu, a0, 4 * p + t4);            // a[p][2t], a[p][2t+1]
+    const double r1 = __shfl_sync(0xffffffffu, a1, 4 * p + t4);
+    const double d = __shfl_sync(0xffffffffu, selp, 4 * p + (p >> 1));     // a[p][p]
+    bad |= !(d > 0.0);
+    double invn = 0.0;
+    if (p < 7) {  // next pivot after this sweep: a[p+1][p+1] - a[p+1][p]^2 / a[p][p]
+      const double e = __shfl_sync(0xffffffffu, selp, 4 * (p + 1) + (p >> 1));
+      const double dn0 = __shfl_sync(0xffffffffu, ((p + 1) & 1) ? a1 : a0, 4 * (p + 1) + ((p + 1) >> 1));
+      invn = fast_rcp(fma(-e * inv, e, dn0));
     }
-    alpha = rr;
-    __syncwarp();
+    const double f = colp * inv;
+    double n0 = fma(-f, r0, a0), n1 = fma(-f, r1, a1);
+    if (g == p) { n0 = r0 * inv; n1 = r1 * inv; }
+    if (t4 == (p >> 1)) {
+      const double pc = (g == p) ? -inv : f;
+      if (p & 1) n1 = pc; else n0 = pc;
+    }
+    a0 = n0;
+    a1 = n1;
+    inv = invn;
   }
-}
-// entries j+1 -> j for j in [l, last) of an int and a double array (warp-collective)
-__device__ __forceinline__ void ws_close_gap(int* wc, double* val, int l, int last, int lane)
-{
-  for (int base = l; base < last; base += 32) {
-    const int j = base + lane;
-    int wn = 0;
-    double vn = 0.0;
-    if (j < last) { wn = wc[j + 1]; vn = val[j + 1]; }
-    __syncwarp();
-    if (j < last) { wc[j] = wn; val[j] = vn; }
-    __syncwarp();
-  }
+  a0 = -a0;
+  a1 = -a1;
+  return bad;
 }
 
 // working-set entry: block index in the high bits, normal index (leg*10+type) in the low byte
 __device__ __forceinline__ int ws_pack(int blk, int nidx) { return (blk << 8) | nidx; }
+__device__ __forceinline__ int tri(int s) { return s * (s + 1) / 2; }
 
 // ------------------------------------------------------------------------------------------------
 // row f-1: the caller's data preparation, one thread per robot (ConvexMPCLocomotion.cpp:283-406 followed by the
@@ -897,18 +929,20 @@ __global__ void hmpc_classify_kernel(const unsigned char* records, int rec_strid
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel.  NT threads; BW = columns of the 6xBW register block each thread sweeps (3 or 6);
+// the kernel.  NT threads = NT/32 warps: warp w owns tile rows w and NT8-1-w of the sweep, thread e owns
+// constraint row e in the active-set iterations and thread NT-1-i owns variable i.
 // NF > 0 fixes the horizon at compile time (layout offsets and loop bounds fold), NF == 0 reads it from
 // the arguments; CLS = size class (capacity N or 2N blocks of 6 variables).
 // ------------------------------------------------------------------------------------------------
-template <int NT, int MINB, int BW, int NF, int CLS>
+constexpr int WS_STATE_INTS = 40;  // persistent working set of one robot: [0] = count, then (step*2+leg) << 8 | normal index
+
+template <int NT, int MINB, int NF, int CLS>
 __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs ka)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   constexpr int NW = NT / 32;
-  constexpr int HPB = 6 / BW;  // threads per 6x6 block
   constexpr bool FIX = NF > 0;
   const int N = FIX ? NF : ka.horizon;
   const int nb_cap = FIX ? class_nb_cap(NF, CLS) : ka.nb_cap;
@@ -916,47 +950,47 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   const int rec_stride = FIX ? record_stride(NF) : ka.rec_stride;
   Layout L;
   if constexpr (FIX) {
-    constexpr Layout LC = class_layout(NF, CLS);
+    constexpr Layout LC = class_layout(NF, CLS, NW);
     L = LC;
   } else {
     L = ka.L;
   }
   const bool dump = (ka.dbg_H != nullptr);
 
-  double* H = reinterpret_cast<double*>(smem + L.H);
+  float* Hf = reinterpret_cast<float*>(smem + L.H);     // assembly: float32 Hessian tiles
+  double* Hd = reinterpret_cast<double*>(smem + L.H);   // after the sweep: float64 inverse tiles
   double* gq = reinterpret_cast<double*>(smem + L.gq);
   double* x0 = reinterpret_cast<double*>(smem + L.x0);
-  double* xv = reinterpret_cast<double*>(smem + L.x);
-  double* HA = reinterpret_cast<double*>(smem + L.HA);
   double* nrm = reinterpret_cast<double*>(smem + L.nrm);  // [leg*10+type][6]
-  double* rhs = reinterpret_cast<double*>(smem + L.rhs);  // [block*10 + type]
+  double* fz = reinterpret_cast<double*>(smem + L.fz);    // [block] f_max * gait
   int* blk_sl = reinterpret_cast<int*>(smem + L.blk);     // block -> step*2+leg
   int* sl_blk = blk_sl + nb_cap;                          // step*2+leg -> block or -1
   unsigned* redk = reinterpret_cast<unsigned*>(smem + L.misc);   // [32] warp partial keys
   int* redi = reinterpret_cast<int*>(smem + L.misc + 128);       // [32] warp partial indices
-  int* flags = reinterpret_cast<int*>(smem + L.misc + 384);  // [0]=NB [1]=stance0 [2]=stance1 [3]=code [4]=decision [5]=drop [6]=ncomb
+  double* redv = reinterpret_cast<double*>(smem + L.misc + 256); // [16] warp partial values
+  // [0]=NB [1]=stance0 [2]=stance1 [3]=code [4]=decision [5]=dropped row [6]=ncomb [7]=free slot [8]=slots in use (step) [9]=slots in use (now)
+  int* flags = reinterpret_cast<int*>(smem + L.misc + 384);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.misc + 448);
-  double* enext = reinterpret_cast<double*>(smem + L.misc + 464);  // [2] next-pivot diagonal, double-buffered
-  double* tstep = reinterpret_cast<double*>(smem + L.misc + 480);  // [1] step length of the current GI iteration
+  double* dsc = reinterpret_cast<double*>(smem + L.misc + 456);    // [0] step length, [1] refreshed slack of the entering row
+  unsigned* amask = reinterpret_cast<unsigned*>(smem + L.misc + 480);  // [8] slots in use (bit set)
 
-  double* Li = reinterpret_cast<double*>(smem + L.Li);
+  double* T = reinterpret_cast<double*>(smem + L.T);
+  double* Sv = reinterpret_cast<double*>(smem + L.Sv);
   double* lam = reinterpret_cast<double*>(smem + L.lam);
-  double* dv = reinterpret_cast<double*>(smem + L.dv);
-  double* yv = reinterpret_cast<double*>(smem + L.yv);
-  double* rv = reinterpret_cast<double*>(smem + L.rv);
-  int* Wc = reinterpret_cast<int*>(smem + L.Wc);
-  unsigned char* act = smem + L.act;
+  double* dvs = reinterpret_cast<double*>(smem + L.dv);
+  double* rr = reinterpret_cast<double*>(smem + L.rr);
+  int* wsl = reinterpret_cast<int*>(smem + L.wsl);
+  double* zb = reinterpret_cast<double*>(smem + L.zb);
 
   unsigned char* rec = smem + L.rec;
   const float* rf = reinterpret_cast<const float*>(rec);
   float* x0f = reinterpret_cast<float*>(smem + L.x0f);
   float* Acd = reinterpret_cast<float*>(smem + L.Acd);
   float* Bcd = reinterpret_cast<float*>(smem + L.Bcd);
-  float* Pbuf = reinterpret_cast<float*>(smem + L.P);  // two 13x13 buffers, 172 floats apart
   float* Mb = reinterpret_cast<float*>(smem + L.M);    // [N][6][12]: rows 0..5 of P_d*Bcd (6..11 equal Bcd's), columns grouped by leg
   float* dd = reinterpret_cast<float*>(smem + L.dd);   // [N][12]
   float* Fblk = reinterpret_cast<float*>(smem + L.fbl);
-  int* comb = reinterpret_cast<int*>(smem + L.HA);     // stage-3 work list (HA is free until the sweep)
+  int* comb = reinterpret_cast<int*>(smem + L.comb);   // stage-3 work list
 
   pdl_trigger();  // the next class's kernel may become resident while this one works
   if (tid == 0) {
@@ -1014,7 +1048,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const int k = __popc(mask & ((1u << lane) - 1u));
       if (lane < 2 * N) {
         sl_blk[lane] = (stance && k < nb_cap) ? k : -1;
-        if (stance && k < nb_cap) blk_sl[k] = lane;
+        if (stance && k < nb_cap) {
+          blk_sl[k] = lane;
+          fz[k] = (double)FM(ka.f_max, (float)gait[lane]);
+        }
       }
       unsigned st0 = 0, st1 = 0;
       for (int s = 0; s < N; s++) {
@@ -1022,8 +1059,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         st1 |= ((mask >> (2 * s + 1)) & 1u) << s;
       }
       // stage-3 work list: (li, lj, delta) combinations that own at least one wanted H block, sorted by chain
-      // length (longest first) so that the 32 items a warp runs in lockstep have similar trip counts and the
-      // warps can balance their load by grabbing chunks from a shared counter
+      // length (longest first) so that the 32 items a warp runs in lockstep have similar trip counts
       int ncomb = 0;
       {
         int pk[2], km[2];
@@ -1052,12 +1088,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         flags[2] = (int)st1;
         flags[3] = ST_OK;
         flags[6] = ncomb;
-        flags[7] = 0;  // stage-3 chunk counter
       }
     }
     __syncthreads();
     const int NB = flags[0];
     const int n = 6 * NB, m = 10 * NB;
+    const int NT8 = (n + 7) >> 3;
     const unsigned stmask[2] = {(unsigned)flags[1], (unsigned)flags[2]};
 
     // ---------------- stage 1: prologue, three roles on different warps ----------------
@@ -1068,9 +1104,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       if (wid == W1 && lane == 2) role_state(rf, ka.dt, x0f, Acd);
       if (wid == W2 && lane == 3) role_inertia(rf, ka.dt, Bcd);
     }
+    for (int e = n + tid; e < 8 * NT8; e += NT) gq[e] = 0.0;  // tile padding of the gradient
     __syncthreads();
 
-    // constraint normals (fp64 copies of the fp32 rows) and right-hand sides, "c'x >= d" form:
+    // constraint normals (fp64 copies of the fp32 rows), "c'x >= d" form:
     // t0-3 friction (lower), t4/t5 Mx lower/upper, t6/t7 line contact (upper), t8/t9 Fz lower/upper
     for (int e = tid; e < 2 * 10 * 6; e += NT) {
       const int leg = e / 60, t = (e / 6) % 10, c = e % 6;
@@ -1080,15 +1117,6 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const float v = Fblk[(8 * leg + row) * 12 + col];
       nrm[e] = (double)(neg ? -v : v);
     }
-    if (!dump) {
-      for (int e = tid; e < m; e += NT) {
-        const int k = e / 10, t = e % 10;
-        double d = 0.0;
-        if (t == 5) d = -(double)0.01f;
-        if (t == 9) d = -(double)FM(ka.f_max, (float)gait[blk_sl[k]]);
-        rhs[e] = d;
-      }
-    }
 
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 1] = clock64();
     // ---------------- stage 2: powers of Acd, Toeplitz blocks, d = A_qp x0 - X_d ----------------
@@ -1097,7 +1125,6 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     //   P_k[0:3][6:9]  (k-fold rounded accumulation of dt*Rb),  P_k[3+c][9+c],  P_k[5][12],  P_k[11][12],
     // and the reference's dense sequential products reduce to the few terms below — every dropped term is an
     // exact zero product, so the values are those of the dense sums (SolverMPC.cpp:148-177).
-    // Pk[k][0..8] = P_k[0:3][6:9], [9..11] = P_k[3+c][9+c], [12] = P_k[5][12], [13] = P_k[11][12]
     // Each item runs its own copy of the (one-FADD-per-step) recurrences, so the stage needs no exchange:
     //   items 0..35  : column c of rows r and 3+r of every M_k (r = item/12)   -> Mb[k][r][.], Mb[k][3+r][.]
     //   items 36..47 : row r of every d_s = P_{s+1} x0 - traj_s
@@ -1161,11 +1188,11 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       float* olb = ka.dbg_lb + (size_t)inst * 16 * N;
       float* oub = ka.dbg_ub + (size_t)inst * 16 * N;
       for (int e = tid; e < 16 * N; e += NT) {
-        const int s = e / 16, r = e % 16, leg = r / 8, rr = r % 8;
+        const int s = e / 16, r = e % 16, leg = r / 8, rr_ = r % 8;
         float lo = 0.f, hi = 0.f;
-        if (rr < 4) hi = (float)5e10;
-        else if (rr == 4) hi = 0.01f;
-        else if (rr < 7) lo = (float)(-5e10);
+        if (rr_ < 4) hi = (float)5e10;
+        else if (rr_ == 4) hi = 0.01f;
+        else if (rr_ < 7) lo = (float)(-5e10);
         else hi = FM(ka.f_max, (float)gait[2 * s + leg]);
         olb[e] = lo;
         oub[e] = hi;
@@ -1177,12 +1204,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       for (int r = 0; r < 12; r++) wr[r] = rf[30 + r];
       // item = (li, lj, delta, i): running sums G_delta(K)[i][leg lj's six columns] = sum_{e<=K} T_{e+delta}^T M_e;
       // block (a,b) of B'SB, b - a = delta, equals G_delta(N-1-b) — the oracle's own summation order.
+      // 32-item chunks in list order (longest chains first) go to the warps round-robin.
       const int nitems = flags[6] * 6;
-      while (true) {
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&flags[7], 1);  // next 32 items (longest chains first)
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk * 32 >= nitems) break;
+      for (int chunk = wid; chunk * 32 < nitems; chunk += NW) {
         const int it = chunk * 32 + lane;
         if (it >= nitems) continue;
         const int cm = comb[it / 6], ci = it % 6;
@@ -1244,9 +1268,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           const int a = N - 1 - K - delta, b = a + delta;
           if ((need >> a) & 1u) {
             if (!dump && delta > 0) {  // block (b,a) strictly below the diagonal: element (cj, ci), no alpha
-              double* dst = H + blk_off(sl_blk[2 * b + lj], sl_blk[2 * a + li]) + ci;
+              const int col = 6 * sl_blk[2 * a + li] + ci, row0 = 6 * sl_blk[2 * b + lj];
 #pragma unroll
-              for (int cj = 0; cj < 6; cj++) dst[cj * 6] = (double)FM(2.f, FA(acc[cj], 0.f));
+              for (int cj = 0; cj < 6; cj++) hput(Hf, row0 + cj, col, FM(2.f, FA(acc[cj], 0.f)));
             } else {
               const int ka_ = dump ? 0 : sl_blk[2 * a + li], kb_ = dump ? 0 : sl_blk[2 * b + lj];
 #pragma unroll
@@ -1260,12 +1284,8 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
                   oH[(size_t)(12 * a + ii) * (12 * N) + 12 * b + jj] = hv;
                   oH[(size_t)(12 * b + jj) * (12 * N) + 12 * a + ii] = hv;
                 } else {
-                  const double hd = (double)hv;
-                  if (ka_ == kb_) {
-                    H[blk_off(ka_, ka_) + ci * 6 + cj] = hd;
-                    H[blk_off(ka_, ka_) + cj * 6 + ci] = hd;
-                  } else if (kb_ > ka_) H[blk_off(kb_, ka_) + cj * 6 + ci] = hd;
-                  else H[blk_off(ka_, kb_) + ci * 6 + cj] = hd;
+                  const int gi = 6 * ka_ + ci, gj = 6 * kb_ + cj;
+                  hput(Hf, gi > gj ? gi : gj, gi > gj ? gj : gi, hv);
                 }
               }
             }
@@ -1307,435 +1327,393 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = 0.0;
       }
       if (ka.tau && tid < 10) ka.tau[(size_t)inst * 10 + tid] = 0.f;
-      if (tid == 0) ka.status[inst] = ST_OK;
+      if (tid == 0) {
+        ka.status[inst] = ST_OK;
+        if (ka.ws_state) ka.ws_state[(size_t)inst * WS_STATE_INTS] = 0;
+      }
       __syncthreads();
       continue;
     }
 
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 3] = clock64();
-    // ---------------- stage 4: sweep inversion, one 6xBW block per thread in registers ----------------
-    // After sweeping every pivot the matrix holds -H^-1 (Goodnight's sweep operator on an SPD matrix).
-    // Per pivot: ONE barrier.  The pivot column k+1 and the current value of diagonal k+2 are published
-    // during step k, and every thread predicts pivot k+1's reciprocal while it applies step k.
-    // The pivot row/column come out of the generic rank-1 update by biasing the column entries at k:
-    //   row factor d-1 instead of d, column factor 1-1/d instead of 1, and (k,k) corrected by -2.
+    // ---------------- stage 4: blocked sweep inversion on the fp64 tensor pipe ----------------
+    // The symmetric matrix is cut into 8x8 tiles (rows/columns beyond n: identity).  Sweeping the diagonal tile k
+    //   A_kk <- -D^-1,  A_ik <- A_ik D^-1,  A_kj <- D^-1 A_kj,  A_ij <- A_ij - A_ik D^-1 A_kj        (D = A_kk)
+    // for k = 0..NT8-1 leaves -H^-1 (Goodnight's sweep operator, block form; every D is a Schur complement of an SPD
+    // matrix, so no pivoting).  Each warp keeps the lower tiles of two tile rows in mma accumulator fragments for the
+    // whole stage.  Per block step: ONE barrier.  During step k the owners of panel k+1 update those tiles first and
+    // publish them (the diagonal one already inverted, in-register) in fragment order, so that in step k+1 every
+    // operand of W_I = P_I D^-1 and of the rank-8 updates A_IJ -= W_I P_J' is one conflict-free 8-byte load.
     {
-      const int nbt = NB * (NB + 1) / 2;
-      const int bt = tid / HPB, hh = tid % HPB;  // block id, strip
-      const bool own = bt < nbt;
-      int ib = 0, jb = 0;
-      if (own) {
-        ib = (int)((sqrtf(8.f * (float)bt + 1.f) - 1.f) * 0.5f);
-        while ((ib + 1) * (ib + 2) / 2 <= bt) ib++;
-        while (ib * (ib + 1) / 2 > bt) ib--;
-        jb = bt - ib * (ib + 1) / 2;
-      }
-      const int c0 = BW * hh;  // first column of this thread's strip inside the block
-      double a[6][BW];
-      if (own) {
-        const double* src = H + blk_off(ib, jb) + c0;
+      constexpr int TS = 2 * NW + 1;  // accumulator slots per warp: rows rA (rA+1 tiles) and rB (rB+1 tiles), rA+rB = NT8-1
+      const int rA = wid, rB = NT8 - 1 - wid;
+      const int ntA = (rA <= rB) ? rA + 1 : 0, ntB = (rA < rB) ? rB + 1 : 0, ntl = ntA + ntB;
+      const int g = lane >> 2, t4 = lane & 3;
+      const int fp = frag_pair(lane);
+      double c0[TS], c1[TS];
 #pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-          for (int c = 0; c < BW; c++) a[r][c] = src[r * 6 + c];
-      }
-      double* colbuf[2] = {xv, HA};
-      // publish pivot column 0 and diagonal 1
-      if (own) {
-        if (jb == 0 && hh == 0) {
-#pragma unroll
-          for (int r = 0; r < 6; r++) colbuf[0][6 * ib + r] = a[r][0];
+      for (int t = 0; t < TS; t++) {
+        c0[t] = 0.0;
+        c1[t] = 0.0;
+        if (t < ntl) {
+          const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
+          const int i = 8 * I + g, j = 8 * J + 2 * t4;
+          const float2 v = *reinterpret_cast<const float2*>(Hf + toff(I, J) + g * 8 + 2 * t4);
+          c0[t] = (i < n && j < n) ? (double)v.x : (i == j ? 1.0 : 0.0);
+          c1[t] = (i < n && j + 1 < n) ? (double)v.y : (i == j + 1 ? 1.0 : 0.0);
         }
-        if (ib == 0 && jb == 0 && hh == 1 / BW) enext[0] = a[1][1 % BW];
       }
+      double* Pbuf = reinterpret_cast<double*>(smem + L.Pb);
+      double* Wscr = reinterpret_cast<double*>(smem + L.Ws) + wid * 64;
+      bool bad = false;
+      // publish slot t's tile into panel kk's buffer if it belongs to it (after inverting the diagonal tile)
+      auto publish = [&](int t, int kk, double v0, double v1) {
+        const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
+        double* Pn = Pbuf + (kk & 1) * NT8 * 64;
+        if (J == kk) {        // column kk: P_I = A_I,kk  (I == kk: D, inverted first)
+          if (I == kk) bad |= tile_inverse_spd(v0, v1, lane);
+          *reinterpret_cast<double2*>(Pn + I * 64 + fp) = make_double2(v0, v1);
+        } else if (I == kk) {  // row kk, J < kk: P_J = A_kk,J transposed
+          Pn[J * 64 + frag_elem(2 * t4, g)] = v0;
+          Pn[J * 64 + frag_elem(2 * t4 + 1, g)] = v1;
+        }
+      };
+#pragma unroll
+      for (int t = 0; t < TS; t++)
+        if (t < ntl) publish(t, 0, c0[t], c1[t]);
       __syncthreads();
-      double inv = fast_rcp(colbuf[0][0]);
-      bool bad = !(colbuf[0][0] > 0.0);
-      const double* rowp = colbuf[0] + 6 * ib;        // this thread's six row entries of the pivot column
-      const double* colp = colbuf[0] + 6 * jb + c0;   // and its BW column entries
-      const int boff = (int)(colbuf[1] - colbuf[0]);
-      for (int kb = 0; kb < NB; kb++) {
-        const bool rowk = own && (ib == kb), colk = own && (jb == kb);
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) {
-          const int k = 6 * kb + kk;
-          const int cur = (kk & 1) ? boff : 0, nxt = (kk & 1) ? 0 : boff;
-          double invn = 0.0;
-          if (k + 1 < n) {  // reciprocal of the next pivot, overlapped with this step's updates
-            const double cn = colbuf[0][cur + k + 1];
-            const double dn = fma(-cn, cn * inv, enext[kk & 1]);
-            bad |= !(dn > 0.0);
-            invn = fast_rcp(dn);
-          }
-          if (own) {
-            double ci[6], cj[BW];
-#pragma unroll
-            for (int r = 0; r < 6; r++) ci[r] = rowp[cur + r];
-#pragma unroll
-            for (int c = 0; c < BW; c++) cj[c] = colp[cur + c] * inv;
-            if (rowk) ci[kk] -= 1.0;
-            if (colk && hh == kk / BW) cj[kk % BW] = 1.0 - inv;
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-              for (int c = 0; c < BW; c++) a[r][c] = fma(-ci[r], cj[c], a[r][c]);
-            if (rowk && colk && hh == kk / BW) a[kk][kk % BW] -= 2.0;
-            // publish column k+1 (and diagonal k+2) for the next step
-            double* coln = colbuf[0] + nxt;
-            if (kk < 5) {
-              if (colk && hh == (kk + 1) / BW) {
-#pragma unroll
-                for (int r = 0; r < 6; r++) coln[6 * ib + r] = a[r][(kk + 1) % BW];
-              } else if (rowk && jb < kb) {
-#pragma unroll
-                for (int c = 0; c < BW; c++) coln[6 * jb + c0 + c] = a[kk + 1][c];
-              }
-              if (kk < 4) {
-                if (rowk && colk && hh == (kk + 2) / BW) enext[(kk + 1) & 1] = a[kk + 2][(kk + 2) % BW];
-              } else {
-                if (ib == kb + 1 && jb == kb + 1 && hh == 0) enext[(kk + 1) & 1] = a[0][0];
-              }
-            } else {
-              if (jb == kb + 1 && hh == 0) {
-#pragma unroll
-                for (int r = 0; r < 6; r++) coln[6 * ib + r] = a[r][0];
-              } else if (ib == kb + 1 && jb < kb + 1) {
-#pragma unroll
-                for (int c = 0; c < BW; c++) coln[6 * jb + c0 + c] = a[0][c];
-              }
-              if (ib == kb + 1 && jb == kb + 1 && hh == 1 / BW) enext[(kk + 1) & 1] = a[1][1 % BW];
-            }
-          }
-          __syncthreads();
-          inv = invn;
+      for (int k = 0; k < NT8; k++) {
+        const double* Pb = Pbuf + (k & 1) * NT8 * 64;
+        const double di0 = Pb[k * 64 + lane], di1 = Pb[k * 64 + 32 + lane];  // D^-1 operand fragments
+        // W_I = P_I D^-1 for the warp's own rows: accumulator layout (the new column-k tile) and, negated, as the
+        // A operand of the rank-8 updates
+        double WA0 = 0.0, WA1 = 0.0, WB0 = 0.0, WB1 = 0.0, wa0 = 0.0, wa1 = 0.0, wb0 = 0.0, wb1 = 0.0;
+        if (ntA && rA != k) {
+          dmma884(WA0, WA1, Pb[rA * 64 + lane], di0);
+          dmma884(WA0, WA1, Pb[rA * 64 + 32 + lane], di1);
+          *reinterpret_cast<double2*>(Wscr + fp) = make_double2(-WA0, -WA1);
+          __syncwarp();
+          wa0 = Wscr[lane];
+          wa1 = Wscr[32 + lane];
+          __syncwarp();
         }
-      }
-      if (own) {
-        double* dst = H + blk_off(ib, jb) + c0;
+        if (ntB && rB != k) {
+          dmma884(WB0, WB1, Pb[rB * 64 + lane], di0);
+          dmma884(WB0, WB1, Pb[rB * 64 + 32 + lane], di1);
+          *reinterpret_cast<double2*>(Wscr + fp) = make_double2(-WB0, -WB1);
+          __syncwarp();
+          wb0 = Wscr[lane];
+          wb1 = Wscr[32 + lane];
+          __syncwarp();
+        }
+        auto update = [&](int t, double& v0, double& v1) {
+          const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
+          if (I == k) {
+            if (J == k) {  // -D^-1
+              const double2 d = *reinterpret_cast<const double2*>(Pb + k * 64 + fp);
+              v0 = -d.x;
+              v1 = -d.y;
+            } else {       // D^-1 P_J'
+              v0 = 0.0;
+              v1 = 0.0;
+              dmma884(v0, v1, di0, Pb[J * 64 + lane]);
+              dmma884(v0, v1, di1, Pb[J * 64 + 32 + lane]);
+            }
+          } else if (J == k) {
+            v0 = (t < ntA) ? WA0 : WB0;
+            v1 = (t < ntA) ? WA1 : WB1;
+          } else {
+            dmma884(v0, v1, (t < ntA) ? wa0 : wb0, Pb[J * 64 + lane]);
+            dmma884(v0, v1, (t < ntA) ? wa1 : wb1, Pb[J * 64 + 32 + lane]);
+          }
+        };
+        // look-ahead: the diagonal tile of the next panel first (its inversion is the longest chain of the step)
+        const int kn = k + 1;
+        const int tdiag = (kn >= NT8) ? -1 : (rA == kn && ntA ? rA : (rB == kn && ntB ? ntA + rB : -1));
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+        for (int t = 0; t < TS; t++)
+          if (t == tdiag) {
+            update(t, c0[t], c1[t]);
+            publish(t, kn, c0[t], c1[t]);
+          }
 #pragma unroll
-          for (int c = 0; c < BW; c++) dst[r * 6 + c] = -a[r][c];
+        for (int t = 0; t < TS; t++)
+          if (t < ntl && t != tdiag) {
+            update(t, c0[t], c1[t]);
+            if (kn < NT8) publish(t, kn, c0[t], c1[t]);
+          }
+        __syncthreads();
       }
-      if (bad && tid == 0) flags[3] = ST_NOT_SPD;
+#pragma unroll
+      for (int t = 0; t < TS; t++)
+        if (t < ntl) {
+          const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
+          *reinterpret_cast<double2*>(Hd + toff(I, J) + g * 8 + 2 * t4) = make_double2(-c0[t], -c1[t]);
+        }
+      if (__any_sync(0xffffffffu, bad) && lane == 0) flags[3] = ST_NOT_SPD;
       __syncthreads();
     }
 
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 4] = clock64();
-    // ---------------- stage 5: dual active-set iterations ----------------
-    // per-thread constants: one variable (row of H^-1)
-    const bool isvar = tid < n;
-    const int vib = tid / 6, vr = tid % 6;
-    double mx = 0.0;
-    if (isvar) {  // x0 = -H^-1 g
-      double acc = 0.0;
-      for (int jbk = 0; jbk < NB; jbk++) acc += hrow6(H, vib, vr, jbk, gq + 6 * jbk);
-      x0[tid] = -acc;
-      xv[tid] = -acc;
-      mx = fabs(acc);
+    // ---------------- stage 5: dual active-set iterations (Goldfarb-Idnani) ----------------
+    // Thread e < m owns constraint row e (slack s_e in a register), thread NT-1-i owns variable i.  A working-set slot
+    // keeps t_j = H^-1 a_j; the Schur complement inverse (A_W H^-1 A_W')^-1 is held explicitly (rank-1 up/downdates).
+    // One working-set change = selection | t_p = H^-1 a_p | warp 0: step direction, ratio test, update | x, slacks:
+    // four barriers.
+    const int vi = NT - 1 - tid;
+    const bool isvar = vi < n, iscon = tid < m;
+    double xreg = 0.0;
+    if (isvar) {
+      xreg = -hinv_rowdot(Hd, vi, NT8, gq);
+      x0[vi] = xreg;
     }
-    for (int e = tid; e < m; e += NT) act[e] = 0;
-    // tolerance scale: max |x0| (float ordering is enough)
-    const int imx = block_argmin32(-(float)mx, tid, redk, redi, NW);
-    const double tol = 1e-9 * fmax(1.0, fabs(x0[imx < n ? imx : 0]));
-    __syncthreads();  // x0/xv/act visible; redk/redi reusable
+    {
+      const unsigned key = __float_as_uint(fabsf((float)xreg));  // non-negative floats order like their bit patterns
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+      if (lane == 0) redk[16 + wid] = kmax;  // upper half: the selection below reuses redk[0..NW) without a barrier in between
+    }
+    if (tid < 8) amask[tid] = 0u;
+    if (tid == 0) { flags[7] = 0; flags[8] = 0; flags[9] = 0; }
+    __syncthreads();
+    double tol;
+    {
+      unsigned kx = redk[16];
+      for (int w = 1; w < NW; w++) kx = redk[16 + w] > kx ? redk[16 + w] : kx;
+      tol = 1e-9 * fmax(1.0, (double)__uint_as_float(kx));
+    }
+    // per-row constants: normal, right-hand side, slack at the unconstrained minimiser
+    double ne[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double se = 0.0;
+    int ke = 0;
+    bool act = false;
+    if (iscon) {
+      ke = tid / 10;
+      const int te = tid - 10 * ke;
+      const double* nn = nrm + ((blk_sl[ke] & 1) * 10 + te) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; c++) ne[c] = nn[c];
+      const double rhs_e = (te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ke] : 0.0);
+      se = dot6(ne, x0 + 6 * ke) - rhs_e;
+    }
 
     int q = 0, iters = 0;
     int code = flags[3];
-
-    // ---- warm start of the working set -------------------------------------------------------------------
-    // Take the most violated row of every block at the unconstrained minimiser, solve for its multipliers and
-    // accept the set if they are all positive: (x, W) is then an S-pair — x minimises the QP on the rows of W held
-    // as equalities, with non-negative multipliers — which is exactly the invariant the dual iteration below
-    // maintains, so it simply continues from there (for a walking gait this is usually already the optimum:
-    // one moment bound per step).  Any doubt (dependent rows, a non-positive multiplier) discards the guess.
-    if (code == ST_OK && ka.warm_start) {
-      if (wid == 0) {
-        int cand = -1, cnidx = 0;
-        double cb = 0.0;
-        if (lane < NB) {
-          const int leg = blk_sl[lane] & 1;
-          const double* xb = xv + 6 * lane;
-          double smin = -tol;
-          for (int t = 0; t < 10; t++) {
-            const double* nn = nrm + (leg * 10 + t) * 6;
-            double sl = -rhs[lane * 10 + t];
-#pragma unroll
-            for (int c = 0; c < 6; c++) sl = fma(nn[c], xb[c], sl);
-            if (sl < smin) { smin = sl; cand = lane * 10 + t; cnidx = leg * 10 + t; }
-          }
-          cb = -smin;
-        }
-        const unsigned has = __ballot_sync(0xffffffffu, cand >= 0);
-        int q0 = __popc(has);
-        if (q0 > qmax) q0 = 0;
-        if (cand >= 0 && q0 > 0) {
-          const int pos = __popc(has & ((1u << lane) - 1u));
-          Wc[pos] = ws_pack(lane, cnidx);
-          rv[pos] = cb;  // right-hand side of S lam = -s_W(x0)
-        }
-        __syncwarp();
-        bool ok = q0 > 0;
-        for (int jn = 0; jn < q0 && ok; jn++) {  // inverse Cholesky factor of S = A_W H^-1 A_W', row by row
-          const int wn = Wc[jn], kn = wn >> 8;
-          const double* nn = nrm + (wn & 0xff) * 6;
-          for (int i = lane; i <= jn; i += 32) {
-            const int wi = Wc[i];
-            const double* ni = nrm + (wi & 0xff) * 6;
-            double acc = 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; r++) acc = fma(nn[r], hrow6(H, kn, r, wi >> 8, ni), acc);
-            dv[i] = acc;
-          }
-          __syncwarp();
-          double yy = 0.0;
-          for (int j = lane; j < jn; j += 32) {
-            const double* row = Li + j * (j + 1) / 2;
-            double acc = 0.0;
-            for (int i = 0; i <= j; i++) acc = fma(row[i], dv[i], acc);
-            yv[j] = acc;
-            yy = fma(acc, acc, yy);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
-          __syncwarp();
-          const double sjj = dv[jn], znn = sjj - yy;
-          if (!(znn > 1e-9 * sjj)) { ok = false; break; }  // (nearly) dependent rows: not a safe start
-          const double irho = rsqrt(znn);
-          double* row = Li + jn * (jn + 1) / 2;
-          for (int i = lane; i < jn; i += 32) {
-            double acc = 0.0;
-            for (int j = i; j < jn; j++) acc = fma(Li[j * (j + 1) / 2 + i], yv[j], acc);
-            row[i] = -acc * irho;
-          }
-          if (lane == 0) row[jn] = irho;
-          __syncwarp();
-        }
-        // multipliers lam = Li'(Li b); rows with a non-positive multiplier are pruned (Givens downdate) and the
-        // rest re-solved, a few rounds at most
-        for (int round = 0; ok && round < 4; round++) {
-          for (int j = lane; j < q0; j += 32) {
-            const double* row = Li + j * (j + 1) / 2;
-            double acc = 0.0;
-            for (int i = 0; i <= j; i++) acc = fma(row[i], rv[i], acc);
-            yv[j] = acc;
-          }
-          __syncwarp();
-          bool neg = false;
-          if (lane < q0) {  // one row per block: q0 <= NB <= 32
-            double acc = 0.0;
-            for (int j = lane; j < q0; j++) acc = fma(Li[j * (j + 1) / 2 + lane], yv[j], acc);
-            lam[lane] = acc;
-            neg = !(acc > 0.0);
-          }
-          unsigned m_ = __ballot_sync(0xffffffffu, neg);
-          if (!m_) break;
-          if (round == 3) { ok = false; break; }
-          while (m_) {  // highest index first keeps the lower ones valid
-            const int l = 31 - __clz(m_);
-            m_ &= ~(1u << l);
-            li_downdate(Li, dv, l, q0, lane);
-            ws_close_gap(Wc, rv, l, q0 - 1, lane);
-            q0--;
-          }
-          if (q0 == 0) ok = false;
-        }
-        if (ok) {
-          for (int j = lane; j < q0; j += 32) {
-            const int w = Wc[j];
-            act[(w >> 8) * 10 + ((w & 0xff) % 10)] = 1;
-          }
-        }
-        if (lane == 0) flags[7] = ok ? q0 : 0;
-      }
-      __syncthreads();
-      q = flags[7];
-      iters = q;
-      if (q > 0) {
-        if (isvar) {
-          double acc = x0[tid];
-          for (int j = 0; j < q; j++) {
-            const int w = Wc[j];
-            acc = fma(lam[j], hrow6(H, vib, vr, w >> 8, nrm + (w & 0xff) * 6), acc);
-          }
-          xv[tid] = acc;
-        }
-        __syncthreads();
-      }
-    }
-
     while (code == ST_OK) {
-      // most violated inactive constraint (slacks straight from x; selection in float, value in double)
-      float sbest = 3.0e38f;
-      int pbest = 0x7fffffff;
-      for (int e = tid; e < m; e += NT) {
-        if (act[e]) continue;
-        const int k = e / 10, t = e - 10 * k, leg = blk_sl[k] & 1;
-        const double* nn = nrm + (leg * 10 + t) * 6;
-        const double* xb = xv + 6 * k;
-        double s = -rhs[e];
-#pragma unroll
-        for (int c = 0; c < 6; c++) s = fma(nn[c], xb[c], s);
-        const float sf = (float)s;
-        if (sf < sbest) { sbest = sf; pbest = e; }
+      // ---- most violated inactive row (selection in float, value in double) ----
+      const float sf = (iscon && !act) ? (float)se : 3.0e38f;
+      const unsigned key = fkey(sf);
+      const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+      const int imin = __reduce_min_sync(0xffffffffu, key == kmin ? tid : 0x7fffffff);
+      if (tid == imin) redv[wid] = se;
+      if (lane == 0) { redk[wid] = kmin; redi[wid] = imin; }
+      __syncthreads();
+      unsigned kb = redk[0];
+      int p = redi[0], wb = 0;
+      for (int w = 1; w < NW; w++) {
+        const unsigned ok = redk[w];
+        if (ok < kb) { kb = ok; p = redi[w]; wb = w; }  // ties: the lower warp holds the lower row index
       }
-      const int p = block_argmin32(sbest, pbest, redk, redi, NW);
-      if (p == 0x7fffffff) break;  // every row is in the working set
+      if (kb == fkey(3.0e38f)) break;  // every row is in the working set
+      double sp = redv[wb];
+      if (!(sp < -tol)) break;         // KKT point reached
       const int kp = p / 10, nip = (blk_sl[kp] & 1) * 10 + (p - 10 * kp);
       const double* np_ = nrm + nip * 6;
-      double sp = -rhs[p];
-#pragma unroll
-      for (int c = 0; c < 6; c++) sp = fma(np_[c], xv[6 * kp + c], sp);
-      if (!(sp < -tol)) break;  // KKT point reached
+      const int f = flags[7];  // slot the entering row will take
+      double* Tf = T + f * n;
+      if (isvar) Tf[vi] = hinv_dot6(Hd, vi, 6 * kp, np_);
+      __syncthreads();
 
-      // ---- add constraint p (possibly after dropping blocking ones) ----
+      // ---- add row p (possibly after dropping blocking ones) ----
       double lam_p = 0.0;
       while (true) {
         iters++;
         if (iters > ka.max_iter) { code = ST_ITER_CAP; break; }
-        double ha = 0.0;
-        if (isvar) {  // HA = H^-1 a_p
-          ha = hrow6(H, vib, vr, kp, np_);
-          HA[tid] = ha;
-        }
-        __syncthreads();
-        // warp 0: step direction in the dual space through the inverse Cholesky factor of the Schur complement
         if (wid == 0) {
-          double cHc = 0.0;
-#pragma unroll
-          for (int c = 0; c < 6; c++) cHc = fma(np_[c], HA[6 * kp + c], cHc);
-          for (int j = lane; j < q; j += 32) {
-            const int w = Wc[j];
-            const double* nj = nrm + (w & 0xff) * 6;
-            const double* hj = HA + 6 * (w >> 8);
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; c++) acc = fma(nj[c], hj[c], acc);
-            dv[j] = acc;
+          const int qhi = flags[9];
+          for (int s2 = lane; s2 < qhi; s2 += 32) {
+            double d = 0.0;
+            if ((amask[s2 >> 5] >> (s2 & 31)) & 1u) {
+              const int w = wsl[s2];
+              d = dot6(nrm + (w & 0xff) * 6, Tf + 6 * (w >> 8));
+            }
+            dvs[s2] = d;
           }
+          const double cHc = dot6(np_, Tf + 6 * kp);
           __syncwarp();
-          double yy = 0.0;
-          for (int j = lane; j < q; j += 32) {
-            const double* row = Li + j * (j + 1) / 2;
-            double acc = 0.0;
-            for (int i = 0; i <= j; i++) acc = fma(row[i], dv[i], acc);
-            yv[j] = acc;
-            yy = fma(acc, acc, yy);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
-          __syncwarp();
-          const double zn = cHc - yy;
-          const bool dependent = !(zn > 1e-11 * cHc);
-          double t1 = 1e300;
-          int l1 = 0x7fffffff;
-          for (int i = lane; i < q; i += 32) {
-            double acc = 0.0;
-            for (int j = i; j < q; j++) acc = fma(Li[j * (j + 1) / 2 + i], yv[j], acc);
-            rv[i] = acc;
+          // step direction in the dual space r = S^-1 d, curvature, ratio test
+          double part = 0.0, tloc = __longlong_as_double(0x7ff0000000000000ll);
+          int lloc = 0x7fffffff;
+          for (int s2 = lane; s2 < qhi; s2 += 32) {
+            const int rs = tri(s2);
+            double a0 = 0.0, a1 = 0.0;
+            int j = 0;
+            for (; j + 1 < qhi; j += 2) {
+              a0 = fma((j <= s2) ? Sv[rs + j] : Sv[tri(j) + s2], dvs[j], a0);
+              a1 = fma((j + 1 <= s2) ? Sv[rs + j + 1] : Sv[tri(j + 1) + s2], dvs[j + 1], a1);
+            }
+            if (j < qhi) a0 = fma((j <= s2) ? Sv[rs + j] : Sv[tri(j) + s2], dvs[j], a0);
+            const double acc = a0 + a1;
+            rr[s2] = acc;
+            part = fma(dvs[s2], acc, part);
             if (acc > 0.0) {
-              const double ratio = lam[i] * fast_rcp(acc);
-              if (ratio < t1 || (ratio == t1 && i < l1)) { t1 = ratio; l1 = i; }
+              const double ratio = lam[s2] * fast_rcp(acc);
+              if (ratio < tloc) { tloc = ratio; lloc = s2; }
             }
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
-            const int ol = __shfl_xor_sync(0xffffffffu, l1, o);
-            if (ot < t1 || (ot == t1 && ol < l1)) { t1 = ot; l1 = ol; }
-          }
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          const double zn = cHc - part;
+          // exact minimum of the non-negative ratios: high word, then low word among the lanes that hold it
+          const unsigned thi = (unsigned)__double2hiint(tloc), tlo = (unsigned)__double2loint(tloc);
+          const unsigned mhi = __reduce_min_sync(0xffffffffu, thi);
+          const unsigned mlo = __reduce_min_sync(0xffffffffu, thi == mhi ? tlo : 0xffffffffu);
+          const int l1 = __reduce_min_sync(0xffffffffu, (thi == mhi && tlo == mlo) ? lloc : 0x7fffffff);
+          const double t1 = (l1 == 0x7fffffff) ? 1e300 : __hiloint2double((int)mhi, (int)mlo);
+          const bool dependent = !(zn > 1e-11 * cHc);
           const double t2 = dependent ? 1e300 : fmax(0.0, -sp * fast_rcp(zn));
           const double t = fmin(t1, t2);
           int decision;  // 0 = full step (p joins W), 1 = partial step (drop l1, retry), 2 = infeasible, 3 = W full
           if (!(t < 1e299)) decision = 2;
           else if (t2 <= t1) decision = (q >= qmax) ? 3 : 0;
           else decision = 1;
+          __syncwarp();
           if (decision < 2) {
-            for (int i = lane; i < q; i += 32) lam[i] = fmax(0.0, lam[i] - t * rv[i]);
+            for (int s2 = lane; s2 < qhi; s2 += 32) lam[s2] = fmax(0.0, lam[s2] - t * rr[s2]);
           }
+          int qhn = qhi;
           if (decision == 0) {
-            // new row of the inverse factor: [-r'/rho, 1/rho], rho = sqrt(zn)
-            const double irho = rsqrt(zn);
-            double* row = Li + q * (q + 1) / 2;
-            for (int i = lane; i < q; i += 32) row[i] = -rv[i] * irho;
-            if (lane == 0) {
-              row[q] = irho;
-              Wc[q] = ws_pack(kp, nip);
-              lam[q] = lam_p + t;
-              act[p] = 1;
+            // bordered inverse: S^-1 <- [S^-1 + r r'/zn, -r/zn; -r'/zn, 1/zn] with the new row in slot f
+            const double izn = fast_rcp(zn);
+            qhn = (f + 1 > qhi) ? f + 1 : qhi;
+            for (int s2 = lane; s2 < qhn; s2 += 32) {
+              const int rs = tri(s2);
+              if (s2 == f) {
+                for (int j = 0; j < f; j++) Sv[rs + j] = -rr[j] * izn;
+                Sv[rs + f] = izn;
+              } else {
+                const double rs_ = rr[s2] * izn;
+                for (int j = 0; j <= s2; j++) Sv[rs + j] = (j == f) ? -rs_ : fma(rs_, rr[j], Sv[rs + j]);
+              }
             }
-          } else if (decision == 1 && lane == 0) {
-            lam[q] = lam_p + t;  // pending multiplier of p, parked behind the working set
-            Wc[q] = ws_pack(kp, nip);
-            flags[5] = l1;
+            __syncwarp();  // the multiplier update above also touched slot f (if it lies below qhi)
+            if (lane == 0) {
+              wsl[f] = ws_pack(kp, nip);
+              lam[f] = lam_p + t;
+              amask[f >> 5] |= 1u << (f & 31);
+            }
+          } else if (decision == 1) {
+            // drop slot l1: S^-1 <- S^-1 - c c'/c_l without row/column l1 (c = column l1), which is then cleared
+            lam_p += t;
+            for (int s2 = lane; s2 < qhi; s2 += 32) dvs[s2] = (s2 >= l1) ? Sv[tri(s2) + l1] : Sv[tri(l1) + s2];
+            __syncwarp();
+            const double ipv = fast_rcp(dvs[l1]);
+            for (int s2 = lane; s2 < qhi; s2 += 32) {
+              const int rs = tri(s2);
+              const double cs = dvs[s2] * ipv;
+              for (int j = 0; j <= s2; j++) Sv[rs + j] = (j == l1 || s2 == l1) ? 0.0 : fma(-cs, dvs[j], Sv[rs + j]);
+            }
+            if (lane == 0) {
+              const int w = wsl[l1];
+              flags[5] = (w >> 8) * 10 + ((w & 0xff) % 10);
+              lam[l1] = 0.0;
+              amask[l1 >> 5] &= ~(1u << (l1 & 31));
+            }
           }
+          __syncwarp();
           if (lane == 0) {
             flags[4] = decision;
-            tstep[0] = dependent ? 0.0 : t;
+            flags[8] = qhi;
+            flags[9] = qhn;
+            dsc[0] = dependent ? 0.0 : t;
+            int fn = 0;  // lowest free slot
+            while (fn < qmax && ((amask[fn >> 5] >> (fn & 31)) & 1u)) fn++;  // at most qmax rows are in use: fn <= qmax, a valid slot
+            flags[7] = fn;
           }
         }
         __syncthreads();
         const int decision = flags[4];
         if (decision >= 2) { code = (decision == 2) ? ST_INFEASIBLE : ST_WS_CAP; break; }
-        // primal step: x += t * (HA - H^-1 A_W' r)
-        {
-          const double t = tstep[0];
-          if (isvar && t != 0.0) {
-            double z = ha;
-            for (int j = 0; j < q; j++) {
-              const int w = Wc[j];
-              z = fma(-rv[j], hrow6(H, vib, vr, w >> 8, nrm + (w & 0xff) * 6), z);
-            }
-            xv[tid] = fma(t, z, xv[tid]);
+        const double t = dsc[0];
+        // primal step direction z = t_p - sum_j r_j t_j, x += t z
+        if (isvar) {
+          const int qhe = flags[8];
+          double z0 = Tf[vi], z1 = 0.0;
+          int j = 0;
+          for (; j + 1 < qhe; j += 2) {
+            z0 = fma(-rr[j], T[j * n + vi], z0);
+            z1 = fma(-rr[j + 1], T[(j + 1) * n + vi], z1);
           }
+          if (j < qhe) z0 = fma(-rr[j], T[j * n + vi], z0);
+          const double z = z0 + z1;
+          zb[vi] = z;
+          xreg = fma(t, z, xreg);
         }
+        __syncthreads();
+        if (iscon && t != 0.0) se = fma(t, dot6(ne, zb + 6 * ke), se);
         if (decision == 0) {
+          if (tid == p) act = true;
           q++;
-          __syncthreads();
           break;
         }
-        // ---- partial step: drop working-set entry l, downdate the inverse factor, refresh s_p ----
-        {
-          const int l = flags[5];
-          lam_p = lam[q];
-          __syncthreads();
-          if (wid == 0) {
-            li_downdate(Li, dv, l, q, lane);
-            if (lane == 0) {
-              const int w = Wc[l];
-              act[(w >> 8) * 10 + ((w & 0xff) % 10)] = 0;
-            }
-            __syncwarp();
-            ws_close_gap(Wc, lam, l, q, lane);  // the parked p sits at q and moves to q-1
-          }
-          q--;
-          __syncthreads();
-          sp = -rhs[p];
-#pragma unroll
-          for (int c = 0; c < 6; c++) sp = fma(np_[c], xv[6 * kp + c], sp);
-        }
+        // partial step: the blocking row left the working set; warp 0 needs the refreshed slack of p
+        if (tid == flags[5]) act = false;
+        if (tid == p) dsc[1] = se;
+        q--;
+        __syncthreads();
+        sp = dsc[1];
       }
     }
 
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 5] = clock64();
     // polish: x from scratch with the final multipliers, x = x0 + sum_j lam_j H^-1 a_j
-    if (code == ST_OK && isvar) {
-      double acc = x0[tid];
-      for (int j = 0; j < q; j++) {
-        const int w = Wc[j];
-        acc = fma(lam[j], hrow6(H, vib, vr, w >> 8, nrm + (w & 0xff) * 6), acc);
+    __syncthreads();
+    const int qhf = flags[9];
+    // The explicit Schur-complement inverse drifts when many nearly dependent rows are active (massively degenerate
+    // optima): refine the multipliers of the final working set against the exact rows S_ij = a_i' t_j,
+    // lam += S^-1 (b - S lam), b_i = d_i - a_i' x0.  Large working sets only; the usual ~N rows do not need it.
+    if (wid == 0 && code == ST_OK && q > 24) {
+      for (int round = 0; round < 2; round++) {
+        for (int s2 = lane; s2 < qhf; s2 += 32) {
+          double acc = 0.0;
+          if ((amask[s2 >> 5] >> (s2 & 31)) & 1u) {
+            const int w = wsl[s2], ki = w >> 8, te = (w & 0xff) % 10;
+            const double* ni = nrm + (w & 0xff) * 6;
+            acc = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
+            for (int j = 0; j < qhf; j++)
+              if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(-lam[j], dot6(ni, T + j * n + 6 * ki), acc);
+          }
+          dvs[s2] = acc;
+        }
+        __syncwarp();
+        for (int s2 = lane; s2 < qhf; s2 += 32) {
+          if (!((amask[s2 >> 5] >> (s2 & 31)) & 1u)) continue;
+          const int rs = tri(s2);
+          double acc = 0.0;
+          for (int j = 0; j < qhf; j++) acc = fma((j <= s2) ? Sv[rs + j] : Sv[tri(j) + s2], dvs[j], acc);
+          lam[s2] = fmax(0.0, lam[s2] + acc);
+        }
+        __syncwarp();
       }
-      HA[tid] = acc;
-    } else if (isvar) HA[tid] = xv[tid];
+    }
+    __syncthreads();
+    if (isvar) {
+      double acc = xreg;
+      if (code == ST_OK) {
+        acc = x0[vi];
+        for (int j = 0; j < qhf; j++)
+          if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
+      }
+      zb[vi] = acc;
+    }
     __syncthreads();
 
     // ---------------- stage 6: scatter (eliminated variables are exactly 0) ----------------
     for (int e = tid; e < 12 * N; e += NT) {
       const int s = e / 12, c12 = e % 12, leg = leg_of(c12);
       const int k = sl_blk[2 * s + leg];
-      const double v = (k >= 0) ? HA[6 * k + loc_of(c12)] : 0.0;
+      const double v = (k >= 0) ? zb[6 * k + loc_of(c12)] : 0.0;
       if (ka.wrench) ka.wrench[(size_t)inst * 12 * N + e] = (float)v;
-      if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = (double)(float)v;
+      if (ka.wrench64) ka.wrench64[(size_t)inst * 12 * N + e] = v;
     }
     if (ka.tau && tid < 10) {
       // row f-2: tau = J_force_moment^T * f_ff, f_ff = -rBody [F; M] of the first-step wrench
@@ -1754,16 +1732,16 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
                            2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx),
                            2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)};
       const int k0 = sl_blk[leg];  // step 0
-      double f[6] = {0, 0, 0, 0, 0, 0};
+      double fw[6] = {0, 0, 0, 0, 0, 0};
       if (k0 >= 0) {
-        const double* w = HA + 6 * k0;
+        const double* w = zb + 6 * k0;
 #pragma unroll
         for (int r = 0; r < 3; r++) {  // rBody = R^T
-          f[r] = -(R[0 * 3 + r] * (double)(float)w[0] + R[1 * 3 + r] * (double)(float)w[1] + R[2 * 3 + r] * (double)(float)w[2]);
-          f[3 + r] = -(R[0 * 3 + r] * (double)(float)w[3] + R[1 * 3 + r] * (double)(float)w[4] + R[2 * 3 + r] * (double)(float)w[5]);
+          fw[r] = -(R[0 * 3 + r] * (double)(float)w[0] + R[1 * 3 + r] * (double)(float)w[1] + R[2 * 3 + r] * (double)(float)w[2]);
+          fw[3 + r] = -(R[0 * 3 + r] * (double)(float)w[3] + R[1 * 3 + r] * (double)(float)w[4] + R[2 * 3 + r] * (double)(float)w[5]);
         }
       }
-      ka.tau[(size_t)inst * 10 + tid] = (float)leg_torque(q5, leg, j, f);
+      ka.tau[(size_t)inst * 10 + tid] = (float)leg_torque(q5, leg, j, fw);
     }
     if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 6] = clock64();
     if (tid == 0) {

@@ -172,6 +172,41 @@ inline int __reduce_min_sync(unsigned mask, int v)
     return m;
   });
 }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
+{
+  return hmpc_emul_exchange(mask, v, [&](const unsigned long long* s) {
+    unsigned m = (unsigned)s[0];
+    for (int l = 1; l < 32; l++) m = (unsigned)s[l] > m ? (unsigned)s[l] : m;
+    return m;
+  });
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+// mma.sync.aligned.m8n8k4.row.col.f64 (the kernel's dmma884 body is replaced by a call to this, test build step):
+// lane 4g+t holds A[g][t], B[t][g] and C[g][2t], C[g][2t+1]; the k-sum runs in index order with fused multiply-adds
+inline void hmpc_emul_dmma884(double& c0, double& c1, double a, double b)
+{
+  hmpc_emul::Warp& w = hmpc_emul_warp();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double A[4], B0[4], B1[4];
+  unsigned long long bits;
+  std::memcpy(&bits, &a, 8);
+  w.slot[lane] = bits;
+  w.bar.wait();
+  for (int k = 0; k < 4; k++) std::memcpy(&A[k], &w.slot[4 * g + k], 8);
+  w.bar.wait();
+  std::memcpy(&bits, &b, 8);
+  w.slot[lane] = bits;
+  w.bar.wait();
+  for (int k = 0; k < 4; k++) {
+    std::memcpy(&B0[k], &w.slot[4 * (2 * t) + k], 8);
+    std::memcpy(&B1[k], &w.slot[4 * (2 * t + 1) + k], 8);
+  }
+  w.bar.wait();
+  for (int k = 0; k < 4; k++) {
+    c0 = std::fma(A[k], B0[k], c0);
+    c1 = std::fma(A[k], B1[k], c1);
+  }
+}
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline long long clock64() { return 0; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -19,6 +19,7 @@
 //   - the four PTX helper bodies (mbar_init / mbar_expect_tx / mbar_wait / bulk_g2s) -> calls to hmpc_emul_* (cuda_runtime.h)
 //   - the `rcp.approx.ftz.f64` seed of fast_rcp -> `1.0 / x` (the Newton steps that follow are kept)
 //   - the dynamic shared-memory declaration -> a pointer to the emulated CTA's buffer
+//   - the body of dmma884 (mma.sync.m8n8k4.f64) -> hmpc_emul_dmma884, a warp-collective exchange + fused multiply-adds
 //   - every other `asm volatile(...)` (fences, griddepcontrol: no arithmetic) -> nothing
 // Everything else is the product's source, byte for byte.
 #include HMPC_DEVICE_HEADER
@@ -58,18 +59,24 @@ void run_cta(int NT, F fn)
   delete cta;
 }
 
-// the kernel variants of hmpc_capi.cu (HMPC_FOR_VARIANT): <threads, min CTAs/SM, strip, fixed horizon, class>
+// the kernel variants of hmpc_capi.cu (HMPC_FOR_VARIANT): <threads, min CTAs/SM, fixed horizon, class>
+const int kBucketThreads[5] = {64, 128, 192, 256, 384};
+int variant_threads(int variant) { return variant == 0 ? 128 : (variant == 1 ? 256 : kBucketThreads[(variant - 10) % 5]); }
 void launch_variant(int variant, const hmpc::KernelArgs& ka)
 {
   switch (variant) {
-    case 0: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 6, 10, 0>(ka); }); break;
-    case 1: run_cta(224, [=] { hmpc::hmpc_solve_kernel<224, 2, 6, 10, 1>(ka); }); break;
-    case 3: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 6, 0, 0>(ka); }); break;
-    case 4: run_cta(224, [=] { hmpc::hmpc_solve_kernel<224, 2, 6, 0, 0>(ka); }); break;
-    case 5: run_cta(544, [=] { hmpc::hmpc_solve_kernel<544, 1, 6, 0, 0>(ka); }); break;
-    case 6: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 6, 0, 1>(ka); }); break;
-    case 7: run_cta(224, [=] { hmpc::hmpc_solve_kernel<224, 2, 6, 0, 1>(ka); }); break;
-    default: run_cta(544, [=] { hmpc::hmpc_solve_kernel<544, 1, 6, 0, 1>(ka); }); break;
+    case 0: run_cta(128, [=] { hmpc::hmpc_solve_kernel<128, 7, 10, 0>(ka); }); break;
+    case 1: run_cta(256, [=] { hmpc::hmpc_solve_kernel<256, 2, 10, 1>(ka); }); break;
+    case 10: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 0, 0>(ka); }); break;
+    case 11: run_cta(128, [=] { hmpc::hmpc_solve_kernel<128, 6, 0, 0>(ka); }); break;
+    case 12: run_cta(192, [=] { hmpc::hmpc_solve_kernel<192, 3, 0, 0>(ka); }); break;
+    case 13: run_cta(256, [=] { hmpc::hmpc_solve_kernel<256, 2, 0, 0>(ka); }); break;
+    case 14: run_cta(384, [=] { hmpc::hmpc_solve_kernel<384, 1, 0, 0>(ka); }); break;
+    case 15: run_cta(64, [=] { hmpc::hmpc_solve_kernel<64, 8, 0, 1>(ka); }); break;
+    case 16: run_cta(128, [=] { hmpc::hmpc_solve_kernel<128, 6, 0, 1>(ka); }); break;
+    case 17: run_cta(192, [=] { hmpc::hmpc_solve_kernel<192, 3, 0, 1>(ka); }); break;
+    case 18: run_cta(256, [=] { hmpc::hmpc_solve_kernel<256, 2, 0, 1>(ka); }); break;
+    default: run_cta(384, [=] { hmpc::hmpc_solve_kernel<384, 1, 0, 1>(ka); }); break;
   }
 }
 struct ClassCfg {
@@ -84,25 +91,25 @@ int build_classes(int N, ClassCfg* cls)
   for (int i = 0; i < 2; i++) {
     ClassCfg& k = cls[i];
     k.nb_cap = hmpc::class_nb_cap(N, i);
-    const int n = 6 * k.nb_cap, nbt = k.nb_cap * (k.nb_cap + 1) / 2, need = nbt > n ? nbt : n;
-    const int bucket = need <= 64 ? 0 : (need <= 224 ? 1 : 2);
-    k.variant = (N == 10) ? i : 3 + 3 * i + bucket;
+    const int warps = hmpc::class_warps(N, i);
+    int bucket = 0;
+    while (bucket < 4 && kBucketThreads[bucket] < 32 * warps) bucket++;
+    k.variant = (N == 10) ? i : 10 + 5 * i + bucket;
     k.qmax = hmpc::class_qmax(N, i);
-    k.L = hmpc::class_layout(N, i);
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, variant_threads(k.variant) / 32);
   }
   {
     ClassCfg& k = cls[2];
     k = cls[1];
-    const int n = 6 * k.nb_cap;
+    if (N == 10) k.variant = 18;
+    const int n = 6 * k.nb_cap, nw = variant_threads(k.variant) / 32;
     k.qmax = n;
-    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs);
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, nw);
     while (k.L.total > 226 * 1024 && k.qmax > cls[1].qmax) {
       k.qmax -= 4;
-      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs);
+      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, nw);
     }
     if (k.qmax <= cls[1].qmax) ncls = 2;
-    const int nbt = k.nb_cap * (k.nb_cap + 1) / 2, need = nbt > n ? nbt : n;
-    k.variant = 6 + (need <= 64 ? 0 : (need <= 224 ? 1 : 2));
   }
   return ncls;
 }
