@@ -141,6 +141,7 @@ struct hmpc_ctx {
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
+  int block_rounds = 4;  // block start of the active-set stage (HMPC_BLOCK_ROUNDS=0: plain dual iteration, for A/B runs)
   // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
   // reference records from them and write results to them in place (no packing, no staging copies, no widening)
   struct Pin { char* base; size_t bytes; };   // what the caller asked for
@@ -295,6 +296,7 @@ hmpc::KernelArgs base_args(const hmpc_ctx* c, const void* d_records, int B, floa
   ka.dt = c->setup.dt;
   ka.f_max = c->setup.f_max;
   ka.max_iter = c->max_iter;
+  ka.block_rounds = c->block_rounds;
   ka.wrench = d_wrench;
   ka.status = d_status;
   return ka;
@@ -411,6 +413,10 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMallocHost(&c->h_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMallocHost results") ||
           cuda_fail(cudaMallocHost(&c->h_cls, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMallocHost lists") ||
           build_classes(c) != HMPC_OK;
+  }
+  if (!bad) {
+    const char* br = getenv("HMPC_BLOCK_ROUNDS");
+    if (br) c->block_rounds = atoi(br);
   }
   if (!bad && max_batch >= 256) {
     const char* e = getenv("HMPC_HOST_THREADS");

@@ -78,7 +78,7 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.zb = s;   s += n * 8;
   int w = L.uni;  // sweep view
   L.Pb = w;   w += 2 * nt8 * 64 * 8;                // pivot panel, double-buffered
-  L.Ws = w;   w += nwarps * 64 * 8;                 // per-warp fragment-layout scratch
+  L.Ws = w;   w += nwarps * 2 * 64 * 8;             // per warp: -W of its two tile rows, fragment order
   int a = L.uni;  // assembly view
   L.rec = a;  a += align16(rec_stride);
   L.x0f = a;  a += 16 * 4;
@@ -136,6 +136,7 @@ struct KernelArgs {
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
+  int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
   int warm_start;                // 1: start from the working set in `ws_state` (previous tick), write it back
   int* ws_state;                 // [batch][WS_STATE_INTS] persistent working sets (closed loop), or nullptr
   float* wrench;                 // [batch][12N] float results, or nullptr
@@ -1345,111 +1346,174 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // publish them (the diagonal one already inverted, in-register) in fragment order, so that in step k+1 every
     // operand of W_I = P_I D^-1 and of the rank-8 updates A_IJ -= W_I P_J' is one conflict-free 8-byte load.
     {
-      constexpr int TS = 2 * NW + 1;  // accumulator slots per warp: rows rA (rA+1 tiles) and rB (rB+1 tiles), rA+rB = NT8-1
+      // accumulator slots: tile J of row rB in c[J], tile J of row rA in c[2NW - J] (rA + rB = NT8 - 1 <= 2NW - 1, so the
+      // two never meet) — every slot index is a compile-time constant of the unrolled loops
+      constexpr int TS = 2 * NW + 1;
       const int rA = wid, rB = NT8 - 1 - wid;
-      const int ntA = (rA <= rB) ? rA + 1 : 0, ntB = (rA < rB) ? rB + 1 : 0, ntl = ntA + ntB;
+      const bool hasA = rA <= rB, hasB = rA < rB;
       const int g = lane >> 2, t4 = lane & 3;
       const int fp = frag_pair(lane);
+      const int ft = frag_elem(2 * t4, g);  // transposed element (2t, g); (2t+1, g) is 4 further
       double c0[TS], c1[TS];
 #pragma unroll
-      for (int t = 0; t < TS; t++) {
-        c0[t] = 0.0;
-        c1[t] = 0.0;
-        if (t < ntl) {
-          const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
-          const int i = 8 * I + g, j = 8 * J + 2 * t4;
-          const float2 v = *reinterpret_cast<const float2*>(Hf + toff(I, J) + g * 8 + 2 * t4);
-          c0[t] = (i < n && j < n) ? (double)v.x : (i == j ? 1.0 : 0.0);
-          c1[t] = (i < n && j + 1 < n) ? (double)v.y : (i == j + 1 ? 1.0 : 0.0);
-        }
+      for (int t = 0; t < TS; t++) { c0[t] = 0.0; c1[t] = 0.0; }
+      {
+        const int i = 8 * rB + g, j = 2 * t4;
+        const float* src = Hf + toff(rB, 0) + g * 8 + 2 * t4;
+#pragma unroll
+        for (int J = 0; J < 2 * NW; J++)
+          if (hasB && J <= rB) {
+            const float2 v = *reinterpret_cast<const float2*>(src + J * 64);
+            c0[J] = (i < n && 8 * J + j < n) ? (double)v.x : (i == 8 * J + j ? 1.0 : 0.0);
+            c1[J] = (i < n && 8 * J + j + 1 < n) ? (double)v.y : (i == 8 * J + j + 1 ? 1.0 : 0.0);
+          }
+      }
+      {
+        const int i = 8 * rA + g, j = 2 * t4;
+        const float* src = Hf + toff(rA, 0) + g * 8 + 2 * t4;
+#pragma unroll
+        for (int J = 0; J < NW; J++)
+          if (hasA && J <= rA) {
+            const float2 v = *reinterpret_cast<const float2*>(src + J * 64);
+            c0[TS - 1 - J] = (i < n && 8 * J + j < n) ? (double)v.x : (i == 8 * J + j ? 1.0 : 0.0);
+            c1[TS - 1 - J] = (i < n && 8 * J + j + 1 < n) ? (double)v.y : (i == 8 * J + j + 1 ? 1.0 : 0.0);
+          }
       }
       double* Pbuf = reinterpret_cast<double*>(smem + L.Pb);
-      double* Wscr = reinterpret_cast<double*>(smem + L.Ws) + wid * 64;
+      double* WsA = reinterpret_cast<double*>(smem + L.Ws) + wid * 128;  // -W of row rA / rB, fragment order
+      double* WsB = WsA + 64;
       bool bad = false;
-      // publish slot t's tile into panel kk's buffer if it belongs to it (after inverting the diagonal tile)
-      auto publish = [&](int t, int kk, double v0, double v1) {
-        const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
-        double* Pn = Pbuf + (kk & 1) * NT8 * 64;
-        if (J == kk) {        // column kk: P_I = A_I,kk  (I == kk: D, inverted first)
-          if (I == kk) bad |= tile_inverse_spd(v0, v1, lane);
-          *reinterpret_cast<double2*>(Pn + I * 64 + fp) = make_double2(v0, v1);
-        } else if (I == kk) {  // row kk, J < kk: P_J = A_kk,J transposed
-          Pn[J * 64 + frag_elem(2 * t4, g)] = v0;
-          Pn[J * 64 + frag_elem(2 * t4 + 1, g)] = v1;
-        }
-      };
-#pragma unroll
-      for (int t = 0; t < TS; t++)
-        if (t < ntl) publish(t, 0, c0[t], c1[t]);
+      // panel 0: column 0 of every row; tile (0,0) (warp 0, row rA = 0) inverted
+      if (hasB) *reinterpret_cast<double2*>(Pbuf + rB * 64 + fp) = make_double2(c0[0], c1[0]);
+      if (hasA) {
+        double d0 = c0[TS - 1], d1 = c1[TS - 1];
+        if (rA == 0) bad |= tile_inverse_spd(d0, d1, lane);
+        *reinterpret_cast<double2*>(Pbuf + rA * 64 + fp) = make_double2(d0, d1);
+      }
       __syncthreads();
       for (int k = 0; k < NT8; k++) {
-        const double* Pb = Pbuf + (k & 1) * NT8 * 64;
-        const double di0 = Pb[k * 64 + lane], di1 = Pb[k * 64 + 32 + lane];  // D^-1 operand fragments
-        // W_I = P_I D^-1 for the warp's own rows: accumulator layout (the new column-k tile) and, negated, as the
-        // A operand of the rank-8 updates
-        double WA0 = 0.0, WA1 = 0.0, WB0 = 0.0, WB1 = 0.0, wa0 = 0.0, wa1 = 0.0, wb0 = 0.0, wb1 = 0.0;
-        if (ntA && rA != k) {
-          dmma884(WA0, WA1, Pb[rA * 64 + lane], di0);
-          dmma884(WA0, WA1, Pb[rA * 64 + 32 + lane], di1);
-          *reinterpret_cast<double2*>(Wscr + fp) = make_double2(-WA0, -WA1);
+        const double* pbl = Pbuf + (k & 1) * NT8 * 64 + lane;  // operand fragments of panel tile I: pbl[I*64], pbl[I*64+32]
+        double* Pn = Pbuf + ((k + 1) & 1) * NT8 * 64;
+        const int kn = k + 1;  // the panel prepared for the next step (look-ahead)
+        const bool genA = hasA && rA != k, genB = hasB && rB != k;
+        double wA0 = 0.0, wA1 = 0.0, wB0 = 0.0, wB1 = 0.0;
+        {
+          // W_R = P_R D^-1 for the warp's rows, negated: stashed in fragment order (it is also the new column-k tile
+          // of the row) and reloaded as the A operand of the rank-8 updates A_RJ -= W_R P_J'
+          const double di0 = pbl[k * 64], di1 = pbl[k * 64 + 32];
+          if (genA) {
+            double W0 = 0.0, W1 = 0.0;
+            dmma884(W0, W1, pbl[rA * 64], di0);
+            dmma884(W0, W1, pbl[rA * 64 + 32], di1);
+            *reinterpret_cast<double2*>(WsA + fp) = make_double2(-W0, -W1);
+          }
+          if (genB) {
+            double W0 = 0.0, W1 = 0.0;
+            dmma884(W0, W1, pbl[rB * 64], di0);
+            dmma884(W0, W1, pbl[rB * 64 + 32], di1);
+            *reinterpret_cast<double2*>(WsB + fp) = make_double2(-W0, -W1);
+          }
           __syncwarp();
-          wa0 = Wscr[lane];
-          wa1 = Wscr[32 + lane];
-          __syncwarp();
+          if (genA) { wA0 = WsA[lane]; wA1 = WsA[32 + lane]; }
+          if (genB) { wB0 = WsB[lane]; wB1 = WsB[32 + lane]; }
         }
-        if (ntB && rB != k) {
-          dmma884(WB0, WB1, Pb[rB * 64 + lane], di0);
-          dmma884(WB0, WB1, Pb[rB * 64 + 32 + lane], di1);
-          *reinterpret_cast<double2*>(Wscr + fp) = make_double2(-WB0, -WB1);
-          __syncwarp();
-          wb0 = Wscr[lane];
-          wb1 = Wscr[32 + lane];
-          __syncwarp();
+        // look-ahead: the next diagonal tile first — its inversion is the longest chain of the step.  It is an ordinary
+        // tile in step k: rank-8 update (on a copy; the slot itself is updated below with the others), then its
+        // in-register inverse goes to the next panel.
+        if (kn < NT8 && ((hasA && rA == kn) || (hasB && rB == kn))) {
+          const bool inA = hasA && rA == kn;
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int J = 0; J < 2 * NW; J++)
+            if (J == kn) {
+              if (J < NW && inA) { d0 = c0[TS - 1 - (J < NW ? J : 0)]; d1 = c1[TS - 1 - (J < NW ? J : 0)]; }
+              else { d0 = c0[J]; d1 = c1[J]; }
+            }
+          dmma884(d0, d1, inA ? wA0 : wB0, pbl[kn * 64]);
+          dmma884(d0, d1, inA ? wA1 : wB1, pbl[kn * 64 + 32]);
+          bad |= tile_inverse_spd(d0, d1, lane);
+          *reinterpret_cast<double2*>(Pn + kn * 64 + fp) = make_double2(d0, d1);
         }
-        auto update = [&](int t, double& v0, double& v1) {
-          const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
-          if (I == k) {
-            if (J == k) {  // -D^-1
-              const double2 d = *reinterpret_cast<const double2*>(Pb + k * 64 + fp);
-              v0 = -d.x;
-              v1 = -d.y;
-            } else {       // D^-1 P_J'
+        {
+          // rank-8 updates of both rows (they share the P_J fragments); the column-k tile becomes W_R; the column-kn
+          // tile goes to the next panel
+          const int limA = genA ? rA : -1, limB = genB ? rB : -1;
+          const int pubA = (hasA && rA > kn) ? kn : -1, pubB = (hasB && rB > kn) ? kn : -1;
+          double* PnA = Pn + rA * 64 + fp;
+          double* PnB = Pn + rB * 64 + fp;
+#pragma unroll
+          for (int J = 0; J < 2 * NW; J++) {
+            if (J > limB && J > limA) break;
+            const double p0 = pbl[J * 64], p1 = pbl[J * 64 + 32];
+            if (J <= limB) {
+              if (J == k) {
+                const double2 d = *reinterpret_cast<const double2*>(WsB + fp);
+                c0[J] = -d.x;
+                c1[J] = -d.y;
+              } else {
+                dmma884(c0[J], c1[J], wB0, p0);
+                dmma884(c0[J], c1[J], wB1, p1);
+              }
+              if (J == pubB) *reinterpret_cast<double2*>(PnB) = make_double2(c0[J], c1[J]);
+            }
+            if (J < NW && J <= limA) {
+              constexpr int dummy = 0;
+              const int sa = TS - 1 - (J < NW ? J : dummy);
+              if (J == k) {
+                const double2 d = *reinterpret_cast<const double2*>(WsA + fp);
+                c0[sa] = -d.x;
+                c1[sa] = -d.y;
+              } else {
+                dmma884(c0[sa], c1[sa], wA0, p0);
+                dmma884(c0[sa], c1[sa], wA1, p1);
+              }
+              if (J == pubA) *reinterpret_cast<double2*>(PnA) = make_double2(c0[sa], c1[sa]);
+            }
+          }
+        }
+        // pivot row k (one warp of the CTA): A_kJ <- D^-1 P_J' for J < k, A_kk <- -D^-1
+        if ((hasB && rB == k) || (hasA && rA == k)) {
+          const bool inA = hasA && rA == k;
+          const double di0 = pbl[k * 64], di1 = pbl[k * 64 + 32];
+          const double2 dk = *reinterpret_cast<const double2*>(Pbuf + (k & 1) * NT8 * 64 + k * 64 + fp);
+#pragma unroll
+          for (int J = 0; J < 2 * NW; J++) {
+            if (J > k) break;
+            double v0 = -dk.x, v1 = -dk.y;
+            if (J < k) {
               v0 = 0.0;
               v1 = 0.0;
-              dmma884(v0, v1, di0, Pb[J * 64 + lane]);
-              dmma884(v0, v1, di1, Pb[J * 64 + 32 + lane]);
+              dmma884(v0, v1, di0, pbl[J * 64]);
+              dmma884(v0, v1, di1, pbl[J * 64 + 32]);
             }
-          } else if (J == k) {
-            v0 = (t < ntA) ? WA0 : WB0;
-            v1 = (t < ntA) ? WA1 : WB1;
-          } else {
-            dmma884(v0, v1, (t < ntA) ? wa0 : wb0, Pb[J * 64 + lane]);
-            dmma884(v0, v1, (t < ntA) ? wa1 : wb1, Pb[J * 64 + 32 + lane]);
+            if (J < NW && inA) { c0[TS - 1 - (J < NW ? J : 0)] = v0; c1[TS - 1 - (J < NW ? J : 0)] = v1; }
+            else { c0[J] = v0; c1[J] = v1; }
           }
-        };
-        // look-ahead: the diagonal tile of the next panel first (its inversion is the longest chain of the step)
-        const int kn = k + 1;
-        const int tdiag = (kn >= NT8) ? -1 : (rA == kn && ntA ? rA : (rB == kn && ntB ? ntA + rB : -1));
+        }
+        // row kn of the next panel, transposed: P_J = A_kn,J'
+        if (kn < NT8 && ((hasB && rB == kn) || (hasA && rA == kn))) {
+          const bool inA = hasA && rA == kn;
 #pragma unroll
-        for (int t = 0; t < TS; t++)
-          if (t == tdiag) {
-            update(t, c0[t], c1[t]);
-            publish(t, kn, c0[t], c1[t]);
+          for (int J = 0; J < 2 * NW; J++) {
+            if (J >= kn) break;
+            const double v0 = (J < NW && inA) ? c0[TS - 1 - (J < NW ? J : 0)] : c0[J];
+            const double v1 = (J < NW && inA) ? c1[TS - 1 - (J < NW ? J : 0)] : c1[J];
+            Pn[J * 64 + ft] = v0;
+            Pn[J * 64 + ft + 4] = v1;
           }
-#pragma unroll
-        for (int t = 0; t < TS; t++)
-          if (t < ntl && t != tdiag) {
-            update(t, c0[t], c1[t]);
-            if (kn < NT8) publish(t, kn, c0[t], c1[t]);
-          }
+        }
         __syncthreads();
       }
+      {
+        double* dstB = Hd + toff(rB, 0) + g * 8 + 2 * t4;
+        double* dstA = Hd + toff(rA, 0) + g * 8 + 2 * t4;
 #pragma unroll
-      for (int t = 0; t < TS; t++)
-        if (t < ntl) {
-          const int I = (t < ntA) ? rA : rB, J = (t < ntA) ? t : t - ntA;
-          *reinterpret_cast<double2*>(Hd + toff(I, J) + g * 8 + 2 * t4) = make_double2(-c0[t], -c1[t]);
+        for (int J = 0; J < 2 * NW; J++) {
+          if (hasB && J <= rB) *reinterpret_cast<double2*>(dstB + J * 64) = make_double2(-c0[J], -c1[J]);
+          if (J < NW && hasA && J <= rA)
+            *reinterpret_cast<double2*>(dstA + J * 64) = make_double2(-c0[TS - 1 - (J < NW ? J : 0)], -c1[TS - 1 - (J < NW ? J : 0)]);
         }
+      }
       if (__any_sync(0xffffffffu, bad) && lane == 0) flags[3] = ST_NOT_SPD;
       __syncthreads();
     }
@@ -1483,7 +1547,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
     // per-row constants: normal, right-hand side, slack at the unconstrained minimiser
     double ne[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    double se = 0.0;
+    double se = 0.0, rhs_e = 0.0;
     int ke = 0;
     bool act = false;
     if (iscon) {
@@ -1492,12 +1556,203 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const double* nn = nrm + ((blk_sl[ke] & 1) * 10 + te) * 6;
 #pragma unroll
       for (int c = 0; c < 6; c++) ne[c] = nn[c];
-      const double rhs_e = (te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ke] : 0.0);
+      rhs_e = (te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ke] : 0.0);
       se = dot6(ne, x0 + 6 * ke) - rhs_e;
     }
 
     int q = 0, iters = 0;
     int code = flags[3];
+
+    // ---- block start ----------------------------------------------------------------------------------------------
+    // Rounds of: take the most violated inactive row of EVERY block, solve on the enlarged working set (all multipliers
+    // at once through the explicit Schur complement S = A_W H^-1 A_W'), drop rows whose multiplier is not positive.
+    // What a round leaves — x minimises the QP on the rows of W held as equalities, all multipliers positive — is an
+    // S-pair, exactly the invariant of the dual iteration below, which therefore continues from it (and, when no row is
+    // violated any more, stops at its first selection).  A walking gait ends with about one active row per stance step:
+    // one to three rounds instead of ~N sequential working-set changes.  Any doubt (capacity, a non-positive pivot of S)
+    // falls back to the plain iteration.
+    {
+      float* sbuf = reinterpret_cast<float*>(gq);  // [m] slacks in float / membership marks (the gradient is spent)
+      int* newslot = reinterpret_cast<int*>(rr);   // slots of the entering rows (rr is not live yet)
+      for (int round = 0; code == ST_OK && round < ka.block_rounds; round++) {
+        if (iscon) sbuf[tid] = act ? 3.0e38f : (float)se;
+        __syncthreads();
+        if (wid == 0) {
+          const float tolf = (float)tol;
+          const unsigned lt = (1u << lane) - 1u;
+          int nadd = 0;
+          for (int kb0 = 0; kb0 < NB; kb0 += 32) {
+            const int kb = kb0 + lane;
+            int bi = -1;
+            if (kb < NB) {
+              float best = -tolf;
+              for (int t = 0; t < 10; t++) {
+                const float v = sbuf[kb * 10 + t];
+                if (v < best) { best = v; bi = t; }
+              }
+            }
+            const unsigned has = __ballot_sync(0xffffffffu, bi >= 0);
+            const int r = nadd + __popc(has & lt);
+            if (bi >= 0 && r <= qmax) newslot[r] = ws_pack(kb, (blk_sl[kb] & 1) * 10 + bi);
+            nadd += __popc(has);
+          }
+          __syncwarp();
+          int verdict = nadd;
+          if (nadd > 0 && q + nadd > qmax) verdict = -1;
+          if (verdict > 0 && lane == 0) {
+            int fn = 0, qh = flags[9];
+            for (int r = 0; r < nadd; r++) {  // the r-th entering row takes the r-th free slot
+              while ((amask[fn >> 5] >> (fn & 31)) & 1u) fn++;
+              wsl[fn] = newslot[r];
+              lam[fn] = 0.0;
+              amask[fn >> 5] |= 1u << (fn & 31);
+              newslot[r] = fn;
+              fn++;
+              qh = fn > qh ? fn : qh;
+            }
+            flags[9] = qh;
+          }
+          if (lane == 0) flags[4] = verdict;
+        }
+        __syncthreads();
+        const int nadd = flags[4];
+        if (nadd <= 0) break;  // 0: no violated row (the iteration below confirms and stops); -1: does not fit
+        const int qh = flags[9];
+        if (isvar) {
+          for (int r = 0; r < nadd; r++) {
+            const int sl = newslot[r], w = wsl[sl];
+            T[sl * n + vi] = hinv_dot6(Hd, vi, 6 * (w >> 8), nrm + (w & 0xff) * 6);
+          }
+        }
+        __syncthreads();
+        if (wid == 0) {
+          // S (packed lower rows; free slots: identity) and b_i = d_i - a_i' x0
+          for (int s2 = lane; s2 < qh; s2 += 32) {
+            const int rs = tri(s2);
+            const bool used = (amask[s2 >> 5] >> (s2 & 31)) & 1u;
+            double b = 0.0;
+            if (used) {
+              const int w = wsl[s2], ki = w >> 8, te = (w & 0xff) % 10;
+              const double* ni = nrm + (w & 0xff) * 6;
+              for (int j = 0; j <= s2; j++)
+                Sv[rs + j] = ((amask[j >> 5] >> (j & 31)) & 1u) ? dot6(ni, T + j * n + 6 * ki) : 0.0;
+              b = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
+            } else {
+              for (int j = 0; j < s2; j++) Sv[rs + j] = 0.0;
+              Sv[rs + s2] = 1.0;
+            }
+            dvs[s2] = b;
+          }
+          __syncwarp();
+          // in-place sweep of the packed symmetric matrix: leaves -S^-1 (lane = row, pivot column through rr)
+          bool sing = false;
+          for (int pv = 0; pv < qh; pv++) {
+            for (int s2 = lane; s2 < qh; s2 += 32) rr[s2] = (s2 >= pv) ? Sv[tri(s2) + pv] : Sv[tri(pv) + s2];
+            __syncwarp();
+            const double d = rr[pv];
+            sing |= !(d > 1e-13);
+            const double inv = fast_rcp(d);
+            for (int s2 = lane; s2 < qh; s2 += 32) {
+              const int rs = tri(s2);
+              const double ci = rr[s2] * inv;
+              if (s2 == pv) {
+                for (int j = 0; j < pv; j++) Sv[rs + j] = rr[j] * inv;
+                Sv[rs + pv] = -inv;
+              } else {
+                for (int j = 0; j <= s2; j++) Sv[rs + j] = (j == pv) ? ci : fma(-ci, rr[j], Sv[rs + j]);
+              }
+            }
+            __syncwarp();
+          }
+          for (int s2 = lane; s2 < qh; s2 += 32) {
+            const int rs = tri(s2);
+            for (int j = 0; j <= s2; j++) Sv[rs + j] = -Sv[rs + j];
+          }
+          __syncwarp();
+          // multipliers; rows whose multiplier is not positive leave again (one at a time, lowest slot first)
+          int ndrop = 0;
+          while (!sing) {
+            bool neg = false;
+            for (int s2 = lane; s2 < qh; s2 += 32) {
+              const int rs = tri(s2);
+              double acc = 0.0;
+              for (int j = 0; j < qh; j++) acc = fma((j <= s2) ? Sv[rs + j] : Sv[tri(j) + s2], dvs[j], acc);
+              const bool used = (amask[s2 >> 5] >> (s2 & 31)) & 1u;
+              lam[s2] = used ? acc : 0.0;
+              neg |= used && !(acc > 0.0);
+            }
+            int l1 = 0x7fffffff;
+            for (int s2 = lane; s2 < qh; s2 += 32)
+              if (((amask[s2 >> 5] >> (s2 & 31)) & 1u) && !(lam[s2] > 0.0)) { l1 = s2; break; }
+            l1 = __reduce_min_sync(0xffffffffu, l1);
+            if (l1 == 0x7fffffff) break;
+            __syncwarp();
+            for (int s2 = lane; s2 < qh; s2 += 32) rr[s2] = (s2 >= l1) ? Sv[tri(s2) + l1] : Sv[tri(l1) + s2];
+            __syncwarp();
+            const double ipv = fast_rcp(rr[l1]);
+            for (int s2 = lane; s2 < qh; s2 += 32) {
+              const int rs = tri(s2);
+              const double cs = rr[s2] * ipv;
+              for (int j = 0; j <= s2; j++) Sv[rs + j] = (j == l1 || s2 == l1) ? 0.0 : fma(-cs, rr[j], Sv[rs + j]);
+            }
+            if (lane == 0) {
+              const int w = wsl[l1];
+              sbuf[(w >> 8) * 10 + ((w & 0xff) % 10)] = 0.f;
+              amask[l1 >> 5] &= ~(1u << (l1 & 31));
+              lam[l1] = 0.0;
+              dvs[l1] = 0.0;
+            }
+            ndrop++;
+            __syncwarp();
+          }
+          // membership marks for the row threads, bookkeeping
+          int qn = 0;
+          for (int s2 = lane; s2 < qh; s2 += 32)
+            if ((amask[s2 >> 5] >> (s2 & 31)) & 1u) {
+              const int w = wsl[s2];
+              sbuf[(w >> 8) * 10 + ((w & 0xff) % 10)] = 3.9e38f;
+              qn++;
+            }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+          if (lane == 0) {
+            flags[10] = qn;
+            flags[11] = ndrop;
+            flags[4] = sing ? -2 : 0;
+            int fn = 0;
+            while (fn < qmax && ((amask[fn >> 5] >> (fn & 31)) & 1u)) fn++;
+            flags[7] = fn;
+          }
+        }
+        __syncthreads();
+        if (flags[4] == -2) {
+          // a pivot of S was not positive (dependent rows): forget the guess, start the plain iteration from x0
+          __syncthreads();
+          if (tid < 8) amask[tid] = 0u;
+          if (tid == 0) { flags[7] = 0; flags[8] = 0; flags[9] = 0; }
+          q = 0;
+          act = false;
+          if (isvar) xreg = x0[vi];
+          if (iscon) se = dot6(ne, x0 + 6 * ke) - rhs_e;
+          __syncthreads();
+          break;
+        }
+        q = flags[10];
+        iters += nadd + flags[11];
+        if (isvar) {
+          double acc = x0[vi];
+          for (int j = 0; j < qh; j++)
+            if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
+          xreg = acc;
+          zb[vi] = acc;
+        }
+        __syncthreads();
+        if (iscon) {
+          se = dot6(ne, zb + 6 * ke) - rhs_e;
+          act = sbuf[tid] > 3.5e38f;
+        }
+      }
+    }
     while (code == ST_OK) {
       // ---- most violated inactive row (selection in float, value in double) ----
       const float sf = (iscon && !act) ? (float)se : 3.0e38f;

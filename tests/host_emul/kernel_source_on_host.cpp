@@ -10,6 +10,7 @@
 //     with working-set-overflow escalation through the lists)
 // so that tests/test_kernel_source_on_host.py can hold the kernels' SOURCE to the oracle / to the reference's compiled
 // controller without a GPU.
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -216,6 +217,7 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.dt = dt;
     ka.f_max = f_max;
     ka.max_iter = max_iter;
+    ka.block_rounds = getenv("HMPC_BLOCK_ROUNDS") ? atoi(getenv("HMPC_BLOCK_ROUNDS")) : 4;  // hmpc_capi.cu's default
     ka.wrench = wrench;
     ka.wrench64 = wrench64;
     ka.status = status;

@@ -258,6 +258,21 @@ def _solve(L, records, N, dump=False, tau=True):
     return w.astype(np.float64), st, t.astype(np.float64), launched, d
 
 
+def _solve_plain(L, records, N):
+    """The same launch with the block start of the active-set stage switched off (HMPC_BLOCK_ROUNDS=0, read per call by
+    the emulation driver like hmpc_create reads it): the plain dual iteration from the unconstrained minimiser."""
+    old = os.environ.get("HMPC_BLOCK_ROUNDS")
+    os.environ["HMPC_BLOCK_ROUNDS"] = "0"
+    try:
+        w, st, _, _, _ = _solve(L, records, N, tau=False)
+    finally:
+        if old is None:
+            del os.environ["HMPC_BLOCK_ROUNDS"]
+        else:
+            os.environ["HMPC_BLOCK_ROUNDS"] = old
+    return w, st
+
+
 def test_solve_kernel_source_assembly_is_bit_exact(emul):
     """Stages 0-3 of the kernel source (TMA staging, SRBD linearisation, powers/Toeplitz blocks, prefix-chain Hessian, swing
     elimination), through the kernel's own assembly-dump mode, against the golden fp32 QP data — the bar the -m gpu suite
@@ -287,7 +302,11 @@ def test_solve_kernel_source_single_support_class(emul, oracle):
     assert (interface.status_code(st) == 0).all()
     assert rel_err(w, g["q_soln"][:B], 12).max() < 5e-6 and rel_err(w, g["q_soln"][:B]).max() < 5e-5
     assert (w[g["q_soln"][:B] == 0.0] == 0.0).all()
-    assert np.array_equal(interface.status_iters(st), g["info"][:B, 1])       # same number of working-set changes as qpOASES
+    # the plain dual iteration (block start off) makes the same number of working-set changes as qpOASES and lands on
+    # the same point as the block start
+    w1, st1 = _solve_plain(emul, g["records"][:B], 10)
+    assert np.array_equal(interface.status_iters(st1), g["info"][:B, 1]) and np.abs(w1 - w).max() < 1e-9 * np.abs(w).max()
+    assert np.array_equal(interface.status_nactive(st1), interface.status_nactive(st))
     # torque epilogue (row f-2) of the same launch
     _, inputs = scenarios.make_batch(2, 64, horizon=10)
     rB = np.array([b["rBody"] for b in inputs[:B]]); ql = np.array([b["q_leg"] for b in inputs[:B]])
@@ -324,7 +343,8 @@ def test_solve_kernel_source_runtime_horizon(emul, name, B):
     assert (interface.status_code(st) == 0).all()
     assert rel_err(w, g["q_soln"][:B], 12).max() < 5e-6 and rel_err(w, g["q_soln"][:B]).max() < 5e-5
     assert (w[g["q_soln"][:B] == 0.0] == 0.0).all()
-    assert np.array_equal(interface.status_iters(st), g["info"][:B, 1])
+    w1, st1 = _solve_plain(emul, g["records"][:B], N)
+    assert np.array_equal(interface.status_iters(st1), g["info"][:B, 1]) and np.abs(w1 - w).max() < 1e-9 * np.abs(w).max()
 
 
 def test_solve_kernel_source_escalates_a_degenerate_optimum(emul):
