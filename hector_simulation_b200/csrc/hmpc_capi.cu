@@ -543,7 +543,7 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
 }
 }  // namespace
 
-// profiling hook: device buffer [batch][8] of clock64() stage timestamps, or NULL to switch off
+// profiling hook: device buffer [batch][32] of clock64() stage timestamps, or NULL to switch off
 HMPC_EXTERNC void hmpc_debug_set_clock_buffer(long long* d_buf) { g_dbg_clk = d_buf; }
 
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls + 1 : 0; }

@@ -72,13 +72,16 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.T = s;    s += ns * n * 8;                      // H^-1 a_j of every working-set slot
   L.Sv = s;   s += ns * (ns + 1) / 2 * 8;           // (A_W H^-1 A_W')^-1, packed lower rows
   L.lam = s;  s += ns * 8;
-  L.dv = s;   s += ns * 8;
+  L.dv = s;   s += 2 * (ns + 2) * 8;                // step-direction scratch / double-buffered pivot column of the block start
   L.rr = s;   s += ns * 8;
   L.wsl = s;  s += align16(ns * 4);
   L.zb = s;   s += n * 8;
-  int w = L.uni;  // sweep view
+  // sweep view: the tiles live in registers during the sweep, so its buffers take H's place when they fit there
+  const int sweep_bytes = 2 * nt8 * 64 * 8 + nwarps * 2 * 64 * 8;
+  int w = (sweep_bytes <= ntile * 64 * 8) ? L.H : L.uni;
   L.Pb = w;   w += 2 * nt8 * 64 * 8;                // pivot panel, double-buffered
   L.Ws = w;   w += nwarps * 2 * 64 * 8;             // per warp: -W of its two tile rows, fragment order
+  if (sweep_bytes <= ntile * 64 * 8) w = L.uni;
   int a = L.uni;  // assembly view
   L.rec = a;  a += align16(rec_stride);
   L.x0f = a;  a += 16 * 4;
@@ -99,20 +102,20 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
 __host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12 * N) * 4 + 2 * N); }
 
 // size classes: class 0 holds at most N blocks of 6 variables, class 1 up to 2N.  Working-set capacity: N + 5 rows for
-// class 0 (a walking gait ends with about one active row per stance step; 15 at N = 10), 32 for class 1; an instance that needs more
+// class 0 (a walking gait ends with about one active row per stance step; 15 at N = 10), 31 for class 1; an instance that needs more
 // escalates to the next class (class 2 = class 1's size with as many slots as shared memory holds).
 __host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
 __host__ __device__ constexpr int class_qmax(int N, int cls)
 {
   const int n = 6 * class_nb_cap(N, cls);
-  const int q = cls == 0 ? N + 5 : 32;
+  const int q = cls == 0 ? N + 5 : (N <= 10 ? 31 : 36);  // (the block start handles up to 31 rows: one mask word)
   return q < n ? q : n;
 }
-// warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (10 per block)
+// warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (3 blocks of 10 per warp)
 __host__ __device__ constexpr int class_warps(int N, int cls)
 {
   const int nb = class_nb_cap(N, cls), n = 6 * nb, nt8 = (n + 7) / 8;
-  const int w_sweep = (nt8 + 1) / 2, w_rows = (10 * nb + 31) / 32;
+  const int w_sweep = (nt8 + 1) / 2, w_rows = (nb + 2) / 3;  // three blocks of ten rows per warp
   return w_sweep > w_rows ? w_sweep : w_rows;
 }
 __host__ __device__ constexpr Layout class_layout(int N, int cls, int nwarps)
@@ -149,7 +152,7 @@ struct KernelArgs {
   float* dbg_lb;                 // [batch][16N]
   float* dbg_ub;                 // [batch][16N]
   float* tau;                    // [batch][10] joint torques of the first-step wrench (row f-2), or nullptr
-  long long* dbg_clk;            // [batch][8] stage timestamps (clock64), profiling hook; null in production
+  long long* dbg_clk;            // [batch][32] stage timestamps (clock64) of thread 0, profiling hook; null in production
   Layout L;
 };
 
@@ -935,6 +938,7 @@ __global__ void hmpc_classify_kernel(const unsigned char* records, int rec_strid
 // NF > 0 fixes the horizon at compile time (layout offsets and loop bounds fold), NF == 0 reads it from
 // the arguments; CLS = size class (capacity N or 2N blocks of 6 variables).
 // ------------------------------------------------------------------------------------------------
+#define HMPC_STAMP(i) do { if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 32 + (i)] = clock64(); } while (0)
 constexpr int WS_STATE_INTS = 40;  // persistent working set of one robot: [0] = count, then (step*2+leg) << 8 | normal index
 
 template <int NT, int MINB, int NF, int CLS>
@@ -1005,7 +1009,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
 
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int inst = ka.list ? ka.list[idx] : idx;
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 0] = clock64();
+    HMPC_STAMP(0);
     // ---------------- stage 0: record -> shared memory (TMA bulk copy) ----------------
     const bool raw = ka.raw_records != nullptr;
     if (raw) {
@@ -1119,7 +1123,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       nrm[e] = (double)(neg ? -v : v);
     }
 
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 1] = clock64();
+    HMPC_STAMP(1);
     // ---------------- stage 2: powers of Acd, Toeplitz blocks, d = A_qp x0 - X_d ----------------
     // Acd = I + dt*A has the SRBD pattern (SolverMPC.cpp:312-318): Rb block (rows 0-2, cols 6-8), dt on
     // (3+c, 9+c) and -dt on (11,12).  Its powers P_k therefore differ from the identity in 14 entries only,
@@ -1181,7 +1185,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
     __syncthreads();
 
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 2] = clock64();
+    HMPC_STAMP(2);
     // ---------------- stage 3: Hessian prefix chains (one 1x6 leg tile per item) + gradient ----------------
     if (dump) {
       float* oF = ka.dbg_F + (size_t)inst * 192;
@@ -1293,7 +1297,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           }
         }
       }
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 7] = clock64();
+    HMPC_STAMP(7);
       // gradient: g(a,ii) = sum_{s>=a} sum_r (T_{s-a}[r][ii]*2) * d_s[r]
       for (int e = tid; e < N * 12; e += NT) {
         const int a = e / 12, ii = e % 12, li = leg_of(ii);
@@ -1336,7 +1340,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       continue;
     }
 
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 3] = clock64();
+    HMPC_STAMP(3);
     // ---------------- stage 4: blocked sweep inversion on the fp64 tensor pipe ----------------
     // The symmetric matrix is cut into 8x8 tiles (rows/columns beyond n: identity).  Sweeping the diagonal tile k
     //   A_kk <- -D^-1,  A_ik <- A_ik D^-1,  A_kj <- D^-1 A_kj,  A_ij <- A_ij - A_ik D^-1 A_kj        (D = A_kk)
@@ -1383,6 +1387,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       double* WsA = reinterpret_cast<double*>(smem + L.Ws) + wid * 128;  // -W of row rA / rB, fragment order
       double* WsB = WsA + 64;
       bool bad = false;
+      __syncthreads();  // the panel buffers may overlay the float32 tiles just read
       // panel 0: column 0 of every row; tile (0,0) (warp 0, row rA = 0) inverted
       if (hasB) *reinterpret_cast<double2*>(Pbuf + rB * 64 + fp) = make_double2(c0[0], c1[0]);
       if (hasA) {
@@ -1417,6 +1422,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           if (genA) { wA0 = WsA[lane]; wA1 = WsA[32 + lane]; }
           if (genB) { wB0 = WsB[lane]; wB1 = WsB[32 + lane]; }
         }
+        if (k == 1) HMPC_STAMP(20);
         // look-ahead: the next diagonal tile first — its inversion is the longest chain of the step.  It is an ordinary
         // tile in step k: rank-8 update (on a copy; the slot itself is updated below with the others), then its
         // in-register inverse goes to the next panel.
@@ -1434,6 +1440,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           bad |= tile_inverse_spd(d0, d1, lane);
           *reinterpret_cast<double2*>(Pn + kn * 64 + fp) = make_double2(d0, d1);
         }
+        if (k == 1) HMPC_STAMP(21);
         {
           // rank-8 updates of both rows (they share the P_J fragments); the column-k tile becomes W_R; the column-kn
           // tile goes to the next panel
@@ -1471,6 +1478,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             }
           }
         }
+        if (k == 1) HMPC_STAMP(22);
         // pivot row k (one warp of the CTA): A_kJ <- D^-1 P_J' for J < k, A_kk <- -D^-1
         if ((hasB && rB == k) || (hasA && rA == k)) {
           const bool inA = hasA && rA == k;
@@ -1502,7 +1510,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             Pn[J * 64 + ft + 4] = v1;
           }
         }
+        if (k == 1) HMPC_STAMP(23);
         __syncthreads();
+        if (k == 1) HMPC_STAMP(24);
+        if (k == 0) HMPC_STAMP(19);
       }
       {
         double* dstB = Hd + toff(rB, 0) + g * 8 + 2 * t4;
@@ -1518,14 +1529,17 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       __syncthreads();
     }
 
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 4] = clock64();
+    HMPC_STAMP(4);
     // ---------------- stage 5: dual active-set iterations (Goldfarb-Idnani) ----------------
     // Thread e < m owns constraint row e (slack s_e in a register), thread NT-1-i owns variable i.  A working-set slot
     // keeps t_j = H^-1 a_j; the Schur complement inverse (A_W H^-1 A_W')^-1 is held explicitly (rank-1 up/downdates).
     // One working-set change = selection | t_p = H^-1 a_p | warp 0: step direction, ratio test, update | x, slacks:
     // four barriers.
+    // rows: three blocks (30 lanes) per warp, so that a block's ten rows share a warp; row id = 10 * block + type
     const int vi = NT - 1 - tid;
-    const bool isvar = vi < n, iscon = tid < m;
+    const int ke = 3 * wid + lane / 10;
+    const bool isvar = vi < n, iscon = lane < 30 && ke < NB;
+    const int erow = iscon ? 10 * ke + (lane - 10 * (lane / 10)) : 0x7fffffff;
     double xreg = 0.0;
     if (isvar) {
       xreg = -hinv_rowdot(Hd, vi, NT8, gq);
@@ -1537,7 +1551,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       if (lane == 0) redk[16 + wid] = kmax;  // upper half: the selection below reuses redk[0..NW) without a barrier in between
     }
     if (tid < 8) amask[tid] = 0u;
-    if (tid == 0) { flags[7] = 0; flags[8] = 0; flags[9] = 0; }
+    if (tid == 0) { flags[7] = 0; flags[8] = 0; flags[9] = 0; flags[11] = 0; }
     __syncthreads();
     double tol;
     {
@@ -1548,12 +1562,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // per-row constants: normal, right-hand side, slack at the unconstrained minimiser
     double ne[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double se = 0.0, rhs_e = 0.0;
-    int ke = 0;
+    int nie = 0, myslot = -1;
     bool act = false;
     if (iscon) {
-      ke = tid / 10;
-      const int te = tid - 10 * ke;
-      const double* nn = nrm + ((blk_sl[ke] & 1) * 10 + te) * 6;
+      const int te = lane - 10 * (lane / 10);
+      nie = (blk_sl[ke] & 1) * 10 + te;
+      const double* nn = nrm + nie * 6;
 #pragma unroll
       for (int c = 0; c < 6; c++) ne[c] = nn[c];
       rhs_e = (te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ke] : 0.0);
@@ -1569,55 +1583,46 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // What a round leaves — x minimises the QP on the rows of W held as equalities, all multipliers positive — is an
     // S-pair, exactly the invariant of the dual iteration below, which therefore continues from it (and, when no row is
     // violated any more, stops at its first selection).  A walking gait ends with about one active row per stance step:
-    // one to three rounds instead of ~N sequential working-set changes.  Any doubt (capacity, a non-positive pivot of S)
-    // falls back to the plain iteration.
-    {
-      float* sbuf = reinterpret_cast<float*>(gq);  // [m] slacks in float / membership marks (the gradient is spent)
-      int* newslot = reinterpret_cast<int*>(rr);   // slots of the entering rows (rr is not live yet)
+    // one to three rounds instead of ~N sequential working-set changes.  Every thread works in every phase: the block
+    // minimum is a masked REDUX over the block's ten lanes, each entry of [S | b] lives in one thread's register during a
+    // Gauss-Jordan sweep with one barrier per pivot.  Any doubt (capacity, a non-positive pivot) falls back to the plain
+    // iteration from the unconstrained minimiser.
+    if (qmax <= 31 && (qmax + 1) * (qmax + 4) / 2 <= 3 * NT) {
+      int* newslot = reinterpret_cast<int*>(rr);       // [nadd] slots of the entering rows (rr is not live yet)
+      double* colb = dvs;                              // [2][qmax + 3] pivot column, b_p and 1/d, double-buffered
+      const int cst = qmax + 3;
       for (int round = 0; code == ST_OK && round < ka.block_rounds; round++) {
-        if (iscon) sbuf[tid] = act ? 3.0e38f : (float)se;
+        if (round == 0) HMPC_STAMP(8);
+        // most violated inactive row of every block
+        const unsigned gm = (lane < 30) ? (0x3ffu << (10 * (lane / 10))) : (1u << lane);
+        const float sf = (iscon && !act) ? (float)se : 3.0e38f;
+        const unsigned key = fkey(sf);
+        const unsigned kmin = __reduce_min_sync(gm, key);
+        const unsigned tie = __ballot_sync(0xffffffffu, key == kmin) & gm;
+        const bool cand = iscon && !act && se < -tol && key == kmin && (__ffs(tie) - 1) == lane;
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) redi[wid] = __popc(cm);
         __syncthreads();
-        if (wid == 0) {
-          const float tolf = (float)tol;
-          const unsigned lt = (1u << lane) - 1u;
-          int nadd = 0;
-          for (int kb0 = 0; kb0 < NB; kb0 += 32) {
-            const int kb = kb0 + lane;
-            int bi = -1;
-            if (kb < NB) {
-              float best = -tolf;
-              for (int t = 0; t < 10; t++) {
-                const float v = sbuf[kb * 10 + t];
-                if (v < best) { best = v; bi = t; }
-              }
-            }
-            const unsigned has = __ballot_sync(0xffffffffu, bi >= 0);
-            const int r = nadd + __popc(has & lt);
-            if (bi >= 0 && r <= qmax) newslot[r] = ws_pack(kb, (blk_sl[kb] & 1) * 10 + bi);
-            nadd += __popc(has);
-          }
-          __syncwarp();
-          int verdict = nadd;
-          if (nadd > 0 && q + nadd > qmax) verdict = -1;
-          if (verdict > 0 && lane == 0) {
-            int fn = 0, qh = flags[9];
-            for (int r = 0; r < nadd; r++) {  // the r-th entering row takes the r-th free slot
-              while ((amask[fn >> 5] >> (fn & 31)) & 1u) fn++;
-              wsl[fn] = newslot[r];
-              lam[fn] = 0.0;
-              amask[fn >> 5] |= 1u << (fn & 31);
-              newslot[r] = fn;
-              fn++;
-              qh = fn > qh ? fn : qh;
-            }
-            flags[9] = qh;
-          }
-          if (lane == 0) flags[4] = verdict;
+        int nadd = 0, rank = __popc(cm & ((1u << lane) - 1u));
+        for (int w = 0; w < NW; w++) {
+          const int c = redi[w];
+          nadd += c;
+          if (w < wid) rank += c;
+        }
+        const unsigned am0 = amask[0];
+        __syncthreads();  // everybody has read the counts and the slot mask
+        if (nadd == 0 || q + nadd > qmax) break;  // no violated row (the iteration below confirms and stops) / no room
+        if (cand) {  // the rank-th entering row takes the rank-th free slot
+          unsigned fm = ~am0;
+          for (int r = 0; r < rank; r++) fm &= fm - 1;
+          const int sl = __ffs(fm) - 1;
+          myslot = sl;
+          wsl[sl] = ws_pack(ke, nie);
+          newslot[rank] = sl;
+          atomicOr(&amask[0], 1u << sl);
         }
         __syncthreads();
-        const int nadd = flags[4];
-        if (nadd <= 0) break;  // 0: no violated row (the iteration below confirms and stops); -1: does not fit
-        const int qh = flags[9];
+        if (round == 0) HMPC_STAMP(9);
         if (isvar) {
           for (int r = 0; r < nadd; r++) {
             const int sl = newslot[r], w = wsl[sl];
@@ -1625,141 +1630,156 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           }
         }
         __syncthreads();
-        if (wid == 0) {
-          // S (packed lower rows; free slots: identity) and b_i = d_i - a_i' x0
-          for (int s2 = lane; s2 < qh; s2 += 32) {
-            const int rs = tri(s2);
-            const bool used = (amask[s2 >> 5] >> (s2 & 31)) & 1u;
-            double b = 0.0;
-            if (used) {
-              const int w = wsl[s2], ki = w >> 8, te = (w & 0xff) % 10;
-              const double* ni = nrm + (w & 0xff) * 6;
-              for (int j = 0; j <= s2; j++)
-                Sv[rs + j] = ((amask[j >> 5] >> (j & 31)) & 1u) ? dot6(ni, T + j * n + 6 * ki) : 0.0;
-              b = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
+        if (round == 0) HMPC_STAMP(10);
+        // solve S lam = b on the working set; rows with a non-positive multiplier leave and the solve is repeated
+        int verdict = 0;  // 0: all multipliers positive, 1: gave up
+        for (int attempt = 0; attempt < 4; attempt++) {
+          const unsigned am = amask[0];
+          const int qh = 32 - __clz(am);
+          const int ntri = tri(qh), nent = ntri + qh;
+          // entries of [S | b]: e2 < ntri -> (i, j), j <= i, row-packed; then b_i
+          double av[3] = {0.0, 0.0, 0.0};
+          int ei[3] = {0, 0, 0}, ej[3] = {0, 0, 0};
+#pragma unroll
+          for (int u = 0; u < 3; u++) {
+            const int e2 = tid + u * NT;
+            if (e2 >= nent) { ei[u] = -1; continue; }
+            int i, j;
+            if (e2 < ntri) {
+              i = (int)((sqrtf(8.f * (float)e2 + 1.f) - 1.f) * 0.5f);
+              while (tri(i + 1) <= e2) i++;
+              while (tri(i) > e2) i--;
+              j = e2 - tri(i);
             } else {
-              for (int j = 0; j < s2; j++) Sv[rs + j] = 0.0;
-              Sv[rs + s2] = 1.0;
+              i = e2 - ntri;
+              j = qh;  // the right-hand side column
             }
-            dvs[s2] = b;
-          }
-          __syncwarp();
-          // in-place sweep of the packed symmetric matrix: leaves -S^-1 (lane = row, pivot column through rr)
-          bool sing = false;
-          for (int pv = 0; pv < qh; pv++) {
-            for (int s2 = lane; s2 < qh; s2 += 32) rr[s2] = (s2 >= pv) ? Sv[tri(s2) + pv] : Sv[tri(pv) + s2];
-            __syncwarp();
-            const double d = rr[pv];
-            sing |= !(d > 1e-13);
-            const double inv = fast_rcp(d);
-            for (int s2 = lane; s2 < qh; s2 += 32) {
-              const int rs = tri(s2);
-              const double ci = rr[s2] * inv;
-              if (s2 == pv) {
-                for (int j = 0; j < pv; j++) Sv[rs + j] = rr[j] * inv;
-                Sv[rs + pv] = -inv;
+            ei[u] = i;
+            ej[u] = j;
+            const bool ui = (am >> i) & 1u, uj = (j == qh) || ((am >> j) & 1u);
+            double v = (i == j) ? 1.0 : 0.0;  // free slots: identity rows
+            if (ui && uj) {
+              const int w = wsl[i], ki = w >> 8;
+              const double* ni = nrm + (w & 0xff) * 6;
+              if (j == qh) {
+                const int te = (w & 0xff) % 10;
+                v = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
               } else {
-                for (int j = 0; j <= s2; j++) Sv[rs + j] = (j == pv) ? ci : fma(-ci, rr[j], Sv[rs + j]);
+                v = dot6(ni, T + j * n + 6 * ki);
+              }
+            } else if (ui != uj || j == qh) {
+              v = 0.0;
+            }
+            av[u] = v;
+          }
+          // publish pivot column 0
+          bool sing = false;
+#pragma unroll
+          for (int u = 0; u < 3; u++) {
+            if (ei[u] < 0) continue;
+            if (ej[u] == 0) colb[ei[u]] = av[u];                      // S(i,0)
+            if (ei[u] == 0 && ej[u] == qh) colb[qh] = av[u];          // b_0
+            if (ei[u] == 0 && ej[u] == 0) { colb[qh + 1] = fast_rcp(av[u]); sing |= !(av[u] > 1e-13); }
+          }
+          if (round == 0 && attempt == 0) HMPC_STAMP(11);
+          __syncthreads();
+          for (int pv = 0; pv < qh; pv++) {
+            const double* cc = colb + (pv & 1) * cst;
+            double* cn = colb + ((pv + 1) & 1) * cst;
+            const double inv = cc[qh + 1];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int i = ei[u], j = ej[u];
+              if (i < 0) continue;
+              const double ci = cc[i], cj = cc[j];  // cc[qh] = b_pv serves the right-hand side column
+              double a = av[u];
+              if (i == pv) a = (j == pv) ? -inv : cj * inv;
+              else if (j == pv) a = ci * inv;
+              else a = fma(-ci * inv, cj, a);
+              av[u] = a;
+              // next pivot's column: S(.,pv+1) = row pv+1 left of the diagonal and column pv+1 below it
+              const int pn = pv + 1;
+              if (pn < qh) {
+                if (j == pn) cn[i] = a;
+                else if (i == pn && j < pn) cn[j] = a;
+                else if (i == pn && j == qh) cn[qh] = a;
+                if (i == pn && j == pn) { cn[qh + 1] = fast_rcp(a); sing |= !(a > 1e-13); }
               }
             }
-            __syncwarp();
+            __syncthreads();
           }
-          for (int s2 = lane; s2 < qh; s2 += 32) {
-            const int rs = tri(s2);
-            for (int j = 0; j <= s2; j++) Sv[rs + j] = -Sv[rs + j];
-          }
-          __syncwarp();
-          // multipliers; rows whose multiplier is not positive leave again (one at a time, lowest slot first)
-          int ndrop = 0;
-          while (!sing) {
-            bool neg = false;
-            for (int s2 = lane; s2 < qh; s2 += 32) {
-              const int rs = tri(s2);
-              double acc = 0.0;
-              for (int j = 0; j < qh; j++) acc = fma((j <= s2) ? Sv[rs + j] : Sv[tri(j) + s2], dvs[j], acc);
-              const bool used = (amask[s2 >> 5] >> (s2 & 31)) & 1u;
-              lam[s2] = used ? acc : 0.0;
-              neg |= used && !(acc > 0.0);
-            }
-            int l1 = 0x7fffffff;
-            for (int s2 = lane; s2 < qh; s2 += 32)
-              if (((amask[s2 >> 5] >> (s2 & 31)) & 1u) && !(lam[s2] > 0.0)) { l1 = s2; break; }
-            l1 = __reduce_min_sync(0xffffffffu, l1);
-            if (l1 == 0x7fffffff) break;
-            __syncwarp();
-            for (int s2 = lane; s2 < qh; s2 += 32) rr[s2] = (s2 >= l1) ? Sv[tri(s2) + l1] : Sv[tri(l1) + s2];
-            __syncwarp();
-            const double ipv = fast_rcp(rr[l1]);
-            for (int s2 = lane; s2 < qh; s2 += 32) {
-              const int rs = tri(s2);
-              const double cs = rr[s2] * ipv;
-              for (int j = 0; j <= s2; j++) Sv[rs + j] = (j == l1 || s2 == l1) ? 0.0 : fma(-cs, rr[j], Sv[rs + j]);
-            }
-            if (lane == 0) {
-              const int w = wsl[l1];
-              sbuf[(w >> 8) * 10 + ((w & 0xff) % 10)] = 0.f;
-              amask[l1 >> 5] &= ~(1u << (l1 & 31));
-              lam[l1] = 0.0;
-              dvs[l1] = 0.0;
-            }
-            ndrop++;
-            __syncwarp();
-          }
-          // membership marks for the row threads, bookkeeping
-          int qn = 0;
-          for (int s2 = lane; s2 < qh; s2 += 32)
-            if ((amask[s2 >> 5] >> (s2 & 31)) & 1u) {
-              const int w = wsl[s2];
-              sbuf[(w >> 8) * 10 + ((w & 0xff) % 10)] = 3.9e38f;
-              qn++;
-            }
+          if (round == 0 && attempt == 0) HMPC_STAMP(12);
+          // -S^-1 and lam = S^-1 b are in the registers: store them for the dual iteration / the x update
+          bool neg = false;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
-          if (lane == 0) {
-            flags[10] = qn;
-            flags[11] = ndrop;
-            flags[4] = sing ? -2 : 0;
-            int fn = 0;
-            while (fn < qmax && ((amask[fn >> 5] >> (fn & 31)) & 1u)) fn++;
-            flags[7] = fn;
+          for (int u = 0; u < 3; u++) {
+            const int i = ei[u], j = ej[u];
+            if (i < 0) continue;
+            if (j == qh) {
+              const bool used = (am >> i) & 1u;
+              lam[i] = used ? av[u] : 0.0;
+              neg |= used && !(av[u] > 0.0);
+            } else {
+              Sv[tri(i) + j] = -av[u];
+            }
           }
-        }
-        __syncthreads();
-        if (flags[4] == -2) {
-          // a pivot of S was not positive (dependent rows): forget the guess, start the plain iteration from x0
+          const int anyneg = __syncthreads_or((int)neg | ((int)sing << 1));
+          if (anyneg & 2) { verdict = 1; break; }
+          if (!(anyneg & 1)) break;
+          if (attempt == 3) { verdict = 1; break; }
+          // drop the rows with non-positive multipliers (their owner threads clear the slot) and solve again
+          if (myslot >= 0 && !(lam[myslot] > 0.0)) {
+            atomicAnd(&amask[0], ~(1u << myslot));
+            myslot = -1;
+            act = false;
+            atomicAdd(&flags[11], 1);
+          }
           __syncthreads();
-          if (tid < 8) amask[tid] = 0u;
-          if (tid == 0) { flags[7] = 0; flags[8] = 0; flags[9] = 0; }
+        }
+        if (round == 0) HMPC_STAMP(13);
+        if (verdict != 0 || amask[0] == 0u) {
+          // dependent rows / no progress: forget the guess, the plain iteration starts from x0
+          __syncthreads();
+          if (tid == 0) { amask[0] = 0u; flags[7] = 0; flags[8] = 0; flags[9] = 0; }
           q = 0;
           act = false;
+          myslot = -1;
           if (isvar) xreg = x0[vi];
           if (iscon) se = dot6(ne, x0 + 6 * ke) - rhs_e;
           __syncthreads();
           break;
         }
-        q = flags[10];
-        iters += nadd + flags[11];
+        const unsigned amf = amask[0];
+        const int qhf2 = 32 - __clz(amf);
+        if (iscon) act = myslot >= 0;
+        q = __popc(amf);
+        iters += nadd;
+        if (tid == 0) {
+          flags[9] = qhf2;
+          flags[7] = __ffs(~amf) - 1;
+        }
         if (isvar) {
           double acc = x0[vi];
-          for (int j = 0; j < qh; j++)
-            if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
+          for (int j = 0; j < qhf2; j++)
+            if ((amf >> j) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
           xreg = acc;
           zb[vi] = acc;
         }
         __syncthreads();
-        if (iscon) {
-          se = dot6(ne, zb + 6 * ke) - rhs_e;
-          act = sbuf[tid] > 3.5e38f;
-        }
+        if (round == 0) HMPC_STAMP(14);
+        if (iscon) se = dot6(ne, zb + 6 * ke) - rhs_e;
+        if (round == 0) HMPC_STAMP(15);
       }
+      iters += flags[11];
     }
+    HMPC_STAMP(16);
     while (code == ST_OK) {
       // ---- most violated inactive row (selection in float, value in double) ----
       const float sf = (iscon && !act) ? (float)se : 3.0e38f;
       const unsigned key = fkey(sf);
       const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-      const int imin = __reduce_min_sync(0xffffffffu, key == kmin ? tid : 0x7fffffff);
-      if (tid == imin) redv[wid] = se;
+      const int imin = __reduce_min_sync(0xffffffffu, key == kmin ? erow : 0x7fffffff);
+      if (iscon && erow == imin) redv[wid] = se;
       if (lane == 0) { redk[wid] = kmin; redi[wid] = imin; }
       __syncthreads();
       unsigned kb = redk[0];
@@ -1906,20 +1926,20 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         __syncthreads();
         if (iscon && t != 0.0) se = fma(t, dot6(ne, zb + 6 * ke), se);
         if (decision == 0) {
-          if (tid == p) act = true;
+          if (erow == p) { act = true; myslot = f; }
           q++;
           break;
         }
         // partial step: the blocking row left the working set; warp 0 needs the refreshed slack of p
-        if (tid == flags[5]) act = false;
-        if (tid == p) dsc[1] = se;
+        if (erow == flags[5]) { act = false; myslot = -1; }
+        if (erow == p) dsc[1] = se;
         q--;
         __syncthreads();
         sp = dsc[1];
       }
     }
 
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 5] = clock64();
+    HMPC_STAMP(5);
     // polish: x from scratch with the final multipliers, x = x0 + sum_j lam_j H^-1 a_j
     __syncthreads();
     const int qhf = flags[9];
@@ -1998,7 +2018,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       }
       ka.tau[(size_t)inst * 10 + tid] = (float)leg_torque(q5, leg, j, fw);
     }
-    if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 8 + 6] = clock64();
+    HMPC_STAMP(6);
     if (tid == 0) {
       if (code == ST_WS_CAP && ka.esc_list) {  // hand over to the next class (larger working-set capacity)
         const int slot = atomicAdd(&ka.counts[ka.cls + 1], 1);

@@ -86,6 +86,8 @@ struct Warp {
 struct Cta {
   Barrier bar;
   Warp warps[32];
+  int orflag[2] = {0, 0};
+  unsigned orphase = 0;
 };
 [[noreturn]] inline void die(const char* what)
 {
@@ -105,6 +107,17 @@ inline void __syncthreads()
 {
   if (!hmpc_emul_cta) hmpc_emul::die("__syncthreads outside an emulated CTA");
   hmpc_emul_cta->bar.wait();
+}
+inline int __syncthreads_or(int pred)
+{
+  if (!hmpc_emul_cta) hmpc_emul::die("__syncthreads_or outside an emulated CTA");
+  __atomic_fetch_or(&hmpc_emul_cta->orflag[hmpc_emul_cta->orphase & 1], pred, __ATOMIC_SEQ_CST);
+  hmpc_emul_cta->bar.wait();
+  const int r = __atomic_load_n(&hmpc_emul_cta->orflag[hmpc_emul_cta->orphase & 1], __ATOMIC_SEQ_CST);
+  hmpc_emul_cta->bar.wait();
+  if (threadIdx.x == 0) { hmpc_emul_cta->orflag[hmpc_emul_cta->orphase & 1] = 0; hmpc_emul_cta->orphase++; }
+  hmpc_emul_cta->bar.wait();
+  return r;
 }
 inline void __syncwarp(unsigned mask = 0xffffffffu)
 {
@@ -153,11 +166,15 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
     return m;
   });
 }
+// group masks are supported for the unsigned minimum: every lane of the warp executes the call (convergent code), each
+// with the mask of its own group, and reduces over the lanes its mask names
 inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
 {
-  return hmpc_emul_exchange(mask, v, [&](const unsigned long long* s) {
-    unsigned m = (unsigned)s[0];
-    for (int l = 1; l < 32; l++) m = (unsigned)s[l] < m ? (unsigned)s[l] : m;
+  if (!((mask >> (threadIdx.x & 31)) & 1u)) hmpc_emul::die("__reduce_min_sync: the caller is not in its mask");
+  return hmpc_emul_exchange(0xffffffffu, v, [&](const unsigned long long* s) {
+    unsigned m = 0xffffffffu;
+    for (int l = 0; l < 32; l++)
+      if ((mask >> l) & 1u) m = (unsigned)s[l] < m ? (unsigned)s[l] : m;
     return m;
   });
 }
@@ -207,6 +224,8 @@ inline void hmpc_emul_dmma884(double& c0, double& c1, double a, double b)
     c1 = std::fma(A[k], B1[k], c1);
   }
 }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline long long clock64() { return 0; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -74,7 +74,7 @@ def main():
     res.update(kernel_ms=ms, qp_per_s=B / ms * 1e3)
     # ---- per-stage latency (clock64 stamps of thread 0 of each CTA) ----
     import ctypes
-    clk = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+    clk = torch.zeros((B, 32), dtype=torch.int64, device="cuda")
     interface.lib().hmpc_debug_set_clock_buffer(ctypes.c_void_p(clk.data_ptr()))
     mpc.solve_device(packed, B, d_w, d_s)
     torch.cuda.synchronize()
@@ -84,6 +84,13 @@ def main():
     names = ["load+prologue", "powers/M/d", "H,g chains", "sweep", "dual active set", "polish+scatter"]
     res["stage_cycles"] = {n: dict(med=float(np.median(dur[:, i])), p99=float(np.percentile(dur[:, i], 99))) for i, n in enumerate(names)}
     res["stage3_items_cycles_med"] = float(np.median(c[:, 7] - c[:, 2]))
+    fine = {"s5 init (x0, slacks)": (4, 8), "s5 round0: slacks->smem": (8, 9), "s5 round0: candidates+slots": (9, 10),
+            "s5 round0: T columns... S build": (10, 11), "s5 round0: S sweep": (11, 12), "s5 round0: multipliers+prune": (12, 13),
+            "s5 round0: marks+barrier": (13, 14), "s5 round0: x, slacks": (14, 15), "s5 all block rounds": (8, 16), "s5 dual iteration after": (16, 5),
+            "s4 step0 total": (3, 19), "s4 step1: W frags": (19, 20), "s4 step1: diag update+inverse": (20, 21), "s4 step1: rank-8 updates": (21, 22),
+            "s4 step1: pivot row+transposed publish": (22, 23), "s4 step1: barrier wait": (23, 24)}
+    res["fine_cycles_med"] = {k: float(np.median((c[:, b] - c[:, a])[(c[:, a] > 0) & (c[:, b] > 0)])) if ((c[:, a] > 0) & (c[:, b] > 0)).any() else None
+                              for k, (a, b) in fine.items()}
     res["cta_total_cycles"] = dict(med=float(np.median(c[:, 6] - c[:, 0])), max=float((c[:, 6] - c[:, 0]).max()))
     it = interface.status_iters(d_s.cpu().numpy())
     gi = dur[:, 4]
