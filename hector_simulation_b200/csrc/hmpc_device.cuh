@@ -309,22 +309,23 @@ __device__ inline void quat_to_R(const float* qq, float* R)
   R[8] = FS(1.f, FA(txx, tyy));
 }
 
-// foot rotation from five offset-corrected joint angles (SolverMPC.cpp:428-433; oracle: foot_rotation)
-__device__ inline void foot_rotation(const float* q, float* Rf)
+// Double-precision libm calls, one out-of-line copy each: inlined, every call site carries the whole routine (slow paths
+// included) — about 2000 instructions of straight-line code that the instruction cache fetches once per robot.
+__device__ __noinline__ void sincos_f64(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __noinline__ double fmod_f64(double x, double y) { return fmod(x, y); }
+__device__ __noinline__ double atan2_f64(double y, double x) { return atan2(y, x); }
+__device__ __noinline__ double asin_f64(double x) { return asin(x); }
+
+// foot rotation from the sines / cosines of five offset-corrected joint angles and of q2+q3+q4
+// (SolverMPC.cpp:428-433; oracle: foot_rotation); sc = {s0, c0, s1, c1, ..., s4, c4, s234, c234}
+__device__ inline void foot_rotation(const double* sc, float* Rf)
 {
-  double s0, c0, s1, c1, s2, c2, s3, c3, s4, c4;
-  sincos((double)q[0], &s0, &c0);
-  sincos((double)q[1], &s1, &c1);
-  sincos((double)q[2], &s2, &c2);
-  sincos((double)q[3], &s3, &c3);
-  sincos((double)q[4], &s4, &c4);
+  const double s0 = sc[0], c0 = sc[1], s1 = sc[2], c1 = sc[3], s2 = sc[4], c2 = sc[5], s3 = sc[6], c3 = sc[7], s4 = sc[8],
+               c4 = sc[9], s234 = sc[10], c234 = sc[11];
   double a = DA(DM(c0, s2), DM(DM(c2, s0), s1));
   double b = DS(DM(c0, c2), DM(DM(s0, s1), s2));
   double c = DA(DM(c2, s0), DM(DM(c0, s1), s2));
   double d = DS(DM(s0, s2), DM(DM(c0, c2), s1));
-  float q234 = FA(FA(q[2], q[3]), q[4]);
-  double s234, c234;
-  sincos((double)q234, &s234, &c234);
   double c3a_s3b = DA(DM(c3, a), DM(s3, b));
   double s3a_c3b = DS(DM(s3, a), DM(c3, b));
   double c3c_s3d = DS(DM(c3, c), DM(s3, d));
@@ -344,21 +345,35 @@ __device__ inline void foot_rotation(const float* q, float* Rf)
 // stage 1, split into three independent roles that run on different warps (each recomputes the cheap R)
 // record floats: p[0..2] v[3..5] q[6..9] w[10..12] r[13..18] joint[19..28] yaw[29] weights[30..41]
 //                alpha[42..53] traj[54..54+12N)  then gait bytes.   Acd/Bcd/Fblk are pre-zeroed.
+// The libm calls of a role run on different lanes (one joint angle per lane, ...), the arithmetic that combines them
+// on one lane as before — operation for operation the oracle's.
 // ------------------------------------------------------------------------------------------------
-// role "leg": joint offsets + fmod (SolverMPC.cpp:374-393), foot rotation, the leg's 8 constraint rows (:488-548)
-__device__ inline void role_leg(const float* rf, int leg, float* Fblk)
+// role "leg" (whole warp; lanes 0..9 = joints, then lanes 0..1 = legs): joint offsets + fmod (SolverMPC.cpp:374-393),
+// foot rotation, the leg's 8 constraint rows (:488-548).  scr: 10 floats + pad, then 2 x 12 doubles.
+__device__ inline void role_leg(const float* rf, int lane, float* Fblk, unsigned char* scr)
 {
   const double PI = 3.14159265359;
-  float q[5];
-  for (int i = 0; i < 5; i++) q[i] = rf[19 + 5 * leg + i];
-  q[2] = (float)DA((double)q[2], DM(0.3, PI));
-  q[3] = (float)DS((double)q[3], DM(0.6, PI));
-  q[4] = (float)DA((double)q[4], DM(0.3, PI));
-  const double PI2 = DM(2.0, PI);
-  for (int i = 0; i < 5; i++) q[i] = (float)fmod((double)q[i], PI2);
+  float* qf = reinterpret_cast<float*>(scr);          // [10] offset-corrected, reduced joint angles
+  double* sc = reinterpret_cast<double*>(scr + 48);   // [2][12] sines / cosines per leg
+  if (lane < 10) {
+    const int i = lane % 5;
+    float q = rf[19 + lane];
+    if (i == 2) q = (float)DA((double)q, DM(0.3, PI));
+    if (i == 3) q = (float)DS((double)q, DM(0.6, PI));
+    if (i == 4) q = (float)DA((double)q, DM(0.3, PI));
+    q = (float)fmod_f64((double)q, DM(2.0, PI));
+    qf[lane] = q;
+    sincos_f64((double)q, sc + 12 * (lane / 5) + 2 * i, sc + 12 * (lane / 5) + 2 * i + 1);
+  }
+  __syncwarp();
+  if (lane >= 2) return;
+  const int leg = lane;
+  const float* q = qf + 5 * leg;
+  const float q234 = FA(FA(q[2], q[3]), q[4]);
+  sincos_f64((double)q234, sc + 12 * leg + 10, sc + 12 * leg + 11);
   float R[9], Rf[9];
   quat_to_R(rf + 6, R);
-  foot_rotation(q, Rf);
+  foot_rotation(sc + 12 * leg, Rf);
   const float mu = 2.0f, lt = 0.09f, lh = 0.06f;
   const int r0 = 8 * leg, cF = 3 * leg, cM = 6 + 3 * leg;
   Fblk[(r0 + 0) * 12 + cF + 0] = -mu; Fblk[(r0 + 0) * 12 + cF + 2] = 1.f;
@@ -380,26 +395,33 @@ __device__ inline void role_leg(const float* rf, int leg, float* Fblk)
   }
   Fblk[(r0 + 7) * 12 + cF + 2] = 2.f;
 }
-// role "state": rpy (SolverMPC.cpp:333-342), Rb (:65-89), x0 (:420), the non-trivial entries of Acd (:145,315-317)
-__device__ inline void role_state(const float* rf, float dt, float* x0f, float* Acd)
+// role "state" (whole warp; lanes 0..2 = the three Euler angles, lanes 0..1 = their sines / cosines, lane 0 the rest):
+// rpy (SolverMPC.cpp:333-342), Rb (:65-89), x0 (:420), the non-trivial entries of Acd (:145,315-317).
+// scr: 3 floats + pad, then 4 doubles.
+__device__ inline void role_state(const float* rf, float dt, float* x0f, float* Acd, int lane, unsigned char* scr)
 {
-  float rpy[3];
-  {
-    float qw = rf[6], qx = rf[7], qy = rf[8], qz = rf[9];
-    double as_d = DM(2.0, (double)FS(FM(qw, qy), FM(qx, qz)));
-    if (!(as_d < .99999)) as_d = .99999;
-    float as = (float)as_d;
-    rpy[0] = (float)atan2((double)FM(2.f, FA(FM(qw, qx), FM(qy, qz))),
-                          DS(1.0, (double)FM(2.f, FA(FM(qx, qx), FM(qy, qy)))));
-    rpy[1] = (float)asin((double)as);
-    rpy[2] = (float)atan2((double)FM(2.f, FA(FM(qw, qz), FM(qx, qy))),
-                          DS(1.0, (double)FM(2.f, FA(FM(qy, qy), FM(qz, qz)))));
+  float* rpy = reinterpret_cast<float*>(scr);
+  double* sc = reinterpret_cast<double*>(scr + 16);  // sp, cp, sy, cy
+  if (lane < 3) {
+    const float qw = rf[6], qx = rf[7], qy = rf[8], qz = rf[9];
+    if (lane == 0) {
+      rpy[0] = (float)atan2_f64((double)FM(2.f, FA(FM(qw, qx), FM(qy, qz))), DS(1.0, (double)FM(2.f, FA(FM(qx, qx), FM(qy, qy)))));
+    } else if (lane == 1) {
+      double as_d = DM(2.0, (double)FS(FM(qw, qy), FM(qx, qz)));
+      if (!(as_d < .99999)) as_d = .99999;
+      const float as = (float)as_d;
+      rpy[1] = (float)asin_f64((double)as);
+    } else {
+      rpy[2] = (float)atan2_f64((double)FM(2.f, FA(FM(qw, qz), FM(qx, qy))), DS(1.0, (double)FM(2.f, FA(FM(qy, qy), FM(qz, qz)))));
+    }
   }
+  __syncwarp();
+  if (lane < 2) sincos_f64((double)rpy[1 + lane], sc + 2 * lane, sc + 2 * lane + 1);
+  __syncwarp();
+  if (lane != 0) return;
   float Rb[9];
   {
-    double sp, cp, sy, cy;
-    sincos((double)rpy[1], &sp, &cp);
-    sincos((double)rpy[2], &sy, &cy);
+    const double sp = sc[0], cp = sc[1], sy = sc[2], cy = sc[3];
     float Rbm[9] = {(float)DM(cy, cp), (float)(-sy), 0.f, (float)DM(sy, cp), (float)cy, 0.f, (float)(-sp), 0.f, 1.f};
     inverse3(Rbm, Rb);
   }
@@ -459,12 +481,12 @@ __device__ inline double leg_torque(const double* q5, int leg, int j, const doub
 {
   const double side = (leg == 0) ? 1.0 : -1.0;
   double s0, c0, s1, c1;
-  sincos(q5[0], &s0, &c0);
-  sincos(q5[1], &s1, &c1);
+  sincos_f64(q5[0], &s0, &c0);
+  sincos_f64(q5[1], &s1, &c1);
   double s234, c234, s23, c23, s2, c2;
-  sincos(q5[2] + q5[3] + q5[4], &s234, &c234);
-  sincos(q5[2] + q5[3], &s23, &c23);
-  sincos(q5[2], &s2, &c2);
+  sincos_f64(q5[2] + q5[3] + q5[4], &s234, &c234);
+  sincos_f64(q5[2] + q5[3], &s23, &c23);
+  sincos_f64(q5[2], &s2, &c2);
   const double h = 0.018 * side + 0.0025, e = 0.015 * side;
   double J[6];
   if (j == 0) {
@@ -1105,9 +1127,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     if (tid < 14) reinterpret_cast<float*>(smem + L.keep)[tid] = (tid < 10) ? rf[19 + tid] : rf[6 + tid - 10];
     {
       constexpr int W1 = (NW > 1) ? 1 : 0, W2 = (NW > 2) ? 2 : 0;
-      if (wid == 0 && lane < 2) role_leg(rf, lane, Fblk);
-      if (wid == W1 && lane == 2) role_state(rf, ka.dt, x0f, Acd);
-      if (wid == W2 && lane == 3) role_inertia(rf, ka.dt, Bcd);
+      unsigned char* scr = smem + L.P;  // 432 bytes of role scratch
+      if (wid == 0) role_leg(rf, lane, Fblk, scr);
+      if (wid == W1) role_state(rf, ka.dt, x0f, Acd, lane, scr + 256);
+      if (wid == W2 && lane == 31) role_inertia(rf, ka.dt, Bcd);
     }
     for (int e = n + tid; e < 8 * NT8; e += NT) gq[e] = 0.0;  // tile padding of the gradient
     __syncthreads();
@@ -1587,7 +1610,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // minimum is a masked REDUX over the block's ten lanes, each entry of [S | b] lives in one thread's register during a
     // Gauss-Jordan sweep with one barrier per pivot.  Any doubt (capacity, a non-positive pivot) falls back to the plain
     // iteration from the unconstrained minimiser.
-    if (qmax <= 31 && (qmax + 1) * (qmax + 4) / 2 <= 3 * NT) {
+    if (qmax <= 31) {
       int* newslot = reinterpret_cast<int*>(rr);       // [nadd] slots of the entering rows (rr is not live yet)
       double* colb = dvs;                              // [2][qmax + 3] pivot column, b_p and 1/d, double-buffered
       const int cst = qmax + 3;
@@ -1611,7 +1634,8 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         }
         const unsigned am0 = amask[0];
         __syncthreads();  // everybody has read the counts and the slot mask
-        if (nadd == 0 || q + nadd > qmax) break;  // no violated row (the iteration below confirms and stops) / no room
+        // no violated row (the iteration below confirms and stops) / no room for the rows or for one S entry per thread
+        if (nadd == 0 || q + nadd > qmax || tri(32 - __clz(am0 | ((1u << (q + nadd)) - 1u))) > NT) break;
         if (cand) {  // the rank-th entering row takes the rank-th free slot
           unsigned fm = ~am0;
           for (int r = 0; r < rank; r++) fm &= fm - 1;
@@ -1631,79 +1655,67 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         }
         __syncthreads();
         if (round == 0) HMPC_STAMP(10);
-        // solve S lam = b on the working set; rows with a non-positive multiplier leave and the solve is repeated
+        // solve S lam = b on the working set; rows with a non-positive multiplier leave and the solve is repeated.
+        // Thread e2 < tri(qh) holds entry (i, j), j <= i, of S; the diagonal owners also hold b_i.
         int verdict = 0;  // 0: all multipliers positive, 1: gave up
         for (int attempt = 0; attempt < 4; attempt++) {
           const unsigned am = amask[0];
           const int qh = 32 - __clz(am);
-          const int ntri = tri(qh), nent = ntri + qh;
-          // entries of [S | b]: e2 < ntri -> (i, j), j <= i, row-packed; then b_i
-          double av[3] = {0.0, 0.0, 0.0};
-          int ei[3] = {0, 0, 0}, ej[3] = {0, 0, 0};
-#pragma unroll
-          for (int u = 0; u < 3; u++) {
-            const int e2 = tid + u * NT;
-            if (e2 >= nent) { ei[u] = -1; continue; }
-            int i, j;
-            if (e2 < ntri) {
-              i = (int)((sqrtf(8.f * (float)e2 + 1.f) - 1.f) * 0.5f);
-              while (tri(i + 1) <= e2) i++;
-              while (tri(i) > e2) i--;
-              j = e2 - tri(i);
-            } else {
-              i = e2 - ntri;
-              j = qh;  // the right-hand side column
-            }
-            ei[u] = i;
-            ej[u] = j;
-            const bool ui = (am >> i) & 1u, uj = (j == qh) || ((am >> j) & 1u);
-            double v = (i == j) ? 1.0 : 0.0;  // free slots: identity rows
+          const bool own = tid < tri(qh);
+          int i = 0, j = 0;
+          double a = 0.0, bi = 0.0;
+          if (own) {
+            i = (int)((sqrtf(8.f * (float)tid + 1.f) - 1.f) * 0.5f);
+            while (tri(i + 1) <= tid) i++;
+            while (tri(i) > tid) i--;
+            j = tid - tri(i);
+            const bool ui = (am >> i) & 1u, uj = (am >> j) & 1u;
+            a = (i == j) ? 1.0 : 0.0;  // free slots: identity rows
             if (ui && uj) {
               const int w = wsl[i], ki = w >> 8;
               const double* ni = nrm + (w & 0xff) * 6;
-              if (j == qh) {
+              a = dot6(ni, T + j * n + 6 * ki);
+              if (i == j) {
                 const int te = (w & 0xff) % 10;
-                v = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
-              } else {
-                v = dot6(ni, T + j * n + 6 * ki);
+                bi = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
               }
-            } else if (ui != uj || j == qh) {
-              v = 0.0;
+            } else if (ui != uj) {
+              a = 0.0;
             }
-            av[u] = v;
           }
-          // publish pivot column 0
+          const bool diag = own && i == j;
+          // publish pivot column 0: S(.,0), b_0, 1/S(0,0)
           bool sing = false;
-#pragma unroll
-          for (int u = 0; u < 3; u++) {
-            if (ei[u] < 0) continue;
-            if (ej[u] == 0) colb[ei[u]] = av[u];                      // S(i,0)
-            if (ei[u] == 0 && ej[u] == qh) colb[qh] = av[u];          // b_0
-            if (ei[u] == 0 && ej[u] == 0) { colb[qh + 1] = fast_rcp(av[u]); sing |= !(av[u] > 1e-13); }
+          if (own && j == 0) {
+            colb[i] = a;
+            if (i == 0) {
+              colb[qh] = bi;
+              colb[qh + 1] = fast_rcp(a);
+              sing = !(a > 1e-13);
+            }
           }
           if (round == 0 && attempt == 0) HMPC_STAMP(11);
           __syncthreads();
           for (int pv = 0; pv < qh; pv++) {
-            const double* cc = colb + (pv & 1) * cst;
-            double* cn = colb + ((pv + 1) & 1) * cst;
-            const double inv = cc[qh + 1];
-#pragma unroll
-            for (int u = 0; u < 3; u++) {
-              const int i = ei[u], j = ej[u];
-              if (i < 0) continue;
-              const double ci = cc[i], cj = cc[j];  // cc[qh] = b_pv serves the right-hand side column
-              double a = av[u];
+            if (own) {
+              const double* cc = colb + (pv & 1) * cst;
+              double* cn = colb + ((pv + 1) & 1) * cst;
+              const double inv = cc[qh + 1];
+              const double ci = cc[i], cj = cc[j];
+              if (diag) bi = (i == pv) ? cc[qh] * inv : fma(-ci * inv, cc[qh], bi);
               if (i == pv) a = (j == pv) ? -inv : cj * inv;
               else if (j == pv) a = ci * inv;
               else a = fma(-ci * inv, cj, a);
-              av[u] = a;
-              // next pivot's column: S(.,pv+1) = row pv+1 left of the diagonal and column pv+1 below it
+              // next pivot's column: row pv+1 left of the diagonal and column pv+1 from the diagonal down
               const int pn = pv + 1;
               if (pn < qh) {
                 if (j == pn) cn[i] = a;
-                else if (i == pn && j < pn) cn[j] = a;
-                else if (i == pn && j == qh) cn[qh] = a;
-                if (i == pn && j == pn) { cn[qh + 1] = fast_rcp(a); sing |= !(a > 1e-13); }
+                else if (i == pn) cn[j] = a;
+                if (diag && i == pn) {
+                  cn[qh] = bi;
+                  cn[qh + 1] = fast_rcp(a);
+                  sing |= !(a > 1e-13);
+                }
               }
             }
             __syncthreads();
@@ -1711,16 +1723,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           if (round == 0 && attempt == 0) HMPC_STAMP(12);
           // -S^-1 and lam = S^-1 b are in the registers: store them for the dual iteration / the x update
           bool neg = false;
-#pragma unroll
-          for (int u = 0; u < 3; u++) {
-            const int i = ei[u], j = ej[u];
-            if (i < 0) continue;
-            if (j == qh) {
+          if (own) {
+            Sv[tid] = -a;  // packed lower rows: index tri(i) + j = tid
+            if (diag) {
               const bool used = (am >> i) & 1u;
-              lam[i] = used ? av[u] : 0.0;
-              neg |= used && !(av[u] > 0.0);
-            } else {
-              Sv[tri(i) + j] = -av[u];
+              lam[i] = used ? bi : 0.0;
+              neg = used && !(bi > 0.0);
             }
           }
           const int anyneg = __syncthreads_or((int)neg | ((int)sing << 1));

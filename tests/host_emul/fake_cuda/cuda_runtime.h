@@ -22,6 +22,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)

@@ -161,11 +161,16 @@ void emul_stage1(const float* rf, float dt, float* Fblk, float* x0, float* Acd, 
   memset(Fblk, 0, 192 * sizeof(float));
   memset(Acd, 0, 169 * sizeof(float));
   memset(Bcd, 0, 156 * sizeof(float));
-  float x0f[16] = {0};
-  hmpc::role_leg(rf, 0, Fblk);
-  hmpc::role_leg(rf, 1, Fblk);
-  hmpc::role_state(rf, dt, x0f, Acd);
-  hmpc::role_inertia(rf, dt, Bcd);
+  static float x0f[16];
+  alignas(16) static unsigned char scr[512];
+  memset(x0f, 0, sizeof(x0f));
+  // the roles are warp-cooperative (libm calls spread over lanes): one emulated warp runs them the way stage 1 does
+  run_cta(32, [=] {
+    const int lane = (int)threadIdx.x;
+    hmpc::role_leg(rf, lane, Fblk, scr);
+    hmpc::role_state(rf, dt, x0f, Acd, lane, scr + 256);
+    if (lane == 31) hmpc::role_inertia(rf, dt, Bcd);
+  });
   memcpy(x0, x0f, 13 * sizeof(float));
 }
 
