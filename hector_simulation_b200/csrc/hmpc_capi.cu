@@ -131,7 +131,9 @@ struct hmpc_ctx {
   unsigned char* d_out = nullptr;  // host-buffer path: per chunk [wrench floats | status ints], contiguous
   int* d_status = nullptr;         // scratch status (assembly hook)
   int* d_counts = nullptr;         // [NCHUNK][2] class list lengths
-  int* d_lists = nullptr;          // [NCHUNK][2][max_batch] class lists
+  int* d_lists = nullptr;          // [NCHUNK][2][max_batch] class lists (host-built, host-buffer path)
+  int* d_cls = nullptr;            // [NCHUNK][2 parities x 4 lengths | class-1 list | class-2 list] (device-resident path)
+  unsigned tick[NCHUNK] = {0, 0, 0, 0};  // calls per slot: parity of the list lengths in use
   unsigned char* h_rec = nullptr;  // pinned
   unsigned char* h_out = nullptr;  // pinned mirror of d_out
   unsigned char* d_states = nullptr;  // hmpc_state_t staging of hmpc_solve_batch_states (row f-1)
@@ -355,6 +357,7 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->d_status) cudaFree(c->d_status);
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->d_lists) cudaFree(c->d_lists);
+  if (c->d_cls) cudaFree(c->d_cls);
   if (c->d_states) cudaFree(c->d_states);
   if (c->h_states) cudaFreeHost(c->h_states);
   if (c->h_rec) cudaFreeHost(c->h_rec);
@@ -406,6 +409,8 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMalloc results") ||
           cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 4 * sizeof(int)), "cudaMalloc counts") ||
           cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMalloc lists") ||
+          cuda_fail(cudaMalloc(&c->d_cls, (size_t)NCHUNK * (8 + 2 * (size_t)max_batch) * sizeof(int)), "cudaMalloc class lists") ||
+          cuda_fail(cudaMemset(c->d_cls, 0, (size_t)NCHUNK * (8 + 2 * (size_t)max_batch) * sizeof(int)), "cudaMemset class lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
           cuda_fail(cudaMalloc(&c->d_states, (size_t)max_batch * sizeof(hmpc_state_t)), "cudaMalloc states") ||
           cuda_fail(cudaMallocHost(&c->h_states, (size_t)max_batch * sizeof(hmpc_state_t)), "cudaMallocHost states") ||
@@ -450,27 +455,23 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
-  int* counts = c->d_lists + (size_t)slot * (4 + 3 * (size_t)c->max_batch);  // per slot: [4 counts][3 lists]
-  int* lists = counts + 4;
+  // per slot: [2 parities][4 list lengths], then the lists of class 1 and class 2.  No classification kernel: the
+  // class-0 launch runs over every instance and hands the ones with more stance blocks than it holds to class 1's list.
+  int* base = c->d_cls + (size_t)slot * (8 + 2 * (size_t)c->max_batch);
+  const int par = (c->tick[slot]++) & 1;
+  int* counts = base + 4 * par;
+  int* counts_next = base + 4 * (par ^ 1);
+  int* lists = base + 8 - (size_t)c->max_batch;  // lists + i * max_batch is class i's list, i = 1, 2
   const bool pdl = pdl_enabled();
-  if (B <= 1024) {
-    CK(launch_chain(hmpc::hmpc_classify1_kernel, dim3(1), dim3((B + 31) / 32 * 32), 0, st, pdl,
-                    static_cast<const unsigned char*>(d_records), c->rec_stride, B, c->horizon, c->setup.f_max,
-                    c->cls[0].nb_hi, counts, lists, c->max_batch));
-  } else {
-    CK(cudaMemsetAsync(counts, 0, 3 * sizeof(int), st));
-    CK(launch_chain(hmpc::hmpc_classify_kernel, dim3((B + 255) / 256), dim3(256), 0, st, false,
-                    static_cast<const unsigned char*>(d_records), c->rec_stride, B, c->horizon, c->setup.f_max,
-                    c->cls[0].nb_hi, counts, lists, c->max_batch));
-  }
-  CK(cudaGetLastError());
   for (int i = 0; i < c->ncls; i++) {
     const ClassCfg& k = c->cls[i];
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
     ka.tau = d_tau;
     ka.warm_start = 0;
-    ka.list = lists + (size_t)i * c->max_batch;
+    ka.list = (i == 0) ? nullptr : lists + (size_t)i * c->max_batch;
+    ka.split_nb = (i == 0) ? k.nb_hi : -1;
+    ka.counts_next = (i == 0) ? counts_next : nullptr;
     ka.counts = counts;
     ka.cls = i;
     ka.esc_list = (i + 1 < c->ncls) ? lists + (size_t)(i + 1) * c->max_batch : nullptr;
@@ -532,6 +533,7 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
     ka.counts = d_block;
     ka.cls = i;
     ka.esc_list = nullptr;  // overflow is handled by the caller's retry
+    ka.split_nb = -1;
     ka.nb_cap = k.nb_cap;
     ka.qmax = k.qmax;
     ka.L = k.L;
@@ -546,7 +548,7 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
 // profiling hook: device buffer [batch][32] of clock64() stage timestamps, or NULL to switch off
 HMPC_EXTERNC void hmpc_debug_set_clock_buffer(long long* d_buf) { g_dbg_clk = d_buf; }
 
-HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls + 1 : 0; }
+HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls : 0; }
 
 // launch configuration of class `cls`: out[0..5] = threads, dynamic smem bytes, working-set capacity,
 // resident-grid cap (CTAs), max blocks of 6 variables, sweep strip width
@@ -587,6 +589,7 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
   const ClassCfg& k = c->cls[c->ncls - 1];
   hmpc::KernelArgs ka = base_args(c, d_records, B, nullptr, c->d_status);
   ka.list = nullptr;  // identity
+  ka.split_nb = -1;
   ka.counts = c->d_counts;
   ka.cls = c->ncls - 1;
   ka.esc_list = nullptr;

@@ -135,7 +135,9 @@ struct KernelArgs {
   const int* list;               // instances of this launch's class (nullptr: identity over [0,batch))
   int* counts;                   // [ncls] list lengths (device); counts[cls] is this launch's
   int cls;                       // class index of this launch
-  int* esc_list;                 // next class's list (working-set overflow escalation) or nullptr
+  int* esc_list;                 // next class's list (working-set overflow escalation, size-class hand-over) or nullptr
+  int split_nb;                  // >= 0: classify in this launch — an instance with more stance blocks goes to esc_list
+  int* counts_next;              // the next call's list lengths, zeroed by this launch (device-resident chain), or nullptr
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
@@ -907,54 +909,6 @@ __global__ void hmpc_swing_kernel(const unsigned char* states, const unsigned ch
 }
 
 // ------------------------------------------------------------------------------------------------
-// classification pre-pass: bucket instances by reduced size (number of stance (step,leg) blocks)
-// ------------------------------------------------------------------------------------------------
-// single-block variant (batch <= 1024): counts via shared-memory atomics, written (not accumulated) at the end,
-// so no memset has to precede it
-__global__ void hmpc_classify1_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,
-                                      int nb_hi0, int* counts, int* lists, int list_stride)
-{
-  __shared__ int cnt[2];
-  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
-  pdl_wait();     // the previous solve's kernels may still read counts/lists
-  pdl_trigger();  // the class kernels may set up while this block classifies
-  __syncthreads();
-  const int i = threadIdx.x;
-  if (i < batch) {
-    const unsigned char* g = records + (size_t)i * rec_stride + (54 + 12 * N) * 4;
-    int nb = 0;
-    for (int e = 0; e < 2 * N; e++) {
-      const float ub = FM(f_max, (float)g[e]);
-      nb += !(ub < 0.0001f && ub > -0.0001f);
-    }
-    const int c = (nb <= nb_hi0) ? 0 : 1;
-    const int slot = atomicAdd(&cnt[c], 1);
-    lists[(size_t)c * list_stride + slot] = i;
-  }
-  __syncthreads();
-  if (threadIdx.x < 2) counts[threadIdx.x] = cnt[threadIdx.x];
-  if (threadIdx.x == 2) counts[2] = 0;  // class 2 is filled by escalation only
-}
-
-__global__ void hmpc_classify_kernel(const unsigned char* records, int rec_stride, int batch, int N, float f_max,
-                                     int nb_hi0, int* counts, int* lists, int list_stride)
-{
-  pdl_wait();
-  pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch) return;
-  const unsigned char* g = records + (size_t)i * rec_stride + (54 + 12 * N) * 4;
-  int nb = 0;
-  for (int e = 0; e < 2 * N; e++) {
-    const float ub = FM(f_max, (float)g[e]);
-    nb += !(ub < 0.0001f && ub > -0.0001f);
-  }
-  const int c = (nb <= nb_hi0) ? 0 : 1;
-  const int slot = atomicAdd(&counts[c], 1);
-  lists[(size_t)c * list_stride + slot] = i;
-}
-
-// ------------------------------------------------------------------------------------------------
 // the kernel.  NT threads = NT/32 warps: warp w owns tile rows w and NT8-1-w of the sweep, thread e owns
 // constraint row e in the active-set iterations and thread NT-1-i owns variable i.
 // NF > 0 fixes the horizon at compile time (layout offsets and loop bounds fold), NF == 0 reads it from
@@ -1027,6 +981,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   __syncthreads();
   uint32_t phase = 0;
   pdl_wait();     // counts / lists / records come from the kernels before this one
+  // the list lengths of the NEXT call (the other parity) are cleared here: every kernel of the previous call, which
+  // used them, completed before pdl_wait() returned, and this call only touches its own
+  if (ka.counts_next && blockIdx.x == 0 && tid < 4) ka.counts_next[tid] = 0;
   const int count = ka.list ? ka.counts[ka.cls] : ka.batch;
 
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
@@ -1119,6 +1076,15 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
     __syncthreads();
     const int NB = flags[0];
+    if (ka.split_nb >= 0 && NB > ka.split_nb) {
+      // size classification folded into the launch: more stance blocks than this class holds -> next class's list
+      if (tid == 0) {
+        const int slot = atomicAdd(&ka.counts[ka.cls + 1], 1);
+        ka.esc_list[slot] = inst;
+      }
+      __syncthreads();
+      continue;
+    }
     const int n = 6 * NB, m = 10 * NB;
     const int NT8 = (n + 7) >> 3;
     const unsigned stmask[2] = {(unsigned)flags[1], (unsigned)flags[2]};

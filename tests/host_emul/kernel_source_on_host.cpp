@@ -190,9 +190,9 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
   if (B < 1 || B > 1024 || (!records && !raw)) return 1;
   ClassCfg cls[3];
   int ncls = build_classes(N, cls);
-  std::vector<int> block(4 + 3 * (size_t)B, 0);
-  int* counts = block.data();
-  int* lists = counts + 4;
+  std::vector<int> block(8 + 3 * (size_t)B, 0);
+  int* counts = block.data();      // [4] list lengths (+ [4] the next call's, which the class-0 launch clears)
+  int* lists = counts + 8;
   const int rs = hmpc::record_stride(N);
   const int nb_hi0 = cls[0].nb_cap;
   if (raw) {
@@ -208,11 +208,13 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     }
     ncls = 2;
   } else {
-    run_cta((B + 31) / 32 * 32, [=] { hmpc::hmpc_classify1_kernel(records, rs, B, N, f_max, nb_hi0, counts, lists, B); });
+    counts[0] = B;       // device-resident path: class 0 runs over every instance and classifies on the way
+    counts[4] = counts[5] = counts[6] = counts[7] = 0x55;  // must come back cleared
   }
   for (int i = 0; i < ncls; i++) {
     if (launched) launched[i] = counts[i];
     if (counts[i] == 0) continue;
+    const bool fused = !raw && i == 0;
     hmpc::KernelArgs ka{};
     ka.records = records;
     ka.raw_records = raw;
@@ -228,7 +230,9 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.status = status;
     ka.tau = tau;
     ka.warm_start = warm_start;
-    ka.list = lists + (size_t)i * B;
+    ka.list = fused ? nullptr : lists + (size_t)i * B;
+    ka.split_nb = fused ? nb_hi0 : -1;
+    ka.counts_next = fused ? counts + 4 : nullptr;
     ka.counts = counts;
     ka.cls = i;
     ka.esc_list = (!raw && i + 1 < ncls) ? lists + (size_t)(i + 1) * B : nullptr;
@@ -237,6 +241,10 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.L = cls[i].L;
     ka.dbg_H = dH; ka.dbg_g = dg; ka.dbg_F = dF; ka.dbg_lb = dlb; ka.dbg_ub = dub;
     launch_variant(cls[i].variant, ka);
+    if (fused) {
+      if (counts[4] | counts[5] | counts[6] | counts[7]) return 2;  // the next call's lengths were not cleared
+      if (launched) launched[0] = B - counts[1];                     // instances class 0 kept
+    }
   }
   return 0;
 }
