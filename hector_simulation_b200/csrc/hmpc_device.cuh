@@ -105,10 +105,17 @@ __host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12
 // class 0 (a walking gait ends with about one active row per stance step; 15 at N = 10), 31 for class 1; an instance that needs more
 // escalates to the next class (class 2 = class 1's size with as many slots as shared memory holds).
 __host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
+__host__ __device__ constexpr int class_warps(int N, int cls);
 __host__ __device__ constexpr int class_qmax(int N, int cls)
 {
-  const int n = 6 * class_nb_cap(N, cls);
-  const int q = cls == 0 ? N + 5 : (N <= 10 ? 31 : 36);  // (the block start handles up to 31 rows: one mask word)
+  const int nb = class_nb_cap(N, cls), n = 6 * nb;
+  int q = cls == 0 ? N + 5 : 31;  // (the block start handles up to 31 rows: one mask word)
+  if (cls == 1 && N > 10) {
+    // long horizons (extension configs): double-support optima hold more rows than 31 — as many slots as one SM's
+    // shared memory leaves (the block start is skipped there, the plain dual iteration runs)
+    const int rs = record_stride(N), nw = class_warps(N, cls);
+    while (q < 2 * N + 16 && make_layout(N, nb, q + 1, rs, nw).total <= 226 * 1024) q++;
+  }
   return q < n ? q : n;
 }
 // warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (3 blocks of 10 per warp)
