@@ -143,6 +143,8 @@ struct hmpc_ctx {
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
+  int* d_ws = nullptr;             // [max_batch][WS_STATE_INTS] working sets of the previous tick (closed-loop warm start)
+  int warm_start = 1;              // hmpc_rollout_device proposes them to the next tick (HMPC_WARM_START=0: cold start every tick)
   int block_rounds = 4;  // block start of the active-set stage (HMPC_BLOCK_ROUNDS=0: plain dual iteration, for A/B runs)
   // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
   // reference records from them and write results to them in place (no packing, no staging copies, no widening)
@@ -358,6 +360,7 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->d_lists) cudaFree(c->d_lists);
   if (c->d_cls) cudaFree(c->d_cls);
+  if (c->d_ws) cudaFree(c->d_ws);
   if (c->d_states) cudaFree(c->d_states);
   if (c->h_states) cudaFreeHost(c->h_states);
   if (c->h_rec) cudaFreeHost(c->h_rec);
@@ -409,6 +412,8 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
           cuda_fail(cudaMalloc(&c->d_out, (size_t)max_batch * (nw * 4 + 4 + 40)), "cudaMalloc results") ||
           cuda_fail(cudaMalloc(&c->d_counts, NCHUNK * 4 * sizeof(int)), "cudaMalloc counts") ||
           cuda_fail(cudaMalloc(&c->d_lists, (size_t)NCHUNK * (4 + 3 * (size_t)max_batch) * sizeof(int)), "cudaMalloc lists") ||
+          cuda_fail(cudaMalloc(&c->d_ws, (size_t)max_batch * hmpc::WS_STATE_INTS * sizeof(int)), "cudaMalloc working sets") ||
+          cuda_fail(cudaMemset(c->d_ws, 0, (size_t)max_batch * hmpc::WS_STATE_INTS * sizeof(int)), "cudaMemset working sets") ||
           cuda_fail(cudaMalloc(&c->d_cls, (size_t)NCHUNK * (8 + 2 * (size_t)max_batch) * sizeof(int)), "cudaMalloc class lists") ||
           cuda_fail(cudaMemset(c->d_cls, 0, (size_t)NCHUNK * (8 + 2 * (size_t)max_batch) * sizeof(int)), "cudaMemset class lists") ||
           cuda_fail(cudaMalloc(&c->d_status, (size_t)max_batch * 4), "cudaMalloc status") ||
@@ -422,6 +427,8 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
   if (!bad) {
     const char* br = getenv("HMPC_BLOCK_ROUNDS");
     if (br) c->block_rounds = atoi(br);
+    const char* wm = getenv("HMPC_WARM_START");
+    if (wm) c->warm_start = atoi(wm);
   }
   if (!bad && max_batch >= 256) {
     const char* e = getenv("HMPC_HOST_THREADS");
@@ -451,7 +458,7 @@ namespace {
 long long* g_dbg_clk = nullptr;  // profiling hook (hmpc_debug_set_clock_buffer)
 // classification pre-pass + one launch per class, all enqueued on `st`
 int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, double* d_wrench64, int* d_status,
-                  cudaStream_t st, int slot = 0, float* d_tau = nullptr)
+                  cudaStream_t st, int slot = 0, float* d_tau = nullptr, int* d_ws = nullptr, int ws_shift = 0, bool ws_read = false)
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
@@ -468,7 +475,9 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
     ka.tau = d_tau;
-    ka.warm_start = 0;
+    ka.warm_start = (d_ws && ws_read) ? 1 : 0;
+    ka.ws_state = d_ws;
+    ka.ws_shift = ws_shift;
     ka.list = (i == 0) ? nullptr : lists + (size_t)i * c->max_batch;
     ka.split_nb = (i == 0) ? k.nb_hi : -1;
     ka.counts_next = (i == 0) ? counts_next : nullptr;
@@ -715,13 +724,21 @@ HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* c, hmpc_state_t* d_states, hmpc_r
     if (d_record_log)
       CK(cudaMemcpyAsync(static_cast<unsigned char*>(d_record_log) + (size_t)t * B * c->rec_stride, c->d_rec,
                          (size_t)B * c->rec_stride, cudaMemcpyDeviceToDevice, st));
-    rc = enqueue_solve(c, c->d_rec, B, dw, nullptr, ds, st, 0, nullptr);
+    rc = enqueue_solve(c, c->d_rec, B, dw, nullptr, ds, st, 0, nullptr, c->warm_start ? c->d_ws : nullptr, 1, true);
     if (rc != HMPC_OK) return rc;
     hmpc::hmpc_advance_kernel<<<(B + 63) / 64, 64, 0, st>>>(reinterpret_cast<unsigned char*>(d_states),
                                                             reinterpret_cast<unsigned char*>(d_loop), B, c->horizon, dtMPC, dw, ds,
                                                             d_wrench_log ? d_wrench_log + (size_t)t * B * 12 : nullptr);
     CK(cudaGetLastError());
   }
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_reset_warm_start(hmpc_ctx* c, void* stream)
+{
+  if (!c) { g_err = "hmpc_reset_warm_start: null context"; return HMPC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->d_ws, 0, (size_t)c->max_batch * hmpc::WS_STATE_INTS * sizeof(int), static_cast<cudaStream_t>(stream)));
   return HMPC_OK;
 }
 

@@ -149,8 +149,9 @@ struct KernelArgs {
   int qmax;                      // working-set capacity
   int max_iter;
   int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
-  int warm_start;                // 1: start from the working set in `ws_state` (previous tick), write it back
-  int* ws_state;                 // [batch][WS_STATE_INTS] persistent working sets (closed loop), or nullptr
+  int warm_start;                // 1: propose the working set in `ws_state` (previous tick) to the block start
+  int ws_shift;                  // MPC steps the horizon moved since that tick (the closed loop: 1)
+  int* ws_state;                 // [batch][WS_STATE_INTS] persistent working sets, read (warm_start) and written back; or nullptr
   float* wrench;                 // [batch][12N] float results, or nullptr
   double* wrench64;              // [batch][12N] double results, or nullptr
   int* status;                   // [batch]
@@ -1587,15 +1588,54 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       int* newslot = reinterpret_cast<int*>(rr);       // [nadd] slots of the entering rows (rr is not live yet)
       double* colb = dvs;                              // [2][qmax + 3] pivot column, b_p and 1/d, double-buffered
       const int cst = qmax + 3;
+      // Warm start (closed loop): the rows that were active at the previous tick's optimum, moved with the horizon, are
+      // proposed as round 0's entering rows instead of the most violated ones; the round solves on them, prunes the ones
+      // whose multiplier is not positive, and the following rounds / the dual iteration repair what changed.
+      bool warm = false;
+      unsigned* wmark = reinterpret_cast<unsigned*>(redi + 16);  // [16] bitmap over the rows
+      if (ka.warm_start && ka.ws_state) {
+        const int* ws = ka.ws_state + (size_t)inst * WS_STATE_INTS;
+        const int cnt = ws[0];
+        if (cnt > 0 && cnt < WS_STATE_INTS) {
+          if (tid < 16) wmark[tid] = 0u;
+          __syncthreads();
+          if (tid < cnt) {
+            const int ent = ws[1 + tid];
+            const int sl = (ent >> 8) - 2 * ka.ws_shift;  // (step, leg): one MPC step later it sits one step earlier
+            if (sl >= 0 && sl < 2 * N) {
+              const int kb = sl_blk[sl];
+              if (kb >= 0) {
+                const int e = 10 * kb + (ent & 0xff) % 10;
+                atomicOr(&wmark[e >> 5], 1u << (e & 31));
+              }
+            }
+            // the steps that entered the horizon have no history: they inherit the rows of the old last step
+            if ((ent >> 8) >= 2 * (N - 1)) {
+              for (int sn = sl + 2; sn >= 0 && sn < 2 * N; sn += 2) {
+                const int kb = sl_blk[sn];
+                if (kb >= 0) {
+                  const int e = 10 * kb + (ent & 0xff) % 10;
+                  atomicOr(&wmark[e >> 5], 1u << (e & 31));
+                }
+              }
+            }
+          }
+          __syncthreads();
+          warm = true;
+        }
+      }
       for (int round = 0; code == ST_OK && round < ka.block_rounds; round++) {
         if (round == 0) HMPC_STAMP(8);
-        // most violated inactive row of every block
+        // most violated inactive row of every block (round 0 of a warm start: the proposed rows)
         const unsigned gm = (lane < 30) ? (0x3ffu << (10 * (lane / 10))) : (1u << lane);
         const float sf = (iscon && !act) ? (float)se : 3.0e38f;
         const unsigned key = fkey(sf);
         const unsigned kmin = __reduce_min_sync(gm, key);
         const unsigned tie = __ballot_sync(0xffffffffu, key == kmin) & gm;
-        const bool cand = iscon && !act && se < -tol && key == kmin && (__ffs(tie) - 1) == lane;
+        bool cand = iscon && !act && se < -tol && key == kmin && (__ffs(tie) - 1) == lane;
+        if (warm) cand = iscon && ((wmark[erow >> 5] >> (erow & 31)) & 1u);
+        const bool warm_round = warm;
+        warm = false;
         const unsigned cm = __ballot_sync(0xffffffffu, cand);
         if (lane == 0) redi[wid] = __popc(cm);
         __syncthreads();
@@ -1734,7 +1774,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const int qhf2 = 32 - __clz(amf);
         if (iscon) act = myslot >= 0;
         q = __popc(amf);
-        iters += nadd;
+        if (!warm_round) iters += nadd;  // proposals of a warm start are not changes; what the solve drops of them is
         if (tid == 0) {
           flags[9] = qhf2;
           flags[7] = __ffs(~amf) - 1;
@@ -1962,6 +2002,17 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       zb[vi] = acc;
     }
     __syncthreads();
+
+    // working set for the next tick (closed loop): (step, leg) and normal index of every active row
+    if (ka.ws_state && wid == 0) {
+      int* ws = ka.ws_state + (size_t)inst * WS_STATE_INTS;
+      const unsigned am = (code == ST_OK && qmax <= 31) ? amask[0] : 0u;
+      if ((am >> lane) & 1u) {
+        const int w = wsl[lane];
+        ws[1 + __popc(am & ((1u << lane) - 1u))] = (blk_sl[w >> 8] << 8) | (w & 0xff);
+      }
+      if (lane == 0) ws[0] = __popc(am);
+    }
 
     // ---------------- stage 6: scatter (eliminated variables are exactly 0) ----------------
     for (int e = tid; e < 12 * N; e += NT) {

@@ -25,7 +25,7 @@ EXPORTS = [
     "hmpc_record_bytes", "hmpc_pack_records", "hmpc_create", "hmpc_destroy", "hmpc_last_error",
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
     "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
-    "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device",
+    "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device", "hmpc_reset_warm_start",
     "hmpc_pin_host_buffer", "hmpc_unpin_host_buffer", "hmpc_swing_device",
 ]
 
@@ -85,6 +85,8 @@ def lib() -> ctypes.CDLL:
         L.hmpc_rollout_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.hmpc_rollout_device.restype = ctypes.c_int
+        L.hmpc_reset_warm_start.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_reset_warm_start.restype = ctypes.c_int
         L.hmpc_pin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.hmpc_pin_host_buffer.restype = ctypes.c_int
         L.hmpc_unpin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -282,6 +284,13 @@ class BatchedMPC:
         _check(lib().hmpc_rollout_device(self._h, d_states.data_ptr(), d_loop.data_ptr(), B, ticks, dt_mpc,
                                          d_wrench_log.data_ptr() if d_wrench_log is not None else None,
                                          d_record_log.data_ptr() if d_record_log is not None else None, ctypes.c_void_p(st)))
+
+    def reset_warm_start(self, stream=None) -> None:
+        """Forget the working sets the closed loop keeps between ticks (a new loop on this context starts cold)."""
+        import torch
+
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _check(lib().hmpc_reset_warm_start(self._h, ctypes.c_void_p(st)))
 
     def swing_device(self, d_states, d_loop, d_phase, d_swing, B: int, d_cmd, dt: float = 0.001, dt_swing: float = 0.04,
                      stream=None) -> None:

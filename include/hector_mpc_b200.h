@@ -209,6 +209,13 @@ struct hmpc_rollout_t
   int iters_total;        /* working-set changes, accumulated */
   int ticks;              /* ticks advanced so far */
 };
+/* Warm start: every tick after the first proposes the previous tick's optimal working set, moved one step with the
+ * horizon, to the active-set stage (the reference cold-starts every tick, SolverMPC.cpp:702-709; BASELINE.json
+ * configs[4] names the warm start).  The optimum is the same point either way — the working set only decides how many
+ * changes the solver makes to reach it; the status word then counts the changes relative to the proposal.  The sets live in
+ * the context; hmpc_reset_warm_start forgets them (a new loop on the same context).  HMPC_WARM_START=0 in the environment
+ * at hmpc_create keeps every tick a cold start. */
+HMPC_EXTERNC int hmpc_reset_warm_start(hmpc_ctx* ctx, void* stream);
 /* ticks >= 1.  d_wrench_log: NULL or float [ticks][B][12] (first-step wrench of every tick); d_record_log: NULL or
  * [ticks][B][hmpc_record_bytes] (the packed records the solver saw, for after-the-fact parity checks). */
 HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* ctx, struct hmpc_state_t* d_states, struct hmpc_rollout_t* d_loop, int B,

@@ -124,7 +124,21 @@ inline void set_thread(int i)
 }
 }  // namespace
 
+namespace {
+int* g_ws = nullptr;  // [B][WS_STATE_INTS] working sets kept between emul_solve* calls (closed-loop warm start), or null
+int g_ws_shift = 0;
+}  // namespace
+
 extern "C" {
+
+/* working-set memory for the following emul_solve* calls: written back by every solve, proposed to the next one when that
+ * call passes warm_start = 1 (shift = MPC steps the horizon moved in between) */
+void emul_set_ws(int* ws, int shift)
+{
+  g_ws = ws;
+  g_ws_shift = shift;
+}
+int emul_ws_ints() { return hmpc::WS_STATE_INTS; }
 
 int emul_record_stride(int N) { return hmpc::record_stride(N); }
 
@@ -229,7 +243,9 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.wrench64 = wrench64;
     ka.status = status;
     ka.tau = tau;
-    ka.warm_start = warm_start;
+    ka.warm_start = (g_ws && warm_start) ? 1 : 0;
+    ka.ws_state = g_ws;
+    ka.ws_shift = g_ws_shift;
     ka.list = fused ? nullptr : lists + (size_t)i * B;
     ka.split_nb = fused ? nb_hi0 : -1;
     ka.counts_next = fused ? counts + 4 : nullptr;

@@ -12,6 +12,8 @@ extern "C" int emul_solve_ex(const unsigned char* records, const unsigned char* 
                              int max_iter, int warm_start, float* wrench, double* wrench64, int* status, float* tau, int* launched,
                              float* dH, float* dg, float* dF, float* dlb, float* dub);
 extern "C" int emul_record_stride(int N);
+extern "C" void emul_set_ws(int* ws, int shift);
+extern "C" int emul_ws_ints();
 
 int main(int argc, char** argv)
 {
@@ -33,8 +35,16 @@ int main(int argc, char** argv)
   std::vector<double> w64((size_t)B * 12 * N);
   std::vector<int> st(B);
   int launched[3] = {0, 0, 0};
-  const int rc = emul_solve_ex(raw ? nullptr : buf.data(), raw ? buf.data() : nullptr, B, N, 0.04f, 500.f, 500, warm ? 1 : 0,
-                               w.data(), w64.data(), st.data(), tau.data(), launched, 0, 0, 0, 0, 0);
+  std::vector<int> ws((size_t)B * emul_ws_ints(), 0);
+  if (warm) emul_set_ws(ws.data(), 0);
+  int rc = emul_solve_ex(raw ? nullptr : buf.data(), raw ? buf.data() : nullptr, B, N, 0.04f, 500.f, 500, 0,
+                         w.data(), w64.data(), st.data(), tau.data(), launched, 0, 0, 0, 0, 0);
+  if (warm && rc == 0) {  // second tick on the same records: the stored working sets are proposed to the block start
+    rc = emul_solve_ex(raw ? nullptr : buf.data(), raw ? buf.data() : nullptr, B, N, 0.04f, 500.f, 500, 1, w.data(), w64.data(),
+                       st.data(), tau.data(), launched, 0, 0, 0, 0, 0);
+    for (int i = 0; i < B; i++)
+      if (((st[i] >> 8) & 0xfff) != 0) rc = 3;  // proposing the optimal set must need no change at all
+  }
   int bad = 0;
   for (int i = 0; i < B; i++) bad += (st[i] & 0xff) != 0;
   printf("rc %d B %d launched %d %d %d not_converged %d\n", rc, B, launched[0], launched[1], launched[2], bad);

@@ -487,6 +487,11 @@ def test_closed_loop_of_kernel_sources(emul, oracle):
         assert (interface.status_code(st) == 0).all()
         return w, st
 
+    # third loop: the kernels' loop again, but every tick proposes the previous tick's working set (hmpc_rollout_device's
+    # warm start) — must stay on the cold loops' trajectory and need far fewer working-set changes
+    s_w, l_w = states.copy(), loop.copy()
+    ws = np.zeros((B, emul.emul_ws_ints()), np.int32)
+    warm_changes, cold_changes = 0, 0
     for t in range(T):
         # host-driven loop
         recs = _host_prepared(states, N)
@@ -499,9 +504,28 @@ def test_closed_loop_of_kernel_sources(emul, oracle):
         emul.emul_prepare(_p(s_k), B, N, ctypes.c_double(0.04), _p(packed))
         w_k, st_k = solve(packed)
         emul.emul_advance(_p(s_k), _p(l_k), B, N, ctypes.c_double(0.04), _p(w_k), _p(st_k))
+        # warm loop
+        packed = np.zeros((B, stride), np.uint8)
+        emul.emul_prepare(_p(s_w), B, N, ctypes.c_double(0.04), _p(packed))
+        emul.emul_set_ws(_p(ws), 1)
+        w_w = np.zeros((B, 12 * N), np.float32)
+        st_w = np.full(B, -1, np.int32)
+        assert emul.emul_solve_ex(_p(packed), None, B, N, ctypes.c_float(0.04), ctypes.c_float(500.0), 500, 1, _p(w_w), None, _p(st_w),
+                                  None, None, None, None, None, None, None) == 0
+        emul.emul_set_ws(None, 0)
+        assert (interface.status_code(st_w) == 0).all()
+        assert np.abs(w_w.astype(np.float64) - w_k).max() < 1e-5 * np.abs(w_k).max()   # same optimum (float output)
+        if t > 0:
+            warm_changes += int(interface.status_iters(st_w).sum())
+            cold_changes += int(interface.status_iters(st_k).sum())
+        emul.emul_advance(_p(s_w), _p(l_w), B, N, ctypes.c_double(0.04), _p(w_w), _p(st_w))
+        for f in ("position", "vWorld", "orientation", "omegaWorld", "rpy", "leg_p", "world_position_desired"):
+            assert np.abs(s_w[f] - states[f]).max() < 1e-6, (t, f, np.abs(s_w[f] - states[f]).max())
         for f in ("position", "vWorld", "orientation", "omegaWorld", "rpy", "leg_p", "world_position_desired"):
             assert np.abs(s_k[f] - states[f]).max() < 1e-9, (t, f, np.abs(s_k[f] - states[f]).max())
         assert np.array_equal(s_k["gait"], states["gait"])
         assert np.abs(l_k["feet_world"] - loop["feet_world"]).max() < 1e-9
     assert (l_k["failures"] == 0).all() and np.array_equal(l_k["ticks"], np.full(B, T))
     assert np.array_equal(l_k["iters_total"], loop["iters_total"])
+    print("closed loop of kernel sources: working-set changes per tick: cold %.2f, warm %.2f" % (cold_changes / (B * (T - 1)), warm_changes / (B * (T - 1))))
+    assert warm_changes < 0.5 * cold_changes
