@@ -52,7 +52,7 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 // float32 values; the sweep leaves float64 there.
 __host__ __device__ constexpr int toff(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
 
-__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride, int nwarps)
+__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride, int nwarps, bool use_T = true)
 {
   Layout L{};
   const int n = 6 * nb_cap;
@@ -69,7 +69,7 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.uni = o;
   int s = L.uni;  // solver view; one slot more than the capacity: the entering row needs one while a blocking row leaves
   const int ns = qmax + 1;
-  L.T = s;    s += ns * n * 8;                      // H^-1 a_j of every working-set slot
+  L.T = s;    s += (use_T ? ns : 1) * n * 8;        // H^-1 a_j of every working-set slot (without the cache: of the entering row)
   L.Sv = s;   s += ns * (ns + 1) / 2 * 8;           // (A_W H^-1 A_W')^-1, packed lower rows
   L.lam = s;  s += ns * 8;
   L.dv = s;   s += 2 * (ns + 2) * 8;                // step-direction scratch / double-buffered pivot column of the block start
@@ -105,17 +105,13 @@ __host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12
 // class 0 (a walking gait ends with about one active row per stance step; 15 at N = 10), 31 for class 1; an instance that needs more
 // escalates to the next class (class 2 = class 1's size with as many slots as shared memory holds).
 __host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
-__host__ __device__ constexpr int class_warps(int N, int cls);
+// The H^-1 a_j cache costs (qmax + 1) * n doubles: the long-horizon double-support class (extension configs) does without
+// it — its primal steps go through a full H^-1 product instead — and spends the room on working-set capacity.
+__host__ __device__ constexpr bool class_use_T(int N, int cls) { return cls == 0 || N <= 10; }
 __host__ __device__ constexpr int class_qmax(int N, int cls)
 {
-  const int nb = class_nb_cap(N, cls), n = 6 * nb;
-  int q = cls == 0 ? N + 5 : 31;  // (the block start handles up to 31 rows: one mask word)
-  if (cls == 1 && N > 10) {
-    // long horizons (extension configs): double-support optima hold more rows than 31 — as many slots as one SM's
-    // shared memory leaves (the block start is skipped there, the plain dual iteration runs)
-    const int rs = record_stride(N), nw = class_warps(N, cls);
-    while (q < 2 * N + 16 && make_layout(N, nb, q + 1, rs, nw).total <= 226 * 1024) q++;
-  }
+  const int n = 6 * class_nb_cap(N, cls);
+  const int q = cls == 0 ? N + 5 : (class_use_T(N, cls) ? 31 : 96);  // (the block start handles up to 31 rows: one mask word)
   return q < n ? q : n;
 }
 // warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (3 blocks of 10 per warp)
@@ -127,7 +123,7 @@ __host__ __device__ constexpr int class_warps(int N, int cls)
 }
 __host__ __device__ constexpr Layout class_layout(int N, int cls, int nwarps)
 {
-  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N), nwarps);
+  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N), nwarps, class_use_T(N, cls));
 }
 
 struct KernelArgs {
@@ -148,6 +144,7 @@ struct KernelArgs {
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
+  int use_T;                     // 1: the shared-memory carve-up holds the H^-1 a_j cache (runtime-layout launches; fixed: yes)
   int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
   int warm_start;                // 1: propose the working set in `ws_state` (previous tick) to the block start
   int ws_shift;                  // MPC steps the horizon moved since that tick (the closed loop: 1)
@@ -937,6 +934,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   const int nb_cap = FIX ? class_nb_cap(NF, CLS) : ka.nb_cap;
   const int qmax = FIX ? class_qmax(NF > 0 ? NF : 1, CLS) : ka.qmax;
   const int rec_stride = FIX ? record_stride(NF) : ka.rec_stride;
+  const bool useT = FIX ? true : (ka.use_T != 0);
   Layout L;
   if constexpr (FIX) {
     constexpr Layout LC = class_layout(NF, CLS, NW);
@@ -1584,7 +1582,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // minimum is a masked REDUX over the block's ten lanes, each entry of [S | b] lives in one thread's register during a
     // Gauss-Jordan sweep with one barrier per pivot.  Any doubt (capacity, a non-positive pivot) falls back to the plain
     // iteration from the unconstrained minimiser.
-    if (qmax <= 31) {
+    if (qmax <= 31 && useT) {
       int* newslot = reinterpret_cast<int*>(rr);       // [nadd] slots of the entering rows (rr is not live yet)
       double* colb = dvs;                              // [2][qmax + 3] pivot column, b_p and 1/d, double-buffered
       const int cst = qmax + 3;
@@ -1815,7 +1813,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const int kp = p / 10, nip = (blk_sl[kp] & 1) * 10 + (p - 10 * kp);
       const double* np_ = nrm + nip * 6;
       const int f = flags[7];  // slot the entering row will take
-      double* Tf = T + f * n;
+      double* Tf = useT ? T + f * n : T;
       if (isvar) Tf[vi] = hinv_dot6(Hd, vi, 6 * kp, np_);
       __syncthreads();
 
@@ -1931,18 +1929,37 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (decision >= 2) { code = (decision == 2) ? ST_INFEASIBLE : ST_WS_CAP; break; }
         const double t = dsc[0];
         // primal step direction z = t_p - sum_j r_j t_j, x += t z
-        if (isvar) {
-          const int qhe = flags[8];
-          double z0 = Tf[vi], z1 = 0.0;
-          int j = 0;
-          for (; j + 1 < qhe; j += 2) {
-            z0 = fma(-rr[j], T[j * n + vi], z0);
-            z1 = fma(-rr[j + 1], T[(j + 1) * n + vi], z1);
+        if (useT) {
+          if (isvar) {
+            const int qhe = flags[8];
+            double z0 = Tf[vi], z1 = 0.0;
+            int j = 0;
+            for (; j + 1 < qhe; j += 2) {
+              z0 = fma(-rr[j], T[j * n + vi], z0);
+              z1 = fma(-rr[j + 1], T[(j + 1) * n + vi], z1);
+            }
+            if (j < qhe) z0 = fma(-rr[j], T[j * n + vi], z0);
+            const double z = z0 + z1;
+            zb[vi] = z;
+            xreg = fma(t, z, xreg);
           }
-          if (j < qhe) z0 = fma(-rr[j], T[j * n + vi], z0);
-          const double z = z0 + z1;
-          zb[vi] = z;
-          xreg = fma(t, z, xreg);
+        } else {
+          // no cache: z = t_p - H^-1 (A_W' r) through one full product (gq, padded to whole tiles, holds A_W' r)
+          if (isvar) {
+            const int qhe = flags[8], kb = vi / 6, c = vi - 6 * kb;
+            double acc = 0.0;
+            for (int j = 0; j < qhe; j++) {
+              const int w = wsl[j];
+              if ((w >> 8) == kb) acc = fma(rr[j], nrm[(w & 0xff) * 6 + c], acc);
+            }
+            gq[vi] = acc;
+          }
+          __syncthreads();
+          if (isvar) {
+            const double z = Tf[vi] - hinv_rowdot(Hd, vi, NT8, gq);
+            zb[vi] = z;
+            xreg = fma(t, z, xreg);
+          }
         }
         __syncthreads();
         if (iscon && t != 0.0) se = fma(t, dot6(ne, zb + 6 * ke), se);
@@ -1961,22 +1978,47 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
 
     HMPC_STAMP(5);
-    // polish: x from scratch with the final multipliers, x = x0 + sum_j lam_j H^-1 a_j
+    // polish: x from scratch with the final multipliers, x = x0 + sum_j lam_j H^-1 a_j.
+    // The explicit Schur-complement inverse drifts when many nearly dependent rows are active (massively degenerate
+    // optima): large working sets get two rounds of refinement against the rows' own slacks at the composed x,
+    // lam += S^-1 (d_W - A_W x), which vanish at the exact multipliers.  The usual ~N rows do not need it.
     __syncthreads();
     const int qhf = flags[9];
-    // The explicit Schur-complement inverse drifts when many nearly dependent rows are active (massively degenerate
-    // optima): refine the multipliers of the final working set against the exact rows S_ij = a_i' t_j,
-    // lam += S^-1 (b - S lam), b_i = d_i - a_i' x0.  Large working sets only; the usual ~N rows do not need it.
-    if (wid == 0 && code == ST_OK && q > 24) {
-      for (int round = 0; round < 2; round++) {
+    const int nref = (code == ST_OK && q > 24) ? 2 : 0;
+    for (int round = 0;; round++) {
+      if (code == ST_OK && !useT) {
+        if (isvar) {
+          const int kb = vi / 6, c = vi - 6 * kb;
+          double acc = 0.0;
+          for (int j = 0; j < qhf; j++) {
+            const int w = wsl[j];
+            if (((amask[j >> 5] >> (j & 31)) & 1u) && (w >> 8) == kb) acc = fma(lam[j], nrm[(w & 0xff) * 6 + c], acc);
+          }
+          gq[vi] = acc;
+        }
+        __syncthreads();
+      }
+      if (isvar) {
+        double acc = xreg;
+        if (code == ST_OK) {
+          acc = x0[vi];
+          if (useT) {
+            for (int j = 0; j < qhf; j++)
+              if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
+          } else {
+            acc += hinv_rowdot(Hd, vi, NT8, gq);
+          }
+        }
+        zb[vi] = acc;
+      }
+      __syncthreads();
+      if (round == nref) break;
+      if (wid == 0) {
         for (int s2 = lane; s2 < qhf; s2 += 32) {
           double acc = 0.0;
           if ((amask[s2 >> 5] >> (s2 & 31)) & 1u) {
             const int w = wsl[s2], ki = w >> 8, te = (w & 0xff) % 10;
-            const double* ni = nrm + (w & 0xff) * 6;
-            acc = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(ni, x0 + 6 * ki);
-            for (int j = 0; j < qhf; j++)
-              if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(-lam[j], dot6(ni, T + j * n + 6 * ki), acc);
+            acc = ((te == 5) ? -(double)0.01f : ((te == 9) ? -fz[ki] : 0.0)) - dot6(nrm + (w & 0xff) * 6, zb + 6 * ki);
           }
           dvs[s2] = acc;
         }
@@ -1988,20 +2030,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           for (int j = 0; j < qhf; j++) acc = fma((j <= s2) ? Sv[rs + j] : Sv[tri(j) + s2], dvs[j], acc);
           lam[s2] = fmax(0.0, lam[s2] + acc);
         }
-        __syncwarp();
       }
+      __syncthreads();
     }
-    __syncthreads();
-    if (isvar) {
-      double acc = xreg;
-      if (code == ST_OK) {
-        acc = x0[vi];
-        for (int j = 0; j < qhf; j++)
-          if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
-      }
-      zb[vi] = acc;
-    }
-    __syncthreads();
 
     // working set for the next tick (closed loop): (step, leg) and normal index of every active row
     if (ka.ws_state && wid == 0) {
