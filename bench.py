@@ -122,7 +122,9 @@ class ClockSampler:
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
     `ncu --set full` summary of this round (profiles/ncu_r1_final_summary.txt); None if absent."""
-    p = os.path.join(ROOT, "profiles", "ncu_r1_final_summary.txt")
+    p = os.path.join(ROOT, "profiles", "ncu_r2_final_summary.txt")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "ncu_r1_final_summary.txt")
     if not os.path.exists(p):
         return None
     tot, unit_mul = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -144,53 +146,73 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback (B200_PROFILING.md)"}
 
 
-def cpu_reference_leg(records, steps: int, warmup: int, sample_per_step: int, budget_s: float = 150.0):
-    """Times the reference's CPU implementation (oracle/_ref: restated solve_mpc + the reference's qpOASES)
-    with one independent solver per host core (the reference is single-threaded and non-reentrant, so
-    cores are used as independent processes).  Returns (QP/s, cores, per-solve seconds array, solves per step).
-    If the first (warm-up) step shows that warmup+steps steps would exceed `budget_s`, the per-step sample is
-    shrunk (never below 4 solves per core) so that the whole run stays within a few minutes."""
-    import multiprocessing as mp
-
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    ctx = mp.get_context("fork")
-
-    def make_jobs(n):
-        chunks = np.array_split(np.arange(n), cores)
-        return [(records[c % len(records)],) for c in chunks if len(c)]
-
-    total_solves = 0
-    lat = []
-    t_total = 0.0
-    jobs = make_jobs(sample_per_step)
-    with ctx.Pool(cores) as pool:
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            outs = pool.map(_cpu_worker, jobs, chunksize=1)
-            dt = time.perf_counter() - t0
-            if it == 0 and dt * (warmup + steps) > budget_s:
-                sample_per_step = max(4 * cores, int(sample_per_step * budget_s / (dt * (warmup + steps))))
-                jobs = make_jobs(sample_per_step)
-            if it >= warmup:
-                t_total += dt
-                total_solves += sum(len(o) for o in outs)
-                lat.extend(np.concatenate(outs).tolist())
-    return total_solves / t_total, cores, np.array(lat), sample_per_step
-
-
-def cpu_sample_size() -> int:
-    """Solves per step for the CPU leg: 64 per core (~0.1 s of work per core per step at ~1.5 ms/solve),
-    cycling through the 1024 records of the workload."""
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return 64 * cores
+def _physical_cpus() -> list[int]:
+    """One logical CPU per physical core among the CPUs this process may use (first sibling of every core)."""
+    allowed = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    seen, out = set(), []
+    for c in allowed:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            out.append(c)
+    return out
 
 
 def _cpu_worker(args):
+    """One solver pinned to one core, running for a fixed wall time: returns (end time, seconds) of every solve."""
+    cpu, recs, t_end = args
+    try:
+        os.sched_setaffinity(0, {cpu})
+    except (AttributeError, OSError):
+        pass
     from oracle import oracle_py as O
 
-    (recs,) = args
     setup = O.make_setup(HORIZON)
-    return O.time_solves(recs, setup, len(recs))
+    O.time_solves(recs[:4], setup, 4)  # page in the library and the solver's buffers
+    stamps, lats = [], []
+    i = 0
+    while time.monotonic() < t_end:
+        lo = (i * 16) % len(recs)
+        chunk = recs[lo:lo + 16] if lo + 16 <= len(recs) else recs[:16]
+        lat = O.time_solves(chunk, setup, len(chunk))
+        now = time.monotonic()
+        stamps.append(now)
+        lats.append(np.asarray(lat))
+        i += 1
+    return np.array(stamps), lats
+
+
+def cpu_reference_leg(records, steps: int, warmup: int, window_s: float | None = None, budget_s: float = 150.0):
+    """Times the reference's CPU implementation of the path — oracle/_ref/liboracle_mpc.so: solve_mpc restated
+    (bit-identical to the reference's own sources compiled against a stand-in, tests/test_reference_compiled.py) + the
+    reference's qpOASES 3.2 compiled unchanged — with one independent solver per PHYSICAL core (the reference is
+    single-threaded and non-reentrant), each pinned to its core and running for a fixed wall time with no barrier between
+    steps.  A "step" is a window of `window_s` seconds; the first `warmup` windows are not counted.
+    Returns (QP/s, cores, per-solve seconds, window_s, per-core QP/s)."""
+    import multiprocessing as mp
+
+    cpus = _physical_cpus()
+    cores = len(cpus)
+    if window_s is None:
+        window_s = min(1.0, budget_s / (warmup + steps))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.monotonic() + 1.0  # workers start up, then everybody runs until the common deadline
+        t_end = t0 + (warmup + steps) * window_s
+        outs = pool.map(_cpu_worker, [(c, records, t_end) for c in cpus], chunksize=1)
+    lo, hi = t0 + warmup * window_s, t_end
+    solves, lat = 0, []
+    for stamps, lats in outs:
+        for ts, l in zip(stamps, lats):
+            if lo < ts <= hi:
+                solves += len(l)
+                lat.append(l)
+    lat = np.concatenate(lat) if lat else np.zeros(1)
+    qps = solves / (hi - lo)
+    return qps, cores, lat, window_s, qps / cores
 
 
 def run_reference(args):
@@ -205,21 +227,24 @@ def run_reference(args):
     if not O.has_qpoases():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref built without qpOASES (no /root/reference, no prebuilt .so)"}))
         return
-    sample = cpu_sample_size()
-    qps, cores, lat, sample = cpu_reference_leg(recs, args.steps, max(args.warmup, 1), sample)
+    qps, cores, lat, win, per_core = cpu_reference_leg(recs, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sample / qps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 assembly / f64 solve",
-        "data": "synthetic", "config": {"workload": "configs[1]: batch=1024 Hector walking-gait states, horizon=10 (bounded sample per step)",
-                                       "horizon": HORIZON, "sample_per_step": sample},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{sample} solves per step ({sample // cores} per core, cycling through the 1024 records), one solver process per core",
-                         "what": "oracle/_ref/liboracle_mpc.so: solve_mpc restated without Eigen (bit-identical to the reference's own sources compiled against a stand-in, tests/test_reference_compiled.py) + the reference's qpOASES 3.2 compiled unchanged",
-                         "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)},
+        "ms_per_step": win * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 assembly / f64 solve",
+        "data": "synthetic", "config": {"workload": "configs[1]: batch=1024 Hector walking-gait states, horizon=10 — same records as the GPU arm; a step is a fixed wall-time window over them",
+                                       "horizon": HORIZON, "window_s": win},
+        "cpu_baseline": cpu_baseline_entry(qps, cores, lat, win, per_core, args.steps),
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_entry(qps, cores, lat, win, per_core, steps):
+    return {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} windows of {win:.2f} s, one solver process pinned to each of the {cores} physical cores, cycling through the 1024 records, no barrier between windows",
+            "what": "oracle/_ref/liboracle_mpc.so: solve_mpc restated without Eigen (bit-identical to the reference's own sources compiled against an Eigen stand-in, oracle/_ref/libref_mpc.so, tests/test_reference_compiled.py) + the reference's qpOASES 3.2 compiled unchanged",
+            "per_core_qps": per_core, "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)}
 
 
 def main():
@@ -229,6 +254,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="robots per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--workload", default="walk", choices=["walk", "mixed"],
+                    help="walk: BASELINE configs[1] (walking-gait states); mixed: configs[2] (25 %% stand / 75 %% walk, randomized)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -255,8 +282,9 @@ def main():
     B, N = args.batch, HORIZON
     K, W = args.steps, args.warmup
 
-    # synthetic walking-gait states (configs[1]); each rank gets its own shard (different seed)
-    recs, inputs = scenarios.make_batch(2, B, horizon=N, seed=scenarios.config_seed(2) + 1000 * rank)
+    # synthetic states (configs[1] walking gait / configs[2] mixed); each rank gets its own shard (different seed)
+    cfg = 2 if args.workload == "walk" else 3
+    recs, inputs = scenarios.make_batch(cfg, B, horizon=N, seed=scenarios.config_seed(cfg) + 1000 * rank)
     mpc = interface.BatchedMPC(B, N, device=local_rank)
     stride = interface.record_bytes(N)
     packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
@@ -291,38 +319,37 @@ def main():
     total_ms = e_all0.elapsed_time(e_all1)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     # ---------------- end-to-end leg (host buffers through the C-ABI) ----------------
-    # N = 1: the reference-facing call hmpc_solve_batch (pack + H2D + kernels + D2H inside).
-    # N > 1: the batch spans devices, so results are exchanged ON DEVICE — per step every rank packs its shard
-    # into pinned memory (C-ABI hmpc_pack_records), solves with hmpc_solve_device reading it in place, joins ONE NCCL
-    # all_gather of the float results, and reads the gathered result back to the host.
-    if world == 1:
+    # Every rank ticks its own slice through sharding.ShardedMPC -> hmpc_solve_batch_sharded: the reference-facing call on
+    # the caller's registered update_data_t / result arrays (records read and double wrenches written in place over PCIe),
+    # this rank's slice back on ITS host arrays.  N > 1: the library also enqueues the path's ONE collective, an
+    # ncclAllGather of the float wrenches into a device buffer on every rank, on a side stream beside the next tick; the
+    # last gather is waited for inside the timed region.  Same code path at N = 1 (no gather).
+    from hector_simulation_b200 import sharding
+
+    def bcast(b):
+        box = [b]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    if world > 1:
+        factory = lambda bl: sharding.GpuBackend(bl, N, rank, world, local_rank, bcast)
+    else:
+        factory = None
+    recs_c = np.ascontiguousarray(recs)
+    if world > 1:
+        sh = sharding.ShardedMPC(world * B, N, rank, world, factory, scenarios.UPDATE_DTYPE)
+        out_w, out_s = sh.out_w, sh.out_s
+
+        def e2e_step():
+            sh.tick(recs_c)
+    else:
         out_w = np.zeros((B, 12 * N), dtype=np.float64)  # caller-owned result buffers, reused every tick
         out_s = np.zeros(B, dtype=np.int32)
-        recs = np.ascontiguousarray(recs)
-        # a control loop reuses its record / result arrays every tick: registered once, hmpc_solve_batch lets the GPU
-        # read the update_data_t records and write the double wrenches in place (same bytes over PCIe, no staging)
-        mpc.pin(recs, out_w, out_s)
+        mpc.pin(recs_c, out_w, out_s)
 
         def e2e_step():
-            mpc.solve_batch(recs, out=(out_w, out_s))
-    else:
-        import ctypes
-
-        h_in = torch.empty((B, stride), dtype=torch.uint8).pin_memory()
-        d_w1 = torch.empty((B, 12 * N), dtype=torch.float32, device="cuda")
-        d_s1 = torch.empty((B,), dtype=torch.int32, device="cuda")
-        d_all = torch.empty((world * B, 12 * N), dtype=torch.float32, device="cuda")
-        h_all = torch.empty((world * B, 12 * N), dtype=torch.float32).pin_memory()
-        h_st = torch.empty((B,), dtype=torch.int32).pin_memory()
-        recs_c = np.ascontiguousarray(recs)
-
-        def e2e_step():
-            interface.lib().hmpc_pack_records(recs_c.ctypes.data, B, N, ctypes.c_void_p(h_in.data_ptr()))
-            mpc.solve_device(h_in, B, d_w1, d_s1)  # pinned + mapped: the kernels pull the packed records over PCIe
-            dist.all_gather_into_tensor(d_all, d_w1)
-            h_all.copy_(d_all, non_blocking=True)
-            h_st.copy_(d_s1, non_blocking=True)
-            torch.cuda.synchronize()
+            mpc.solve_batch(recs_c, out=(out_w, out_s))
     for _ in range(W):
         e2e_step()
     barrier()
@@ -332,8 +359,34 @@ def main():
         t1 = time.perf_counter()
         e2e_step()
         e2e_lat.append(time.perf_counter() - t1)
+    if world > 1:
+        sh.backend.wait()  # the last tick's gather
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert (interface.status_code(out_s[:B]) == 0).all(), "non-converged instances in the end-to-end leg"
+    # after the timed region: what the gather delivered (every rank's slice, on this device) against the oracle
+    parity = None
+    if world > 1:
+        whole = sh.whole_batch()
+        if rank == 0:
+            try:
+                from oracle import oracle_py as O
+
+                if O.has_qpoases():
+                    worst, checked = 0.0, 0
+                    for r in range(world):
+                        rr, _ = scenarios.make_batch(cfg, B, horizon=N, seed=scenarios.config_seed(cfg) + 1000 * r)
+                        idx = np.arange(r % 7, B, max(1, B // 6))[:6]
+                        ref, info = O.solve_batch(rr[idx], O.make_setup(N))
+                        got = whole[r * B + idx].astype(np.float64)
+                        ok = info[:, 0] == 0
+                        e = np.linalg.norm(got[ok, :12] - ref[ok, :12], axis=1) / np.maximum(np.linalg.norm(ref[ok, :12], axis=1), 1e-9)
+                        worst = max(worst, float(e.max()))
+                        checked += int(ok.sum())
+                    parity = {"gathered_vs_oracle_worst_rel_err": worst, "robots_checked": checked, "ranks": world, "contract": 1e-4}
+            except Exception as e:  # reported, never required
+                parity = {"unavailable": str(e)}
+        sh.close()
     clocks = sampler.stop()
 
     t = torch.tensor([total_ms, e2e_s * 1e3, float(np.percentile(step_ms, 99))], dtype=torch.float64, device="cuda")
@@ -352,7 +405,7 @@ def main():
     e2e_qps = world * B * K / (e2e_ms * 1e-3)
     peaks = measured_peaks()
     k_mean = float(iters.mean())
-    nv = 6.0 * N  # walking gait: one stance leg per step
+    nv = 6.0 * N if args.workload == "walk" else 6.0 * N * 1.25  # walking gait: one stance leg per step; mix: a quarter stands
     flops = algorithmic_flops_per_qp(N, nv, k_mean) * B
     byts = algorithmic_bytes_per_qp(N) * B
     kern_ms = float(np.mean(step_ms))  # all launches of one step (classification + one per size class)
@@ -362,26 +415,29 @@ def main():
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 assembly (bit-exact to reference arithmetic) / f64 solve", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch=1024 Hector walking-gait states per GPU, horizon=10, cold start every tick",
+        "config": {"workload": ("configs[1]: batch=%d Hector walking-gait states per GPU, horizon=10, cold start every tick" % B) if args.workload == "walk" else
+                               ("configs[2]: %d randomized CoM/velocity/contact-schedule states per GPU (25 %% stand / 75 %% walk), horizon=10, cold start every tick" % B),
                    "horizon": N, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}",
                    "l2": f"ring of {ring} input/output buffers ({ring * B * (stride + 48 * N + 4) / 1e6:.0f} MB > L2)"},
         "latency_ms": {"batch_p50": float(np.percentile(step_ms, 50)), "batch_p99": p99_step_ms,
                        "note": "device time for the whole 1024-robot batch; every robot's result is ready within it"},
         "solver": {"mean_working_set_changes": k_mean, "max": int(iters.max())},
-        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int((world * B * 48 * N + B * 4) if world > 1 else B * (96 * N + 4)),
-                "transfer": ("pack into pinned memory, kernels read it over PCIe, device all_gather, D2H copy" if world > 1 else
-                             "in place: kernels gather the live 720 B of every host update_data_t over PCIe and store double wrenches + status into the caller's registered arrays"),
+        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(B * stride), "d2h_bytes_per_step": int(B * (96 * N + 4)),
+                "transfer": "in place, per rank: kernels gather the live 720 B of every host update_data_t over PCIe and store double wrenches + status into the caller's registered arrays"
+                            + ("; plus ONE ncclAllGather of the float wrenches (device to device, %d B per rank) on a side stream beside the next tick, last one waited for inside the timed region" % (B * 48 * N) if world > 1 else ""),
                 "ms_per_step": e2e_ms / K, "latency_ms_p99": float(np.percentile(e2e_lat, 99) * 1e3)},
-        "gpu_launches": int(K * mpc.launches_per_solve),  # per step: 1 classification kernel + 1 solve kernel per size class
+        "gpu_launches": int(K * mpc.launches_per_solve),  # per step: one solve-kernel launch per size class (class 0 classifies on the way)
         "launch_config": {"class0": mpc.class_config(0), "class1": mpc.class_config(1)},
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["bf16_tflops"],
                      "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes per launch (dominant kernel, 1024 QPs; algorithmic = %d)" % byts,
                      "peak_source": peaks["_source"],
-                     "note": "algorithmic flops (SURVEY.md §8d: F_asm + k*F_it, nv=6N) / mean kernel time; the kernel's math is fp32 FMUL/FADD + fp64 DFMA on CUDA cores, see DESIGN.md §6",
+                     "note": "algorithmic flops (SURVEY.md §8d: F_asm + k*F_it, nv=6N) / mean step time against the measured bf16 tensor peak (the schema's denominator); the kernel's tensor-pipe work is the fp64 sweep (mma.m8n8k4.f64), whose own pipe peak is ~37 TFLOP/s (tests/tools/ubench.cu), the assembly is bit-exact fp32 on CUDA cores — DESIGN.md §6",
                      "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                              "bytes_per_qp": algorithmic_bytes_per_qp(N)}},
     }
+    if parity is not None:
+        line["parity"] = parity
     if world == 1:
         # one robot through the reference's own boundary (setup_problem / update_problem_data / get_solution),
         # the call sequence of ConvexMPCLocomotion.cpp:410-430 — per-tick latency against the 500 Hz (2 ms) deadline
@@ -436,23 +492,48 @@ def main():
             ms5 = c0.elapsed_time(c1)
             lo5 = d_clo.cpu().numpy().view(scenarios.ROLLOUT_DTYPE).reshape(Bc)
             z5 = d_cst.cpu().numpy().view(scenarios.STATE_DTYPE).reshape(Bc)["position"][:, 2]
-            line["closed_loop"] = {"workload": "configs[4]: batch=4096 walking robots, 200 consecutive ticks, cold start each tick, loop resident on the device",
+            line["closed_loop"] = {"workload": "configs[4]: batch=4096 walking robots, 200 consecutive ticks with warm start (previous tick's working set proposed), loop resident on the device",
                                    "value": Bc * Tc / (ms5 * 1e-3), "unit": UNIT, "ms_per_tick": ms5 / Tc, "failures": int(lo5["failures"].sum()),
                                    "mean_working_set_changes": float(lo5["iters_total"].sum() / lo5["ticks"].sum()),
+                                   "mean_working_set_changes_note": "changes relative to the warm-start proposal (a cold start installs ~12 rows per tick)",
                                    "body_height_min_max": [float(z5.min()), float(z5.max())]}
             mpc5.close()
         except Exception as e:
             line["closed_loop"] = {"unavailable": str(e)}
+        # other BASELINE configs on this GPU, device-resident, short runs (extra keys): configs[2]'s mix at 8192 robots and
+        # the horizon-16 extension at 4096
+        extra = {}
+        for name, cfg_x, Bx, Nx in (("configs2_mix_8192_robots", 3, 8192, 10), ("configs3_horizon16_4096_robots", 4, 4096, 16),
+                                    ("configs3_horizon5_4096_robots", 4, 4096, 5)):
+            try:
+                rx, _ = scenarios.make_batch(cfg_x, Bx, horizon=Nx)
+                mx = interface.BatchedMPC(Bx, Nx, device=local_rank)
+                px = torch.from_numpy(interface.pack_records(rx, Nx)).cuda()
+                wx = torch.zeros((Bx, 12 * Nx), dtype=torch.float32, device="cuda")
+                sx = torch.zeros((Bx,), dtype=torch.int32, device="cuda")
+                for _ in range(2):
+                    mx.solve_device(px, Bx, wx, sx)
+                torch.cuda.synchronize()
+                x0e, x1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                x0e.record(stream)
+                for _ in range(5):
+                    mx.solve_device(px, Bx, wx, sx)
+                x1e.record(stream)
+                torch.cuda.synchronize()
+                msx = x0e.elapsed_time(x1e) / 5
+                codes = np.bincount(interface.status_code(sx.cpu().numpy()), minlength=5)
+                extra[name] = {"value": Bx / (msx * 1e-3), "unit": UNIT, "ms_per_step": msx, "not_converged": int(codes[1:].sum())}
+                mx.close()
+            except Exception as e:
+                extra[name] = {"unavailable": str(e)}
+        line["other_configs"] = extra
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import oracle_py as O
 
             if O.has_qpoases():
-                sample = cpu_sample_size()
-                cq, cores, lat, sample = cpu_reference_leg(recs, 3, 1, sample)
-                line["cpu_baseline"] = {"value": cq, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": f"3 steps of {sample} solves (64 per core, cycling through the {B} records), one solver process per core (restated solve_mpc + the reference's qpOASES 3.2)",
-                                        "latency_ms_p50": float(np.percentile(lat, 50) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3)}
+                cq, cores, lat, win, per_core = cpu_reference_leg(recs, 10, 2, window_s=1.0)
+                line["cpu_baseline"] = cpu_baseline_entry(cq, cores, lat, win, per_core, 10)
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"unavailable": str(e)}
     print(json.dumps(line))

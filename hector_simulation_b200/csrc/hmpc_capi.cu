@@ -3,6 +3,7 @@
 // Part 1 re-exports the reference's boundary (convexMPC_interface.h:39-43) on top of a one-robot
 // context; part 2 is the batched interface.  There is no CPU solve path in this library.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <chrono>
 #include <cstddef>
@@ -143,6 +144,15 @@ struct hmpc_ctx {
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};  // further chunks of the pipelined host path
   HostPool* pool = nullptr;        // helper threads for packing / widening (large batches only)
   int max_iter = 500;  // same cap as the reference's nWSR (SolverMPC.cpp:584)
+  // multi-GPU (one process per GPU, batch sharded): NCCL communicator + double-buffered float results for the gather
+  void* nccl = nullptr;            // ncclComm_t
+  int shard_rank = 0, shard_world = 1;
+  float* shard_buf[2] = {nullptr, nullptr};   // [max_batch][12N] this rank's results of tick t / t+1
+  float* shard_out = nullptr;      // where the kernels of the current sharded tick also store float results (else null)
+  unsigned shard_tick = 0;
+  bool shard_used = false;         // the in-place chain stored this tick's floats (else the staged path ran)
+  cudaStream_t gstream = nullptr;  // the gather runs here, behind `solved`, beside the next tick
+  cudaEvent_t solved = nullptr, gathered[2] = {nullptr, nullptr};
   int* d_ws = nullptr;             // [max_batch][WS_STATE_INTS] working sets of the previous tick (closed-loop warm start)
   int warm_start = 1;              // hmpc_rollout_device proposes them to the next tick (HMPC_WARM_START=0: cold start every tick)
   int block_rounds = 4;  // block start of the active-set stage (HMPC_BLOCK_ROUNDS=0: plain dual iteration, for A/B runs)
@@ -351,6 +361,140 @@ HMPC_EXTERNC int hmpc_pack_records(const update_data_t* in, int n, int horizon, 
 // ---------------------------------------------------------------------------------------------------
 HMPC_EXTERNC const char* hmpc_last_error(void) { return g_err.c_str(); }
 
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU: one process per GPU, contiguous batch slices, identical kernels, no data-path collective;
+// ONE ncclAllGather of the float results when a consumer needs the whole batch on every device.  NCCL is looked up at
+// run time (libnccl.so.2 — the copy the process already holds when PyTorch is loaded), so the library has no link
+// dependency on it and single-GPU users never touch it.
+// ---------------------------------------------------------------------------------------------------
+struct Id128 { char b[128]; };  // ncclUniqueId, passed by value
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+namespace {
+NcclApi g_nccl;
+bool nccl_load()
+{
+  if (g_nccl.h) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_err = std::string("NCCL not found: ") + dlerror(); return false; }
+  g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+  g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+    g_err = "NCCL library lacks ncclGetUniqueId / ncclCommInitRank / ncclAllGather / ncclCommDestroy";
+    return false;
+  }
+  g_nccl.h = h;
+  return true;
+}
+bool nccl_fail(int rc, const char* what)
+{
+  if (rc == 0) return false;
+  g_err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+  return true;
+}
+void shard_release(hmpc_ctx* c)
+{
+  if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+  c->nccl = nullptr;
+  for (int i = 0; i < 2; i++) {
+    if (c->shard_buf[i]) cudaFree(c->shard_buf[i]);
+    if (c->gathered[i]) cudaEventDestroy(c->gathered[i]);
+    c->shard_buf[i] = nullptr;
+    c->gathered[i] = nullptr;
+  }
+  if (c->solved) cudaEventDestroy(c->solved);
+  if (c->gstream) cudaStreamDestroy(c->gstream);
+  c->solved = nullptr;
+  c->gstream = nullptr;
+}
+}  // namespace
+
+HMPC_EXTERNC int hmpc_shard_unique_id(void* id128)
+{
+  if (!id128) { g_err = "hmpc_shard_unique_id: null argument"; return HMPC_ERR_ARG; }
+  if (!nccl_load()) return HMPC_ERR_CUDA;
+  if (nccl_fail(g_nccl.GetUniqueId(id128), "ncclGetUniqueId")) return HMPC_ERR_CUDA;
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_shard_init(hmpc_ctx* c, int rank, int world, const void* id128)
+{
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) { g_err = "hmpc_shard_init: bad argument"; return HMPC_ERR_ARG; }
+  if (c->nccl) { g_err = "hmpc_shard_init: context already belongs to a shard group"; return HMPC_ERR_ARG; }
+  if (!nccl_load()) return HMPC_ERR_CUDA;
+  CK(cudaSetDevice(c->device));
+  Id128 id;
+  memcpy(id.b, id128, 128);
+  if (nccl_fail(g_nccl.CommInitRank(&c->nccl, world, id, rank), "ncclCommInitRank")) return HMPC_ERR_CUDA;
+  c->shard_rank = rank;
+  c->shard_world = world;
+  const size_t nw = (size_t)12 * c->horizon;
+  CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->solved, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaMalloc(&c->shard_buf[i], (size_t)c->max_batch * nw * sizeof(float)));
+    CK(cudaEventCreateWithFlags(&c->gathered[i], cudaEventDisableTiming));
+  }
+  return HMPC_OK;
+}
+
+HMPC_EXTERNC int hmpc_solve_batch_sharded(hmpc_ctx* c, const update_data_t* in_local, int B_local, double* wrench_local,
+                                          int* status_local, float* d_all)
+{
+  if (!c || !c->nccl) { g_err = "hmpc_solve_batch_sharded: call hmpc_shard_init first"; return HMPC_ERR_ARG; }
+  if (B_local < 1 || B_local > c->max_batch) { g_err = "hmpc_solve_batch_sharded: every rank needs 1 <= B_local <= capacity"; return HMPC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  const int par = (int)(c->shard_tick++ & 1u);
+  const size_t nw = (size_t)12 * c->horizon;
+  if (d_all) {
+    // this tick's kernels also leave float results in shard_buf[par]; the gather that last read it (two ticks ago)
+    // must be done before they overwrite it — a stream-side wait, the host does not block
+    CK(cudaStreamWaitEvent(c->stream, c->gathered[par], 0));
+    c->shard_out = c->shard_buf[par];
+  }
+  const int rc = hmpc_solve_batch(c, in_local, B_local, wrench_local, status_local);
+  const bool staged = d_all && c->shard_out && !c->shard_used;
+  c->shard_out = nullptr;
+  if (rc != HMPC_OK && rc != HMPC_ERR_NOT_CONVERGED) return rc;
+  if (d_all) {
+    if (staged) {
+      // the staged host path did not run the in-place chain: put the float results on the device for the gather
+      std::vector<float> tmp((size_t)B_local * nw);
+      for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (float)wrench_local[i];
+      CK(cudaMemcpyAsync(c->shard_buf[par], tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      CK(cudaEventRecord(c->solved, c->stream));
+    }
+    c->shard_used = false;
+    // the path's ONE collective: every rank's slice of float wrenches to every device, beside the next tick
+    CK(cudaStreamWaitEvent(c->gstream, c->solved, 0));
+    if (nccl_fail(g_nccl.AllGather(c->shard_buf[par], d_all, (size_t)B_local * nw, /* ncclFloat32 */ 7, c->nccl, c->gstream), "ncclAllGather"))
+      return HMPC_ERR_CUDA;
+    CK(cudaEventRecord(c->gathered[par], c->gstream));
+  }
+  return rc;
+}
+
+HMPC_EXTERNC int hmpc_shard_wait(hmpc_ctx* c)
+{
+  if (!c || !c->nccl) { g_err = "hmpc_shard_wait: call hmpc_shard_init first"; return HMPC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->gstream));
+  return HMPC_OK;
+}
+
 HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
 {
   if (!c) return;
@@ -364,6 +508,7 @@ HMPC_EXTERNC void hmpc_destroy(hmpc_ctx* c)
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->d_lists) cudaFree(c->d_lists);
   if (c->d_cls) cudaFree(c->d_cls);
+  shard_release(c);
   if (c->d_ws) cudaFree(c->d_ws);
   if (c->d_states) cudaFree(c->d_states);
   if (c->h_states) cudaFreeHost(c->h_states);
@@ -462,7 +607,8 @@ namespace {
 long long* g_dbg_clk = nullptr;  // profiling hook (hmpc_debug_set_clock_buffer)
 // classification pre-pass + one launch per class, all enqueued on `st`
 int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, double* d_wrench64, int* d_status,
-                  cudaStream_t st, int slot = 0, float* d_tau = nullptr, int* d_ws = nullptr, int ws_shift = 0, bool ws_read = false)
+                  cudaStream_t st, int slot = 0, float* d_tau = nullptr, int* d_ws = nullptr, int ws_shift = 0, bool ws_read = false,
+                  const update_data_t* raw = nullptr)
 {
   if (B > c->max_batch) { g_err = "batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
@@ -478,6 +624,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     const ClassCfg& k = c->cls[i];
     hmpc::KernelArgs ka = base_args(c, d_records, B, d_wrench32, d_status);
     ka.wrench64 = d_wrench64;
+    ka.raw_records = reinterpret_cast<const unsigned char*>(raw);
     ka.tau = d_tau;
     ka.warm_start = (d_ws && ws_read) ? 1 : 0;
     ka.ws_state = d_ws;
@@ -800,26 +947,22 @@ static int solve_batch_impl(hmpc_ctx* c, const update_data_t* in, const hmpc_sta
   // wants them — the call is host classification + launches + one synchronize
   if (in && zc_env != 0 && !c->pins.empty() && c->pinned(in, (size_t)B * sizeof(update_data_t)) &&
       c->pinned(wrench_out, (size_t)B * nw * sizeof(double)) && (!status || c->pinned(status, (size_t)B * sizeof(int)))) {
-    int* hblk = c->h_cls;
-    classify_host(c, in[0].gait, sizeof(update_data_t), B, hblk);
+    // the device-resident chain on the caller's records: class 0 classifies on the way, overflow escalates on the device
     int* ds = status ? status : reinterpret_cast<int*>(c->h_out + (size_t)c->max_batch * nw * 4);
     float* dt_ = tau_out ? reinterpret_cast<float*>(c->h_out + (size_t)c->max_batch * (nw * 4 + 4)) : nullptr;
-    int rc = enqueue_solve_hostlists(c, nullptr, B, hblk, nullptr, ds, c->stream, 0, dt_, true, in, wrench_out);
+    int rc = enqueue_solve(c, nullptr, B, c->shard_out, wrench_out, ds, c->stream, 0, dt_, nullptr, 0, false, in);
     if (rc != HMPC_OK) return rc;
+    if (c->shard_out) {
+      CK(cudaEventRecord(c->solved, c->stream));
+      c->shard_used = true;
+    }
     CK(cudaStreamSynchronize(c->stream));
-    bool all_ok = true, overflow = false;
-    for (int i = 0; i < B; i++) {
-      const int cd = HMPC_STATUS_CODE(ds[i]);
-      overflow |= (cd == hmpc::ST_WS_CAP);
-      all_ok &= (cd == 0);
-    }
-    if (!overflow) {
-      if (tau_out)
-        for (int i = 0; i < B * 10; i++) tau_out[i] = (double)dt_[i];
-      if (!all_ok) { g_err = "hmpc_solve_batch: at least one instance did not reach a KKT point (see status[])"; return HMPC_ERR_NOT_CONVERGED; }
-      return HMPC_OK;
-    }
-    // working-set overflow (rare): fall through to the staged path, which escalates
+    bool all_ok = true;
+    for (int i = 0; i < B; i++) all_ok &= (HMPC_STATUS_CODE(ds[i]) == 0);
+    if (tau_out)
+      for (int i = 0; i < B * 10; i++) tau_out[i] = (double)dt_[i];
+    if (!all_ok) { g_err = "hmpc_solve_batch: at least one instance did not reach a KKT point (see status[])"; return HMPC_ERR_NOT_CONVERGED; }
+    return HMPC_OK;
   }
   double tr[4 * NCHUNK + 2];
   int ntr = 0;

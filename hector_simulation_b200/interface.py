@@ -26,6 +26,7 @@ EXPORTS = [
     "hmpc_set_problem", "hmpc_solve_batch", "hmpc_solve_device", "hmpc_launches_per_solve",
     "hmpc_assemble_device", "hmpc_class_config", "hmpc_solve_batch_ex", "hmpc_solve_device_ex",
     "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device", "hmpc_reset_warm_start",
+    "hmpc_shard_unique_id", "hmpc_shard_init", "hmpc_solve_batch_sharded", "hmpc_shard_wait",
     "hmpc_pin_host_buffer", "hmpc_unpin_host_buffer", "hmpc_swing_device",
 ]
 
@@ -87,6 +88,14 @@ def lib() -> ctypes.CDLL:
         L.hmpc_rollout_device.restype = ctypes.c_int
         L.hmpc_reset_warm_start.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.hmpc_reset_warm_start.restype = ctypes.c_int
+        L.hmpc_shard_unique_id.argtypes = [ctypes.c_void_p]
+        L.hmpc_shard_unique_id.restype = ctypes.c_int
+        L.hmpc_shard_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.hmpc_shard_init.restype = ctypes.c_int
+        L.hmpc_solve_batch_sharded.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.hmpc_solve_batch_sharded.restype = ctypes.c_int
+        L.hmpc_shard_wait.argtypes = [ctypes.c_void_p]
+        L.hmpc_shard_wait.restype = ctypes.c_int
         L.hmpc_pin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.hmpc_pin_host_buffer.restype = ctypes.c_int
         L.hmpc_unpin_host_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -284,6 +293,29 @@ class BatchedMPC:
         _check(lib().hmpc_rollout_device(self._h, d_states.data_ptr(), d_loop.data_ptr(), B, ticks, dt_mpc,
                                          d_wrench_log.data_ptr() if d_wrench_log is not None else None,
                                          d_record_log.data_ptr() if d_record_log is not None else None, ctypes.c_void_p(st)))
+
+    # ---- multi-GPU: one process per GPU, batch sharded (hmpc_shard_*) ----
+    @staticmethod
+    def shard_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _check(lib().hmpc_shard_unique_id(buf))
+        return buf.raw
+
+    def shard_init(self, rank: int, world: int, unique_id: bytes) -> None:
+        assert len(unique_id) == 128
+        _check(lib().hmpc_shard_init(self._h, rank, world, ctypes.c_char_p(unique_id)))
+
+    def solve_batch_sharded(self, records: np.ndarray, out, d_all=None, strict: bool = True):
+        """This rank's slice through hmpc_solve_batch_sharded: results of the slice into `out` = (wrench f64 [b,12N], status
+        i32 [b]) like solve_batch(out=...); `d_all` (torch CUDA f32 [world*b, 12N]) receives the one all-gather."""
+        w, s = out
+        rc = lib().hmpc_solve_batch_sharded(self._h, records.ctypes.data, len(records), w.ctypes.data, s.ctypes.data,
+                                            ctypes.c_void_p(d_all.data_ptr()) if d_all is not None else None)
+        _check(rc, allow_not_converged=not strict)
+        return w, s
+
+    def shard_wait(self) -> None:
+        _check(lib().hmpc_shard_wait(self._h))
 
     def reset_warm_start(self, stream=None) -> None:
         """Forget the working sets the closed loop keeps between ticks (a new loop on this context starts cold)."""

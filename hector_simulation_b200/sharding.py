@@ -1,55 +1,125 @@
-"""Batch sharding across GPUs.
+"""Batch sharding across GPUs — the host-side driver of the library's hmpc_shard_* entry points.
 
-Robots are independent, so the batch is cut into contiguous slices, one per rank (one process per
-GPU); every rank runs the identical kernel on its slice and the path's only exchange is ONE
-all_gather of the results (wrench floats + status words) — issued only when the batch spans more than
-one device.  `torch.distributed` is plumbing here: NCCL over NVLink on GPUs, gloo in the CPU tests.
+Robots are independent, so a batch that exceeds one device is cut into contiguous, equally sized slices, one process
+per GPU; every rank runs the identical kernels on its slice (hmpc_solve_batch_sharded: the slice's results come back to
+the rank's own host arrays, in place) and the path's only exchange is ONE all-gather of the float wrenches — issued by the
+library (ncclAllGather on a side stream, overlapped with the next tick) when a consumer wants the whole batch on every
+device.  `ShardedMPC.tick` is the one function both bench.py (NCCL, GPUs) and tests/test_sharding_gloo.py (gloo, CPU, the
+oracle standing in for the local solve) drive; what differs is the `backend` that solves a slice and moves the gather.
 """
 from __future__ import annotations
 
-from typing import Callable
-
 import numpy as np
-import torch
-import torch.distributed as dist
 
 
 def shard_bounds(batch: int, world: int) -> list[tuple[int, int]]:
-    """Contiguous [lo, hi) per rank; the first `batch % world` ranks get one extra robot."""
-    base, extra = divmod(batch, world)
-    out, lo = [], 0
-    for r in range(world):
-        hi = lo + base + (1 if r < extra else 0)
-        out.append((lo, hi))
-        lo = hi
-    return out
+    """Contiguous [lo, hi) per rank over slices of ceil(batch / world) robots; the tail ranks may hold fewer (or none)."""
+    per = -(-batch // world)
+    return [(min(r * per, batch), min((r + 1) * per, batch)) for r in range(world)]
 
 
-def solve_sharded(records: np.ndarray, horizon: int, solve_local: Callable[[np.ndarray], tuple[np.ndarray, np.ndarray]],
-                  group=None, device: torch.device | None = None):
-    """Each rank solves its slice of `records` with `solve_local` (-> wrench [b,12N] f64, status [b] i32)
-    and all ranks end up with the full [B,12N] / [B] results.  With world_size 1 no collective is issued."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    B = records.shape[0]
-    bounds = shard_bounds(B, world)
-    lo, hi = bounds[rank]
-    w_loc, s_loc = solve_local(records[lo:hi])
-    if world == 1:
-        return w_loc, s_loc
-    dev = device if device is not None else torch.device("cpu")
-    width = 12 * horizon
-    bmax = max(h - l for l, h in bounds)
-    # one fused buffer per rank: [bmax, width + 1] (status carried as the last column) -> ONE all_gather
-    buf = torch.zeros((bmax, width + 1), dtype=torch.float64, device=dev)
-    buf[: hi - lo, :width] = torch.from_numpy(np.ascontiguousarray(w_loc)).to(dev)
-    buf[: hi - lo, width] = torch.from_numpy(s_loc.astype(np.float64)).to(dev)
-    gathered = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(gathered, buf, group=group)
-    wrench = np.zeros((B, width), dtype=np.float64)
-    status = np.zeros(B, dtype=np.int32)
-    for r, (l, h) in enumerate(bounds):
-        g = gathered[r].cpu().numpy()
-        wrench[l:h] = g[: h - l, :width]
-        status[l:h] = g[: h - l, width].astype(np.int32)
-    return wrench, status
+class GpuBackend:
+    """The product path: libhector_mpc_b200 on this rank's GPU, NCCL for the gather (inside the library)."""
+
+    def __init__(self, b_local: int, horizon: int, rank: int, world: int, device: int, broadcast_bytes):
+        import torch
+
+        from . import interface
+
+        self.torch = torch
+        self.mpc = interface.BatchedMPC(b_local, horizon, device=device)
+        uid = interface.BatchedMPC.shard_unique_id() if rank == 0 else None
+        uid = broadcast_bytes(uid)            # rank 0's 128 bytes to everybody (any torch.distributed backend)
+        self.mpc.shard_init(rank, world, uid)
+        self.d_all = torch.zeros((world * b_local, 12 * horizon), dtype=torch.float32, device=f"cuda:{device}")
+
+    def register(self, recs, out_w, out_s):
+        self.mpc.pin(recs, out_w, out_s)      # the control loop's arrays: solved in place from now on
+
+    def solve(self, recs, out_w, out_s, gather: bool):
+        self.mpc.solve_batch_sharded(recs, (out_w, out_s), self.d_all if gather else None)
+
+    def wait(self):
+        self.mpc.shard_wait()
+
+    def gathered(self) -> np.ndarray:
+        self.mpc.shard_wait()
+        return self.d_all.cpu().numpy()
+
+    def close(self):
+        self.mpc.close()
+
+
+class TorchBackend:
+    """Any local solver + torch.distributed for the gather (the CPU test: oracle + gloo)."""
+
+    def __init__(self, b_local: int, horizon: int, world: int, solve_local, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.solve_local = solve_local
+        self.all = torch.zeros((world * b_local, 12 * horizon), dtype=torch.float32)
+
+    def register(self, recs, out_w, out_s):
+        pass
+
+    def solve(self, recs, out_w, out_s, gather: bool):
+        w, s = self.solve_local(recs)
+        out_w[:] = w
+        out_s[:] = s
+        if gather:
+            loc = self.torch.from_numpy(np.ascontiguousarray(out_w, dtype=np.float32))
+            self.dist.all_gather_into_tensor(self.all, loc, group=self.group)
+
+    def wait(self):
+        pass
+
+    def gathered(self) -> np.ndarray:
+        return self.all.numpy()
+
+    def close(self):
+        pass
+
+
+class ShardedMPC:
+    """One tick of a batch of `batch` robots spread over `world` ranks.
+
+    tick(records_local) solves this rank's slice (padded to the common slice size with copies of its last record, so that
+    every rank moves the same number of elements in the gather) and returns views of the slice's results;
+    whole_batch() assembles the gathered wrenches of the last tick in global robot order."""
+
+    def __init__(self, batch: int, horizon: int, rank: int, world: int, backend_factory, record_dtype):
+        self.batch, self.horizon, self.rank, self.world = batch, horizon, rank, world
+        self.bounds = shard_bounds(batch, world)
+        self.lo, self.hi = self.bounds[rank]
+        self.b_local = max(h - l for l, h in self.bounds)
+        self.backend = backend_factory(self.b_local)
+        self.recs = np.zeros(self.b_local, dtype=record_dtype)
+        self.out_w = np.zeros((self.b_local, 12 * horizon), dtype=np.float64)
+        self.out_s = np.zeros(self.b_local, dtype=np.int32)
+        self.backend.register(self.recs, self.out_w, self.out_s)
+
+    def local_slice(self, records_global: np.ndarray) -> np.ndarray:
+        return records_global[self.lo:self.hi]
+
+    def tick(self, records_local: np.ndarray, gather: bool = True):
+        n = self.hi - self.lo
+        assert len(records_local) == n
+        self.recs[:n] = records_local
+        if 0 < n < self.b_local:
+            self.recs[n:] = records_local[-1]     # padding: a valid problem, its results are dropped
+        elif n == 0:
+            self.recs[:] = 0
+        self.backend.solve(self.recs, self.out_w, self.out_s, gather and self.world > 1)
+        return self.out_w[:n], self.out_s[:n]
+
+    def whole_batch(self) -> np.ndarray:
+        """[batch, 12N] float32 wrenches of the last tick(gather=True), global robot order."""
+        if self.world == 1:
+            return self.out_w[: self.hi - self.lo].astype(np.float32)
+        g = self.backend.gathered().reshape(self.world, self.b_local, 12 * self.horizon)
+        return np.concatenate([g[r, : h - l] for r, (l, h) in enumerate(self.bounds)], axis=0)
+
+    def close(self):
+        self.backend.close()

@@ -221,6 +221,23 @@ HMPC_EXTERNC int hmpc_reset_warm_start(hmpc_ctx* ctx, void* stream);
 HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* ctx, struct hmpc_state_t* d_states, struct hmpc_rollout_t* d_loop, int B,
                                      int ticks, double dtMPC, float* d_wrench_log, void* d_record_log, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (the reference has nothing here: one robot per process).  Robots are independent, so a batch
+ * larger than one device is cut into contiguous slices, one process per GPU, identical kernels, no data-path collective.
+ * Every rank gets ITS slice back on the host exactly like hmpc_solve_batch (in place when the arrays are pinned); when a
+ * consumer needs the whole batch on every device, `d_all` (device, float [world * B_local][12 * horizon], rank-major)
+ * receives ONE ncclAllGather of the float wrenches, enqueued behind the solve on a side stream so that it overlaps the
+ * next tick (results are double-buffered); hmpc_shard_wait blocks until the last gather has landed.  NCCL is loaded at run
+ * time (libnccl.so.2), only by these calls.
+ *   rank 0: hmpc_shard_unique_id(id)  ->  ship the 128 bytes to every rank  ->  all: hmpc_shard_init(ctx, rank, world, id)
+ * B_local must be the same on every rank (pad the last slice). */
+#define HMPC_SHARD_ID_BYTES 128
+HMPC_EXTERNC int hmpc_shard_unique_id(void* id128);
+HMPC_EXTERNC int hmpc_shard_init(hmpc_ctx* ctx, int rank, int world, const void* id128);
+HMPC_EXTERNC int hmpc_solve_batch_sharded(hmpc_ctx* ctx, const update_data_t* in_local, int B_local, double* wrench_local,
+                                          int* status_local, float* d_all);
+HMPC_EXTERNC int hmpc_shard_wait(hmpc_ctx* ctx);
+
 /* Row f-4: the swing-leg controller, batched — swingLegController::updateSwingLeg
  * (src/common/SwingLegController.cpp:46-219): foot position, swing sub-phase (Gait::getSwingSubPhase,
  * GaitGenerator.cpp:54-80), swing-time countdown, touch-down placement (:98-128), Bezier swing trajectory

@@ -1,6 +1,8 @@
-"""CPU, world_size 2 over gloo: the multi-GPU path's host logic (contiguous batch shards, one
-all_gather of results).  The per-shard solve is stood in for by the oracle (the checker), so what is
-under test is the sharding/gather plumbing, not a CPU product path."""
+"""CPU, world_size 2 over gloo: the multi-GPU path's host logic — sharding.ShardedMPC.tick / whole_batch, the very
+functions bench.py drives on GPUs (contiguous equal slices, padded tail, this rank's slice back on its own arrays, ONE
+all-gather of the float wrenches).  The backend differs: here the per-slice solve is stood in for by the oracle (the
+checker) and the gather goes through torch.distributed/gloo instead of the library's ncclAllGather — what is under test is
+the partition / padding / ordering logic, not a CPU product path."""
 import os
 import socket
 
@@ -16,7 +18,7 @@ from hector_simulation_b200 import sharding
 def test_shard_bounds():
     assert sharding.shard_bounds(8192, 8) == [(i * 1024, (i + 1) * 1024) for i in range(8)]
     b = sharding.shard_bounds(10, 4)
-    assert b == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert b == [(0, 3), (3, 6), (6, 9), (9, 10)]          # equal slices of ceil(B / world), the tail holds the rest
     assert sharding.shard_bounds(1, 2) == [(0, 1), (1, 1)]
     assert sharding.shard_bounds(0, 2) == [(0, 0), (0, 0)]
 
@@ -32,13 +34,21 @@ def _worker(rank, world, port, n, q):
     setup = O.make_setup(10)
 
     def solve_local(r):
-        if len(r) == 0:
-            return np.zeros((0, 120)), np.zeros(0, np.int32)
         w, info = O.solve_batch(r, setup)
         return w, info[:, 1].astype(np.int32)
 
-    w, s = sharding.solve_sharded(recs, 10, solve_local)
-    ok = np.array_equal(w, g["q_soln"][:n]) and np.array_equal(s, g["info"][:n, 1])
+    from hector_simulation_b200 import scenarios
+
+    sh = sharding.ShardedMPC(n, 10, rank, world, lambda b: sharding.TorchBackend(b, 10, world, solve_local), scenarios.UPDATE_DTYPE)
+    mine = sh.local_slice(recs.view(scenarios.UPDATE_DTYPE).reshape(-1))
+    ok = True
+    for tick in range(2):                                     # two ticks through the same registered arrays
+        w_loc, s_loc = sh.tick(mine)
+        lo, hi = sh.bounds[rank]
+        ok &= np.array_equal(w_loc, g["q_soln"][lo:hi]) and np.array_equal(s_loc, g["info"][lo:hi, 1])
+        whole = sh.whole_batch()                              # every rank ends up with the whole batch, global order
+        ok &= whole.shape == (n, 120) and np.array_equal(whole, g["q_soln"][:n].astype(np.float32))
+    sh.close()
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
