@@ -4,6 +4,7 @@
 // context; part 2 is the batched interface.  There is no CPU solve path in this library.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cstddef>
@@ -73,7 +74,7 @@ class HostPool {
     }
     cv_.notify_all();
     fn(0, np);
-    while (pending_.load(std::memory_order_acquire) != 0) { /* spin: the parts are equal-sized */ }
+    while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // the parts are equal-sized: a short wait
   }
 
  private:
@@ -707,6 +708,15 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
 }
 }  // namespace
 
+// The kernels stage a record with a 1-D bulk copy (cp.async.bulk), whose global source must be 16-byte aligned: the record
+// stride is a multiple of 16 by construction, the base pointer is the caller's (a sliced tensor view may not be).
+static int check_device_records(const hmpc_ctx* c, const void* d_records, int B, const char* who)
+{
+  if (B > c->max_batch) { g_err = std::string(who) + ": batch exceeds the context's capacity"; return HMPC_ERR_ARG; }
+  if (reinterpret_cast<uintptr_t>(d_records) & 15u) { g_err = std::string(who) + ": d_records must be 16-byte aligned"; return HMPC_ERR_ARG; }
+  return HMPC_OK;
+}
+
 // profiling hook: device buffer [batch][32] of clock64() stage timestamps, or NULL to switch off
 HMPC_EXTERNC void hmpc_debug_set_clock_buffer(long long* d_buf) { g_dbg_clk = d_buf; }
 
@@ -728,6 +738,7 @@ HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* c, const void* d_records, int B, fl
 {
   if (!c || !d_records || !d_wrench || !d_status || B < 0) { g_err = "hmpc_solve_device: bad argument"; return HMPC_ERR_ARG; }
   if (B == 0) return HMPC_OK;
+  if (int rc = check_device_records(c, d_records, B, "hmpc_solve_device")) return rc;
   return enqueue_solve(c, d_records, B, d_wrench, nullptr, d_status, static_cast<cudaStream_t>(stream));
 }
 
@@ -736,6 +747,7 @@ HMPC_EXTERNC int hmpc_solve_device_ex(hmpc_ctx* c, const void* d_records, int B,
 {
   if (!c || !d_records || !d_wrench || !d_status || B < 0) { g_err = "hmpc_solve_device_ex: bad argument"; return HMPC_ERR_ARG; }
   if (B == 0) return HMPC_OK;
+  if (int rc = check_device_records(c, d_records, B, "hmpc_solve_device_ex")) return rc;
   return enqueue_solve(c, d_records, B, d_wrench, nullptr, d_status, static_cast<cudaStream_t>(stream), 0, d_tau);
 }
 
@@ -747,6 +759,7 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
     return HMPC_ERR_ARG;
   }
   if (B == 0) return HMPC_OK;
+  if (int rc = check_device_records(c, d_records, B, "hmpc_assemble_device")) return rc;
   CK(cudaSetDevice(c->device));
   const ClassCfg& k = c->cls[c->ncls - 1];
   hmpc::KernelArgs ka = base_args(c, d_records, B, nullptr, c->d_status);
@@ -805,7 +818,7 @@ HMPC_EXTERNC int hmpc_pin_host_buffer(hmpc_ctx* c, void* ptr, size_t bytes)
   CK(cudaSetDevice(c->device));
   // registration is page-granular and two small caller arrays may share a page: register only the page runs of
   // [ptr, ptr+bytes) that no earlier pin covers
-  const uintptr_t PG = 4096;
+  const uintptr_t PG = (uintptr_t)(sysconf(_SC_PAGESIZE) > 0 ? sysconf(_SC_PAGESIZE) : 4096);  // 64 KiB on some aarch64 hosts
   const uintptr_t lo = reinterpret_cast<uintptr_t>(ptr) & ~(PG - 1);
   const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes + PG - 1) & ~(PG - 1);
   auto covered = [&](uintptr_t pg) {
@@ -818,7 +831,11 @@ HMPC_EXTERNC int hmpc_pin_host_buffer(hmpc_ctx* c, void* ptr, size_t bytes)
     uintptr_t end = pg + PG;
     while (end < hi && !covered(end)) end += PG;
     void* base = reinterpret_cast<void*>(pg);
-    CK(cudaHostRegister(base, end - pg, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    {
+      cudaError_t re = cudaHostRegister(base, end - pg, cudaHostRegisterMapped | cudaHostRegisterPortable);
+      if (re == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();  // registered by somebody else: usable as it is
+      else if (cuda_fail(re, "cudaHostRegister")) return HMPC_ERR_CUDA;
+    }
     void* dptr = nullptr;
     cudaError_t e = cudaHostGetDevicePointer(&dptr, base, 0);
     if (e != cudaSuccess || dptr != base) {  // the in-place mode hands host addresses to the kernels
@@ -842,6 +859,7 @@ HMPC_EXTERNC int hmpc_unpin_host_buffer(hmpc_ctx* c, void* ptr)
   if (idx == c->pins.size()) { g_err = "hmpc_unpin_host_buffer: pointer was not pinned through this context"; return HMPC_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(c->xstream[i]));
   c->pins.erase(c->pins.begin() + idx);
   // release the page runs no remaining pin touches
   for (size_t r = 0; r < c->runs.size();) {

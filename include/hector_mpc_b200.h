@@ -141,6 +141,7 @@ HMPC_EXTERNC int hmpc_solve_batch(hmpc_ctx* ctx, const struct update_data_t* in,
 /* Device-resident path: `d_records` = B packed records already in HBM, `d_wrench`
  * [B][12*horizon] float, `d_status` [B] int, all device pointers; enqueued on `stream`
  * (a cudaStream_t passed as void*), returns without synchronising. */
+/* d_records must be 16-byte aligned (the kernels stage records with a bulk copy); B <= the context's capacity. */
 HMPC_EXTERNC int hmpc_solve_device(hmpc_ctx* ctx, const void* d_records, int B, float* d_wrench,
                                    int* d_status, void* stream);
 

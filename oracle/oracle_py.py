@@ -89,14 +89,14 @@ def _p(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _mode(assembly_fp64: bool, trig_as_compiled: bool, gemv_by4: bool = False) -> ctypes.c_int:
+def _mode(assembly_fp64: bool, trig_as_compiled: bool, gemv_by4: bool = False, gemm_kc: int = 0) -> ctypes.c_int:
     """Bit mask of solve_mpc_oracle.cpp: 1 = formulation in double, 2 = trig as the reference's TU resolves it,
     4 = matrix-vector products grouped like Eigen 3.3's gemv kernel (sensitivity probe)."""
-    return ctypes.c_int(int(bool(assembly_fp64)) | (2 if trig_as_compiled else 0) | (4 if gemv_by4 else 0))
+    return ctypes.c_int(int(bool(assembly_fp64)) | (2 if trig_as_compiled else 0) | (4 if gemv_by4 else 0) | ((int(gemm_kc) & 0xff) << 8))
 
 
 def solve_batch(records: np.ndarray, setup: np.ndarray, assembly_fp64: bool = False, trig_as_compiled: bool = False,
-                gemv_by4: bool = False):
+                gemv_by4: bool = False, gemm_kc: int = 0):
     """-> (q_soln [n,12N] f64, info [n,4] i32 = {rc, nWSR, nv_red, nc_red})."""
     records = np.ascontiguousarray(records, dtype=UPDATE_DTYPE)
     n = records.shape[0]
@@ -105,7 +105,7 @@ def solve_batch(records: np.ndarray, setup: np.ndarray, assembly_fp64: bool = Fa
     info = np.zeros((n, 4), dtype=np.int32)
     if not has_qpoases():
         raise RuntimeError("oracle was built without qpOASES (no /root/reference and no prebuilt oracle/_ref)")
-    lib().oracle_solve_batch(_p(records), ctypes.c_int(n), _p(setup), _mode(assembly_fp64, trig_as_compiled, gemv_by4), _p(q), _p(info))
+    lib().oracle_solve_batch(_p(records), ctypes.c_int(n), _p(setup), _mode(assembly_fp64, trig_as_compiled, gemv_by4, gemm_kc), _p(q), _p(info))
     return q, info
 
 

@@ -97,6 +97,25 @@ void matmul(const T* A, const T* B, T* C, int r, int k, int c)
   }
 }
 
+// The same product with the k-sum cut into depth blocks the way a blocked GEBP kernel accumulates — every block summed from
+// zero in a register, then added to the result, C = ((0 + s_0) + s_1) + ... — sensitivity probe of the freedom Eigen's
+// cache blocking has (a single block, kc >= k, is the sequential sum above).
+template <typename T>
+void matmul_kblocked(const T* A, const T* B, T* C, int r, int k, int c, int kc)
+{
+  for (int i = 0; i < r; i++)
+    for (int j = 0; j < c; j++) {
+      T res = (T)0;
+      for (int k0 = 0; k0 < k; k0 += kc) {
+        const int k1 = k0 + kc < k ? k0 + kc : k;
+        T acc = A[(size_t)i * k + k0] * B[(size_t)k0 * c + j];
+        for (int t = k0 + 1; t < k1; t++) acc = acc + A[(size_t)i * k + t] * B[(size_t)t * c + j];
+        res = res + acc;
+      }
+      C[(size_t)i * c + j] = res;
+    }
+}
+
 // Eigen's 3x3 inverse (Eigen/src/LU/InverseImpl.h, compute_inverse<...,3>): cofactors, det from
 // the first cofactor column dotted with the first matrix column, multiply by 1/det.
 template <class T>
@@ -219,7 +238,7 @@ struct Formulation {
 
 template <class T>
 static void formulate(const update_data_t* u, const problem_setup* setup, Formulation<T>& F, bool trig_as_compiled = false,
-                      bool gemv_by4 = false)
+                      bool gemv_by4 = false, int gemm_kc = 0)
 {
   const int N = setup->horizon;
   const int nx = 13 * N, nu = 12 * N, nc = 16 * N;
@@ -425,7 +444,8 @@ static void formulate(const update_data_t* u, const problem_setup* setup, Formul
     }
     matmul(Bt.data(), Sd.data(), T1.data(), nu, nx, nx);
     std::vector<T> BSB((size_t)nu * nu);
-    matmul(T1.data(), F.B_qp.data(), BSB.data(), nu, nx, nu);
+    if (gemm_kc > 0) matmul_kblocked(T1.data(), F.B_qp.data(), BSB.data(), nu, nx, nu, gemm_kc);
+    else matmul(T1.data(), F.B_qp.data(), BSB.data(), nu, nx, nu);
     F.H.assign((size_t)nu * nu, (T)0);
     for (int i = 0; i < nu; i++)
       for (int j = 0; j < nu; j++) {
@@ -541,10 +561,10 @@ static int solve_reduced(ReducedQP& Q, std::vector<double>& x, int* nwsr_out)
 
 template <class T>
 static int solve_one(const update_data_t* u, const problem_setup* s, double* q_soln, int* info, bool trig_as_compiled = false,
-                     bool gemv_by4 = false)
+                     bool gemv_by4 = false, int gemm_kc = 0)
 {
   Formulation<T> F;
-  formulate<T>(u, s, F, trig_as_compiled, gemv_by4);
+  formulate<T>(u, s, F, trig_as_compiled, gemv_by4, gemm_kc);
   ReducedQP Q;
   eliminate(F, Q);
   std::vector<double> x;
@@ -588,9 +608,10 @@ int oracle_solve_batch(const update_data_t* u, int n, const problem_setup* s, in
   int bad = 0;
   const int nu = 12 * s->horizon;
   const bool tac = (mode & 2) != 0, by4 = (mode & 4) != 0;
+  const int kc = (mode >> 8) & 0xff;  // bits 8-15: depth block of the Hessian product's k-sum (0: one sequential sum)
   for (int i = 0; i < n; i++) {
-    int rc = (mode & 1) ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac, by4)
-                        : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac, by4);
+    int rc = (mode & 1) ? solve_one<double>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac, by4, kc)
+                        : solve_one<float>(&u[i], s, q_soln + (size_t)i * nu, info ? info + 4 * i : NULL, tac, by4, kc);
     if (rc) bad++;
   }
   return bad;

@@ -362,3 +362,39 @@ def test_in_place_mode_escalates_on_the_device():
     assert (interface.status_code(s) == 0).all() and np.array_equal(w.astype(np.float32), w_ref.astype(np.float32))
     assert interface.status_nactive(s).max() > 64
     mpc.close()
+
+
+def test_contexts_of_different_horizons_coexist(torch_cuda):
+    """The runtime-horizon kernel instantiations are shared by every context of the process, and their dynamic
+    shared-memory attribute is process-wide: a horizon-8 context created after a horizon-10 one (and the reference-style
+    global context) must not lower it under the others' launches.  Also: a misaligned device record pointer is an
+    argument error, not a device fault."""
+    torch = torch_cuda
+    ctx = {}
+    for N in (10, 8, 16, 5):  # created in this order, all alive together
+        recs, _ = scenarios.make_batch(3, 96, horizon=N, seed=700 + N)
+        ctx[N] = (interface.BatchedMPC(96, N), recs)
+    b = scenarios.stand_inputs(10)
+    interface.setup_problem(scenarios.DT_MPC, 10, scenarios.MU_PASSED, scenarios.F_MAX)   # the global one-robot context too
+    for _ in range(2):
+        for N, (mpc, recs) in ctx.items():
+            packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
+            d_w = torch.zeros((96, 12 * N), dtype=torch.float32, device="cuda")
+            d_s = torch.full((96,), -1, dtype=torch.int32, device="cuda")
+            mpc.solve_device(packed, 96, d_w, d_s)
+            torch.cuda.synchronize()
+            assert (interface.status_code(d_s.cpu().numpy()) == 0).all(), N
+            w, s = mpc.solve_batch(recs)
+            assert rel_err(d_w.cpu().numpy().astype(np.float64), w).max() < 1e-6
+        interface.update_problem_data(b["p"], b["v"], b["q"], b["w"], b["r"], b["joint_angles"], b["yaw"], b["weights"],
+                                      b["state_trajectory"], b["Alpha_K"], b["gait"])
+        assert abs(interface.get_solution(2) - 47.84) < 0.05
+    mpc, recs = ctx[10]
+    raw = torch.zeros(96 * interface.record_bytes(10) + 64, dtype=torch.uint8, device="cuda")
+    view = raw[8: 8 + 96 * interface.record_bytes(10)].view(96, -1)     # 8 bytes off: not 16-byte aligned
+    d_w = torch.zeros((96, 120), dtype=torch.float32, device="cuda")
+    d_s = torch.zeros((96,), dtype=torch.int32, device="cuda")
+    with pytest.raises(interface.HmpcError, match="16-byte aligned"):
+        mpc.solve_device(view, 96, d_w, d_s)
+    for mpc, _ in ctx.values():
+        mpc.close()
