@@ -360,6 +360,9 @@ def main():
             mpc.solve_batch(recs_c, out=(out_w, out_s))
     for _ in range(W):
         e2e_step()
+    if world > 1:
+        sh.backend.wait()  # no gather in flight while torch's own communicator runs the barrier below (two NCCL
+                           # communicators must not have collectives in flight on one device in different orders)
     barrier()
     t0 = time.perf_counter()
     e2e_lat = []

@@ -231,7 +231,9 @@ HMPC_EXTERNC int hmpc_rollout_device(hmpc_ctx* ctx, struct hmpc_state_t* d_state
  * next tick (results are double-buffered); hmpc_shard_wait blocks until the last gather has landed.  NCCL is loaded at run
  * time (libnccl.so.2), only by these calls.
  *   rank 0: hmpc_shard_unique_id(id)  ->  ship the 128 bytes to every rank  ->  all: hmpc_shard_init(ctx, rank, world, id)
- * B_local must be the same on every rank (pad the last slice). */
+ * B_local must be the same on every rank (pad the last slice).  The gather is a collective of the context's own NCCL
+ * communicator: call hmpc_shard_wait before another communicator (e.g. torch.distributed's) runs a collective on the same
+ * device, as with any two NCCL communicators. */
 #define HMPC_SHARD_ID_BYTES 128
 HMPC_EXTERNC int hmpc_shard_unique_id(void* id128);
 HMPC_EXTERNC int hmpc_shard_init(hmpc_ctx* ctx, int rank, int world, const void* id128);

@@ -398,3 +398,25 @@ def test_contexts_of_different_horizons_coexist(torch_cuda):
         mpc.solve_device(view, 96, d_w, d_s)
     for mpc, _ in ctx.values():
         mpc.close()
+
+
+def test_sharded_entry_points_single_rank(torch_cuda):
+    """hmpc_shard_* with a one-rank group: the slice comes back on the caller's arrays like hmpc_solve_batch, and the
+    (here trivial) ncclAllGather delivers the float wrenches to the device buffer, tick after tick (double-buffered)."""
+    torch = torch_cuda
+    from hector_simulation_b200 import sharding
+
+    N, B = 10, 200
+    recs, _ = scenarios.make_batch(3, B, horizon=N, seed=77)
+    ref = interface.BatchedMPC(B, N)
+    w_ref, s_ref = ref.solve_batch(recs)
+    ref.close()
+    sh = sharding.ShardedMPC(B, N, 0, 1, lambda bl: sharding.GpuBackend(bl, N, 0, 1, 0, lambda b: b), scenarios.UPDATE_DTYPE)
+    for tick in range(3):
+        w, s = sh.tick(recs, gather=False)
+        sh.backend.solve(sh.recs, sh.out_w, sh.out_s, True)     # the gather path itself (world == 1 skips it in tick())
+        torch.cuda.synchronize()
+        assert np.array_equal(s, s_ref) and np.array_equal(w.astype(np.float32), w_ref.astype(np.float32))
+        g = sh.backend.gathered()
+        assert np.array_equal(g, w_ref.astype(np.float32))
+    sh.close()
