@@ -315,6 +315,8 @@ hmpc::KernelArgs base_args(const hmpc_ctx* c, const void* d_records, int B, floa
   ka.dt = c->setup.dt;
   ka.f_max = c->setup.f_max;
   ka.max_iter = c->max_iter;
+  ka.tol_kkt = 1e-9;
+  ka.tol_dep = 1e-11;
   ka.block_rounds = c->block_rounds;
   ka.wrench = d_wrench;
   ka.status = d_status;

@@ -144,6 +144,8 @@ struct KernelArgs {
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
+  double tol_kkt;                // a row counts as violated below -tol_kkt * max(1, |x0|_inf)   (default 1e-9)
+  double tol_dep;                // an entering row is dependent on the working set when its curvature falls below tol_dep * a'H^-1a (1e-11)
   int use_T;                     // 1: the shared-memory carve-up holds the H^-1 a_j cache (runtime-layout launches; fixed: yes)
   int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
   int warm_start;                // 1: propose the working set in `ws_state` (previous tick) to the block start
@@ -1552,7 +1554,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     {
       unsigned kx = redk[16];
       for (int w = 1; w < NW; w++) kx = redk[16 + w] > kx ? redk[16 + w] : kx;
-      tol = 1e-9 * fmax(1.0, (double)__uint_as_float(kx));
+      tol = ka.tol_kkt * fmax(1.0, (double)__uint_as_float(kx));
     }
     // per-row constants: normal, right-hand side, slack at the unconstrained minimiser
     double ne[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1863,7 +1865,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           const unsigned mlo = __reduce_min_sync(0xffffffffu, thi == mhi ? tlo : 0xffffffffu);
           const int l1 = __reduce_min_sync(0xffffffffu, (thi == mhi && tlo == mlo) ? lloc : 0x7fffffff);
           const double t1 = (l1 == 0x7fffffff) ? 1e300 : __hiloint2double((int)mhi, (int)mlo);
-          const bool dependent = !(zn > 1e-11 * cHc);
+          const bool dependent = !(zn > ka.tol_dep * cHc);
           const double t2 = dependent ? 1e300 : fmax(0.0, -sp * fast_rcp(zn));
           const double t = fmin(t1, t2);
           int decision;  // 0 = full step (p joins W), 1 = partial step (drop l1, retry), 2 = infeasible, 3 = W full

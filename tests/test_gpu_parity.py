@@ -420,3 +420,43 @@ def test_sharded_entry_points_single_rank(torch_cuda):
         g = sh.backend.gathered()
         assert np.array_equal(g, w_ref.astype(np.float32))
     sh.close()
+
+
+@pytest.mark.parametrize("N", [5, 10, 16])
+def test_horizon_sweep_batch_4096(torch_cuda, oracle, N):
+    """BASELINE configs[3] (N = 20 is refused, like horizons above 19 by the reference): 4096 mixed robots per horizon, every
+    instance converges, and on a strided sample
+      * the first-step wrench (what the caller uses) is inside the 1e-4 contract against qpOASES;
+      * the whole horizon is held to 1e-4 too, EXCEPT where a tight-tolerance fp64 referee shows that qpOASES itself is the
+        party that is off (its termination tolerance is 2.2e-7 in homotopy length, Options.cpp:206, and the N = 16 Hessians
+        have cond ~1.5e7): every such case is adjudicated here — the GPU result must sit on the referee's optimum (1e-6) —
+        and even then the gap to qpOASES stays below 3e-4."""
+    B = 4096
+    recs, _ = scenarios.make_batch(4, B, horizon=N, seed=1000 + N)
+    mpc = interface.BatchedMPC(B, N)
+    w, st = mpc.solve_batch(recs, strict=False)
+    mpc.close()
+    assert (interface.status_code(st) == 0).all(), np.bincount(interface.status_code(st))
+    if not oracle.has_qpoases():
+        pytest.skip("oracle/_ref without qpOASES")
+    from oracle import qp_dual_active_set as G
+
+    idx = np.arange(3, B, 64 if N <= 10 else 128)
+    setup = oracle.make_setup(N)
+    ref, info = oracle.solve_batch(recs[idx], setup)
+    good = info[:, 0] == 0
+    e0, ef = rel_err(w[idx], ref, 12), rel_err(w[idx], ref)
+    assert e0[good].max() < 1e-4 and np.median(e0[good]) < 1e-5
+    refereed = 0
+    for k in np.nonzero(good & (ef > 5e-5))[0]:
+        Q = oracle.reduced_qp(recs[idx[k]], setup)
+        x, inf = G.solve(Q["H"], Q["g"], Q["A"], Q["lb"], Q["ub"], tol=1e-12, max_iter=3000)
+        full = np.zeros(12 * N)
+        full[Q["var_ind"]] = x
+        assert inf["status"] == 0
+        assert rel_err(w[idx[k]][None], full[None])[0] < 1e-6, (N, int(idx[k]))          # the GPU sits on the exact optimum
+        assert rel_err(ref[k][None], full[None])[0] > 0.5 * ef[k]                          # ... and qpOASES is what is off
+        refereed += 1
+    print("horizon %d, %d robots: first step worst %.2e, whole horizon worst %.2e vs qpOASES (%d cases above 5e-5 refereed in fp64)"
+          % (N, len(idx), e0[good].max(), ef[good].max(), refereed))
+    assert ef[good].max() < 3e-4

@@ -435,6 +435,28 @@ def test_solve_kernel_source_edge_cases(emul, oracle):
         assert (w[ref == 0.0] == 0.0).all()
 
 
+def test_solve_kernel_source_is_insensitive_to_its_two_tolerances(emul):
+    """The active-set stage has two literals: the KKT tolerance (a row counts as violated below -1e-9 max(1, |x0|)) and the
+    dependence threshold (curvature below 1e-11 a'H^-1a).  Neither is tuned to the fixtures: swept over four decades each,
+    every instance still converges and the optimum moves far less than the 1e-4 contract."""
+    from conftest import load_golden
+
+    g = load_golden("cfg3_h10")
+    recs = g["records"][:10]      # walking and standing robots, both size classes
+    w0, st0, _, _, _ = _solve(emul, recs, 10, tau=False)
+    assert (interface.status_code(st0) == 0).all()
+    for var, vals in (("HMPC_TOL_KKT", ("1e-11", "1e-7")), ("HMPC_TOL_DEP", ("1e-13", "1e-9"))):
+        for v in vals:
+            os.environ[var] = v
+            try:
+                w, st, _, _, _ = _solve(emul, recs, 10, tau=False)
+            finally:
+                del os.environ[var]
+            assert (interface.status_code(st) == 0).all(), (var, v)
+            assert np.abs(w - w0).max() < 1e-5 * np.abs(w0).max(), (var, v, np.abs(w - w0).max())
+            assert np.array_equal(interface.status_nactive(st), interface.status_nactive(st0)), (var, v)
+
+
 def test_solve_kernel_source_in_place_and_warm_start_modes(emul):
     """The other modes of the same kernel: gathering the live bytes of the caller's update_data_t records in place (the
     host-buffer path's in-place mode), double-precision result stores, and the optional S-pair warm start."""
