@@ -259,7 +259,7 @@ __device__ __forceinline__ double dot6(const double* a, const double* b)
 // C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
 {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // Pivot-panel tiles are kept in "fragment order": element (r,c) at (c>>2)*32 + r*4 + (c&3), so that the A/B operand
@@ -1649,6 +1649,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         __syncthreads();  // everybody has read the counts and the slot mask
         // no violated row (the iteration below confirms and stops) / no room for the rows or for one S entry per thread
         if (nadd == 0 || q + nadd > qmax || tri(32 - __clz(am0 | ((1u << (q + nadd)) - 1u))) > NT) break;
+        unsigned mybit = 0u;
         if (cand) {  // the rank-th entering row takes the rank-th free slot
           unsigned fm = ~am0;
           for (int r = 0; r < rank; r++) fm &= fm - 1;
@@ -1656,8 +1657,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           myslot = sl;
           wsl[sl] = ws_pack(ke, nie);
           newslot[rank] = sl;
-          atomicOr(&amask[0], 1u << sl);
+          mybit = 1u << sl;
         }
+        mybit = __reduce_or_sync(0xffffffffu, mybit);  // one shared-memory atomic per warp, not per row
+        if (lane == 0 && mybit) atomicOr(&amask[0], mybit);
         __syncthreads();
         if (round == 0) HMPC_STAMP(9);
         if (isvar) {

@@ -198,6 +198,14 @@ inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
     return m;
   });
 }
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+  return hmpc_emul_exchange(mask, v, [&](const unsigned long long* s) {
+    unsigned m = 0u;
+    for (int l = 0; l < 32; l++) m |= (unsigned)s[l];
+    return m;
+  });
+}
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
 // mma.sync.aligned.m8n8k4.row.col.f64 (the kernel's dmma884 body is replaced by a call to this, test build step):
 // lane 4g+t holds A[g][t], B[t][g] and C[g][2t], C[g][2t+1]; the k-sum runs in index order with fused multiply-adds
