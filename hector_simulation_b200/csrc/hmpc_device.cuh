@@ -1017,10 +1017,6 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       mbar_expect_tx(bar, (uint32_t)rec_stride);
       bulk_g2s(rec, ka.records + (size_t)inst * rec_stride, (uint32_t)rec_stride, bar);
     }
-    // meanwhile: zero the sparse fp32 operands, P_0 = I
-    for (int e = tid; e < 169; e += NT) Acd[e] = 0.f;
-    for (int e = tid; e < 156; e += NT) Bcd[e] = 0.f;
-    for (int e = tid; e < 192; e += NT) Fblk[e] = 0.f;
     if (raw) {
       __syncthreads();
     } else {
@@ -1082,6 +1078,28 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         flags[6] = ncomb;
       }
     }
+    // ---------------- stage 1: prologue, three roles on the other warps (beside the block list on warp 0) ----------------
+    if (tid < 14) reinterpret_cast<float*>(smem + L.keep)[tid] = (tid < 10) ? rf[19 + tid] : rf[6 + tid - 10];
+    {
+      constexpr int WL = (NW > 3) ? 3 : 0, W1 = (NW > 1) ? 1 : 0, W2 = (NW > 2) ? 2 : 0;
+      unsigned char* scr = smem + L.P;  // 432 bytes of role scratch
+      // every role zeroes the sparse fp32 operand it fills (no barrier separates the roles from earlier code)
+      if (wid == WL) {
+        for (int e = lane; e < 192; e += 32) Fblk[e] = 0.f;
+        __syncwarp();
+        role_leg(rf, lane, Fblk, scr);
+      }
+      if (wid == W1) {
+        for (int e = lane; e < 169; e += 32) Acd[e] = 0.f;
+        __syncwarp();
+        role_state(rf, ka.dt, x0f, Acd, lane, scr + 256);
+      }
+      if (wid == W2) {
+        for (int e = lane; e < 156; e += 32) Bcd[e] = 0.f;
+        __syncwarp();
+        if (lane == 31) role_inertia(rf, ka.dt, Bcd);
+      }
+    }
     __syncthreads();
     const int NB = flags[0];
     if (ka.split_nb >= 0 && NB > ka.split_nb) {
@@ -1097,15 +1115,6 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     const int NT8 = (n + 7) >> 3;
     const unsigned stmask[2] = {(unsigned)flags[1], (unsigned)flags[2]};
 
-    // ---------------- stage 1: prologue, three roles on different warps ----------------
-    if (tid < 14) reinterpret_cast<float*>(smem + L.keep)[tid] = (tid < 10) ? rf[19 + tid] : rf[6 + tid - 10];
-    {
-      constexpr int W1 = (NW > 1) ? 1 : 0, W2 = (NW > 2) ? 2 : 0;
-      unsigned char* scr = smem + L.P;  // 432 bytes of role scratch
-      if (wid == 0) role_leg(rf, lane, Fblk, scr);
-      if (wid == W1) role_state(rf, ka.dt, x0f, Acd, lane, scr + 256);
-      if (wid == W2 && lane == 31) role_inertia(rf, ka.dt, Bcd);
-    }
     for (int e = n + tid; e < 8 * NT8; e += NT) gq[e] = 0.0;  // tile padding of the gradient
     __syncthreads();
 
@@ -1270,9 +1279,19 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           const int a = N - 1 - K - delta, b = a + delta;
           if ((need >> a) & 1u) {
             if (!dump && delta > 0) {  // block (b,a) strictly below the diagonal: element (cj, ci), no alpha
+              // six consecutive rows of one column: at most two tiles, addresses by increments (hput, specialised)
               const int col = 6 * sl_blk[2 * a + li] + ci, row0 = 6 * sl_blk[2 * b + lj];
+              const int I0 = row0 >> 3, r0 = row0 & 7, Jc = col >> 3, cb = col & 7;
+              float* t0 = Hf + toff(I0, Jc);
+              float* t1 = t0 + (I0 + 1) * 64;  // tile (I0 + 1, Jc)
 #pragma unroll
-              for (int cj = 0; cj < 6; cj++) hput(Hf, row0 + cj, col, FM(2.f, FA(acc[cj], 0.f)));
+              for (int cj = 0; cj < 6; cj++) {
+                const float hv = FM(2.f, FA(acc[cj], 0.f));
+                const int r = r0 + cj;
+                float* t = (r < 8) ? t0 : t1;
+                t[((r & 7) << 3) + cb] = hv;
+                if (((r < 8) ? I0 : I0 + 1) == Jc) t[(cb << 3) + (r & 7)] = hv;  // diagonal tile: both triangles
+              }
             } else {
               const int ka_ = dump ? 0 : sl_blk[2 * a + li], kb_ = dump ? 0 : sl_blk[2 * b + lj];
 #pragma unroll
