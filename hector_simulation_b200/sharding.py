@@ -32,6 +32,7 @@ class GpuBackend:
         uid = broadcast_bytes(uid)            # rank 0's 128 bytes to everybody (any torch.distributed backend)
         self.mpc.shard_init(rank, world, uid)
         self.d_all = torch.zeros((world * b_local, 12 * horizon), dtype=torch.float32, device=f"cuda:{device}")
+        self.h_all = torch.zeros((world * b_local, 12 * horizon), dtype=torch.float32).pin_memory()
 
     def register(self, recs, out_w, out_s):
         self.mpc.pin(recs, out_w, out_s)      # the control loop's arrays: solved in place from now on
@@ -44,7 +45,10 @@ class GpuBackend:
 
     def gathered(self) -> np.ndarray:
         self.mpc.shard_wait()
-        return self.d_all.cpu().numpy()
+        with self.torch.cuda.device(self.d_all.device):
+            self.h_all.copy_(self.d_all)
+            self.torch.cuda.synchronize()
+        return self.h_all.numpy()
 
     def close(self):
         self.mpc.close()
@@ -103,12 +107,19 @@ class ShardedMPC:
     def local_slice(self, records_global: np.ndarray) -> np.ndarray:
         return records_global[self.lo:self.hi]
 
-    def tick(self, records_local: np.ndarray, gather: bool = True):
+    @property
+    def records(self) -> np.ndarray:
+        """This rank's registered record array (first hi - lo entries are its robots): a control loop fills it in place and
+        calls tick() without arguments — no copy, like hmpc_solve_batch on pinned arrays."""
+        return self.recs
+
+    def tick(self, records_local: np.ndarray | None = None, gather: bool = True):
         n = self.hi - self.lo
-        assert len(records_local) == n
-        self.recs[:n] = records_local
+        if records_local is not None:
+            assert len(records_local) == n
+            self.recs[:n] = records_local
         if 0 < n < self.b_local:
-            self.recs[n:] = records_local[-1]     # padding: a valid problem, its results are dropped
+            self.recs[n:] = self.recs[n - 1]      # padding: a valid problem, its results are dropped
         elif n == 0:
             self.recs[:] = 0
         self.backend.solve(self.recs, self.out_w, self.out_s, gather and self.world > 1)

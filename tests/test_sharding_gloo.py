@@ -42,8 +42,8 @@ def _worker(rank, world, port, n, q):
     sh = sharding.ShardedMPC(n, 10, rank, world, lambda b: sharding.TorchBackend(b, 10, world, solve_local), scenarios.UPDATE_DTYPE)
     mine = sh.local_slice(recs.view(scenarios.UPDATE_DTYPE).reshape(-1))
     ok = True
-    for tick in range(2):                                     # two ticks through the same registered arrays
-        w_loc, s_loc = sh.tick(mine)
+    for tick in range(2):                                     # two ticks through the same registered arrays:
+        w_loc, s_loc = sh.tick(mine) if tick == 0 else sh.tick()  # records handed over, then left in place
         lo, hi = sh.bounds[rank]
         ok &= np.array_equal(w_loc, g["q_soln"][lo:hi]) and np.array_equal(s_loc, g["info"][lo:hi, 1])
         whole = sh.whole_batch()                              # every rank ends up with the whole batch, global order
