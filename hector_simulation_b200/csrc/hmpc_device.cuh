@@ -75,7 +75,8 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.dv = s;   s += 2 * (ns + 2) * 8;                // step-direction scratch / double-buffered pivot column of the block start
   L.rr = s;   s += ns * 8;
   L.wsl = s;  s += align16(ns * 4);
-  L.zb = s;   s += n * 8;
+  if (use_T) L.zb = L.gq;  // the gradient is spent once x0 is known; the no-cache mode keeps A_W'r there and needs both
+  else { L.zb = s; s += n * 8; }
   // sweep view: the tiles live in registers during the sweep, so its buffers take H's place when they fit there
   const int sweep_bytes = 2 * nt8 * 64 * 8 + nwarps * 2 * 64 * 8;
   int w = (sweep_bytes <= ntile * 64 * 8) ? L.H : L.uni;
@@ -101,8 +102,8 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
 // packed record stride (include/hector_mpc_b200.h: hmpc_record_bytes)
 __host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12 * N) * 4 + 2 * N); }
 
-// size classes: class 0 holds at most N blocks of 6 variables, class 1 up to 2N.  Working-set capacity: N + 5 rows for
-// class 0 (a walking gait ends with about one active row per stance step; 15 at N = 10), 31 for class 1; an instance that needs more
+// size classes: class 0 holds at most N blocks of 6 variables, class 1 up to 2N.  Working-set capacity: N + 7 rows for
+// class 0 (a walking gait ends with about one active row per stance step; 17 at N = 10 — what 7 CTAs/SM leave room for), 31 for class 1; an instance that needs more
 // escalates to the next class (class 2 = class 1's size with as many slots as shared memory holds).
 __host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
 // The H^-1 a_j cache costs (qmax + 1) * n doubles: the long-horizon double-support class (extension configs) does without
@@ -111,7 +112,7 @@ __host__ __device__ constexpr bool class_use_T(int N, int cls) { return cls == 0
 __host__ __device__ constexpr int class_qmax(int N, int cls)
 {
   const int n = 6 * class_nb_cap(N, cls);
-  const int q = cls == 0 ? N + 5 : (class_use_T(N, cls) ? 31 : 96);  // (the block start handles up to 31 rows: one mask word)
+  const int q = cls == 0 ? N + 7 : (class_use_T(N, cls) ? 31 : 96);  // (the block start handles up to 31 rows: one mask word)
   return q < n ? q : n;
 }
 // warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (3 blocks of 10 per warp)
