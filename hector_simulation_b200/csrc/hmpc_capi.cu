@@ -118,7 +118,7 @@ class HostPool {
 constexpr int NCHUNK = 4;  // the host-buffer path pipelines pack / H2D / solve / D2H over this many chunks
 
 struct ClassCfg {
-  int nb_hi, nb_cap, qmax, threads, smem, grid_cap, variant, use_T;
+  int nb_hi, nb_cap, qmax, threads, smem, grid_cap, variant, tcap;
   hmpc::Layout L;
 };
 
@@ -262,15 +262,15 @@ int build_classes(hmpc_ctx* c)
       const int n = 6 * k.nb_cap;
       if (c->cls[1].qmax >= n) { c->ncls = 2; break; }  // class 1 already holds every row
       k.qmax = n;
-      k.use_T = 0;
+      k.tcap = 0;
       if (N == 10) {  // the runtime-layout instantiation of the same shape (the fixed one folds class 1's layout)
         k.variant = 18;
         k.threads = 256;
       }
-      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32, false);
+      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32, 0);
       while (k.L.total > 226 * 1024 && k.qmax > c->cls[1].qmax) {
         k.qmax -= 4;
-        k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32, false);
+        k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32, 0);
       }
       if (k.qmax <= c->cls[1].qmax) { c->ncls = 2; break; }
       k.smem = k.L.total;
@@ -294,8 +294,8 @@ int build_classes(hmpc_ctx* c)
       k.threads = kBucketThreads[bucket];
     }
     k.qmax = hmpc::class_qmax(N, i);
-    k.use_T = hmpc::class_use_T(N, i) ? 1 : 0;
-    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32, k.use_T != 0);
+    k.tcap = hmpc::class_tcap(N, i);
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, c->rec_stride, k.threads / 32, k.tcap);
     k.smem = k.L.total;
     int occ = 0;
     if (cuda_fail(prep_class(k, &occ), "kernel attribute/occupancy (is this an sm_100a device?)")) return HMPC_ERR_CUDA;
@@ -640,7 +640,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     ka.esc_list = (i + 1 < c->ncls) ? lists + (size_t)(i + 1) * c->max_batch : nullptr;
     ka.nb_cap = k.nb_cap;
     ka.qmax = k.qmax;
-    ka.use_T = k.use_T;
+    ka.tcap = k.tcap;
     ka.L = k.L;
     ka.dbg_clk = g_dbg_clk;
     const int grid = B < k.grid_cap ? B : k.grid_cap;
@@ -700,7 +700,7 @@ int enqueue_solve_hostlists(hmpc_ctx* c, const void* d_records, int nb, int* h_b
     ka.split_nb = -1;
     ka.nb_cap = k.nb_cap;
     ka.qmax = k.qmax;
-    ka.use_T = k.use_T;
+    ka.tcap = k.tcap;
     ka.L = k.L;
     ka.dbg_clk = g_dbg_clk;
     const int grid = cnt < k.grid_cap ? cnt : k.grid_cap;
@@ -772,7 +772,7 @@ HMPC_EXTERNC int hmpc_assemble_device(hmpc_ctx* c, const void* d_records, int B,
   ka.esc_list = nullptr;
   ka.nb_cap = k.nb_cap;
   ka.qmax = k.qmax;
-  ka.use_T = k.use_T;
+  ka.tcap = k.tcap;
   ka.L = k.L;
   ka.dbg_H = d_H;
   ka.dbg_g = d_g;

@@ -52,7 +52,7 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 // float32 values; the sweep leaves float64 there.
 __host__ __device__ constexpr int toff(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
 
-__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride, int nwarps, bool use_T = true)
+__host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, int rec_stride, int nwarps, int tcap)
 {
   Layout L{};
   const int n = 6 * nb_cap;
@@ -69,14 +69,13 @@ __host__ __device__ constexpr Layout make_layout(int N, int nb_cap, int qmax, in
   L.uni = o;
   int s = L.uni;  // solver view; one slot more than the capacity: the entering row needs one while a blocking row leaves
   const int ns = qmax + 1;
-  L.T = s;    s += (use_T ? ns : 1) * n * 8;        // H^-1 a_j of every working-set slot (without the cache: of the entering row)
+  L.T = s;    s += (tcap + 1) * n * 8;              // H^-1 a_j of the first tcap working-set slots + one column for an entering row beyond them
   L.Sv = s;   s += ns * (ns + 1) / 2 * 8;           // (A_W H^-1 A_W')^-1, packed lower rows
   L.lam = s;  s += ns * 8;
   L.dv = s;   s += 2 * (ns + 2) * 8;                // step-direction scratch / double-buffered pivot column of the block start
   L.rr = s;   s += ns * 8;
   L.wsl = s;  s += align16(ns * 4);
-  if (use_T) L.zb = L.gq;  // the gradient is spent once x0 is known; the no-cache mode keeps A_W'r there and needs both
-  else { L.zb = s; s += n * 8; }
+  L.zb = L.gq;  // the gradient is spent once x0 is known (the steps that also keep A_W'r there order the two uses by a barrier)
   // sweep view: the tiles live in registers during the sweep, so its buffers take H's place when they fit there
   const int sweep_bytes = 2 * nt8 * 64 * 8 + nwarps * 2 * 64 * 8;
   int w = (sweep_bytes <= ntile * 64 * 8) ? L.H : L.uni;
@@ -106,13 +105,20 @@ __host__ __device__ constexpr int record_stride(int N) { return align16((54 + 12
 // class 0 (a walking gait ends with about one active row per stance step; 17 at N = 10 — what 7 CTAs/SM leave room for), 31 for class 1; an instance that needs more
 // escalates to the next class (class 2 = class 1's size with as many slots as shared memory holds).
 __host__ __device__ constexpr int class_nb_cap(int N, int cls) { return N * (1 + cls); }
-// The H^-1 a_j cache costs (qmax + 1) * n doubles: the long-horizon double-support class (extension configs) does without
-// it — its primal steps go through a full H^-1 product instead — and spends the room on working-set capacity.
-__host__ __device__ constexpr bool class_use_T(int N, int cls) { return cls == 0 || N <= 10; }
+// The H^-1 a_j cache costs n doubles per working-set slot.  Class 0 caches the first N + 4 slots (a walking gait ends with
+// about one active row per stance step) and holds up to 2N + 4 rows: the rare instance that needs more than the cache takes
+// its primal steps through a full H^-1 product for the uncached slots instead of escalating to the next class.  The
+// long-horizon double-support class (extension configs) and class 2 do without the cache and spend the room on capacity.
+__host__ __device__ constexpr int class_tcap(int N, int cls)
+{
+  const int n = 6 * class_nb_cap(N, cls);
+  const int t = cls == 0 ? N + 4 : (N <= 10 ? 31 : 0);
+  return t < n ? t : n;
+}
 __host__ __device__ constexpr int class_qmax(int N, int cls)
 {
   const int n = 6 * class_nb_cap(N, cls);
-  const int q = cls == 0 ? N + 7 : (class_use_T(N, cls) ? 31 : 96);  // (the block start handles up to 31 rows: one mask word)
+  const int q = cls == 0 ? 2 * N + 4 : (N <= 10 ? 31 : 96);  // (the block start handles up to 31 rows: one mask word)
   return q < n ? q : n;
 }
 // warps a class needs: one per pair of tile rows of the sweep, one thread per constraint row (3 blocks of 10 per warp)
@@ -124,7 +130,7 @@ __host__ __device__ constexpr int class_warps(int N, int cls)
 }
 __host__ __device__ constexpr Layout class_layout(int N, int cls, int nwarps)
 {
-  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N), nwarps, class_use_T(N, cls));
+  return make_layout(N, class_nb_cap(N, cls), class_qmax(N, cls), record_stride(N), nwarps, class_tcap(N, cls));
 }
 
 struct KernelArgs {
@@ -147,7 +153,7 @@ struct KernelArgs {
   int max_iter;
   double tol_kkt;                // a row counts as violated below -tol_kkt * max(1, |x0|_inf)   (default 1e-9)
   double tol_dep;                // an entering row is dependent on the working set when its curvature falls below tol_dep * a'H^-1a (1e-11)
-  int use_T;                     // 1: the shared-memory carve-up holds the H^-1 a_j cache (runtime-layout launches; fixed: yes)
+  int tcap;                      // working-set slots with a cached H^-1 a_j column (runtime-layout launches; fixed: class_tcap)
   int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
   int warm_start;                // 1: propose the working set in `ws_state` (previous tick) to the block start
   int ws_shift;                  // MPC steps the horizon moved since that tick (the closed loop: 1)
@@ -937,7 +943,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   const int nb_cap = FIX ? class_nb_cap(NF, CLS) : ka.nb_cap;
   const int qmax = FIX ? class_qmax(NF > 0 ? NF : 1, CLS) : ka.qmax;
   const int rec_stride = FIX ? record_stride(NF) : ka.rec_stride;
-  const bool useT = FIX ? true : (ka.use_T != 0);
+  const int tcap = FIX ? class_tcap(NF > 0 ? NF : 1, CLS) : ka.tcap;
   Layout L;
   if constexpr (FIX) {
     constexpr Layout LC = class_layout(NF, CLS, NW);
@@ -1604,7 +1610,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // minimum is a masked REDUX over the block's ten lanes, each entry of [S | b] lives in one thread's register during a
     // Gauss-Jordan sweep with one barrier per pivot.  Any doubt (capacity, a non-positive pivot) falls back to the plain
     // iteration from the unconstrained minimiser.
-    if (qmax <= 31 && useT) {
+    if (qmax <= 31 && tcap > 0) {
       int* newslot = reinterpret_cast<int*>(rr);       // [nadd] slots of the entering rows (rr is not live yet)
       double* colb = dvs;                              // [2][qmax + 3] pivot column, b_p and 1/d, double-buffered
       const int cst = qmax + 3;
@@ -1668,7 +1674,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const unsigned am0 = amask[0];
         __syncthreads();  // everybody has read the counts and the slot mask
         // no violated row (the iteration below confirms and stops) / no room for the rows or for one S entry per thread
-        if (nadd == 0 || q + nadd > qmax || tri(32 - __clz(am0 | ((1u << (q + nadd)) - 1u))) > NT) break;
+        // (every slot of a block round needs its cached column: the highest slot must stay below tcap)
+        const int qh_new = 32 - __clz(am0 | ((1u << (q + nadd)) - 1u));
+        if (nadd == 0 || q + nadd > qmax || qh_new > tcap || tri(qh_new) > NT) break;
         unsigned mybit = 0u;
         if (cand) {  // the rank-th entering row takes the rank-th free slot
           unsigned fm = ~am0;
@@ -1838,7 +1846,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       const int kp = p / 10, nip = (blk_sl[kp] & 1) * 10 + (p - 10 * kp);
       const double* np_ = nrm + nip * 6;
       const int f = flags[7];  // slot the entering row will take
-      double* Tf = useT ? T + f * n : T;
+      double* Tf = T + (f < tcap ? f : tcap) * n;  // a slot beyond the cache uses the spare column
       if (isvar) Tf[vi] = hinv_dot6(Hd, vi, 6 * kp, np_);
       __syncthreads();
 
@@ -1954,34 +1962,37 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         if (decision >= 2) { code = (decision == 2) ? ST_INFEASIBLE : ST_WS_CAP; break; }
         const double t = dsc[0];
         // primal step direction z = t_p - sum_j r_j t_j, x += t z
-        if (useT) {
+        {
+          // z = t_p - sum_j r_j t_j: cached columns directly, the slots beyond the cache through one H^-1 product of
+          // A_W' r restricted to them (gq, padded to whole tiles, holds it; zb shares that memory: barriers in between)
+          const int qhe = flags[8];
+          const int qc = qhe < tcap ? qhe : tcap;
+          double z = 0.0;
           if (isvar) {
-            const int qhe = flags[8];
             double z0 = Tf[vi], z1 = 0.0;
             int j = 0;
-            for (; j + 1 < qhe; j += 2) {
+            for (; j + 1 < qc; j += 2) {
               z0 = fma(-rr[j], T[j * n + vi], z0);
               z1 = fma(-rr[j + 1], T[(j + 1) * n + vi], z1);
             }
-            if (j < qhe) z0 = fma(-rr[j], T[j * n + vi], z0);
-            const double z = z0 + z1;
-            zb[vi] = z;
-            xreg = fma(t, z, xreg);
+            if (j < qc) z0 = fma(-rr[j], T[j * n + vi], z0);
+            z = z0 + z1;
           }
-        } else {
-          // no cache: z = t_p - H^-1 (A_W' r) through one full product (gq, padded to whole tiles, holds A_W' r)
-          if (isvar) {
-            const int qhe = flags[8], kb = vi / 6, c = vi - 6 * kb;
-            double acc = 0.0;
-            for (int j = 0; j < qhe; j++) {
-              const int w = wsl[j];
-              if ((w >> 8) == kb) acc = fma(rr[j], nrm[(w & 0xff) * 6 + c], acc);
+          if (qhe > tcap) {
+            if (isvar) {
+              const int kb = vi / 6, c = vi - 6 * kb;
+              double acc = 0.0;
+              for (int j = tcap; j < qhe; j++) {
+                const int w = wsl[j];
+                if ((w >> 8) == kb) acc = fma(rr[j], nrm[(w & 0xff) * 6 + c], acc);
+              }
+              gq[vi] = acc;
             }
-            gq[vi] = acc;
+            __syncthreads();
+            if (isvar) z -= hinv_rowdot(Hd, vi, NT8, gq);
+            __syncthreads();
           }
-          __syncthreads();
           if (isvar) {
-            const double z = Tf[vi] - hinv_rowdot(Hd, vi, NT8, gq);
             zb[vi] = z;
             xreg = fma(t, z, xreg);
           }
@@ -2011,11 +2022,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     const int qhf = flags[9];
     const int nref = (code == ST_OK && q > 24) ? 2 : 0;
     for (int round = 0;; round++) {
-      if (code == ST_OK && !useT) {
+      const bool beyond = code == ST_OK && qhf > tcap;  // rows in slots without a cached column
+      if (beyond) {
         if (isvar) {
           const int kb = vi / 6, c = vi - 6 * kb;
           double acc = 0.0;
-          for (int j = 0; j < qhf; j++) {
+          for (int j = tcap; j < qhf; j++) {
             const int w = wsl[j];
             if (((amask[j >> 5] >> (j & 31)) & 1u) && (w >> 8) == kb) acc = fma(lam[j], nrm[(w & 0xff) * 6 + c], acc);
           }
@@ -2023,19 +2035,16 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         }
         __syncthreads();
       }
-      if (isvar) {
-        double acc = xreg;
-        if (code == ST_OK) {
-          acc = x0[vi];
-          if (useT) {
-            for (int j = 0; j < qhf; j++)
-              if ((amask[j >> 5] >> (j & 31)) & 1u) acc = fma(lam[j], T[j * n + vi], acc);
-          } else {
-            acc += hinv_rowdot(Hd, vi, NT8, gq);
-          }
-        }
-        zb[vi] = acc;
+      double xfin = xreg;
+      if (isvar && code == ST_OK) {
+        xfin = x0[vi];
+        const int qc = qhf < tcap ? qhf : tcap;
+        for (int j = 0; j < qc; j++)
+          if ((amask[j >> 5] >> (j & 31)) & 1u) xfin = fma(lam[j], T[j * n + vi], xfin);
+        if (beyond) xfin += hinv_rowdot(Hd, vi, NT8, gq);
       }
+      if (beyond) __syncthreads();  // zb shares gq's memory
+      if (isvar) zb[vi] = xfin;
       __syncthreads();
       if (round == nref) break;
       if (wid == 0) {

@@ -81,7 +81,7 @@ void launch_variant(int variant, const hmpc::KernelArgs& ka)
   }
 }
 struct ClassCfg {
-  int variant, nb_cap, qmax, use_T;
+  int variant, nb_cap, qmax, tcap;
   hmpc::Layout L;
 };
 // hmpc_capi.cu build_classes, minus the CUDA occupancy calls
@@ -97,8 +97,8 @@ int build_classes(int N, ClassCfg* cls)
     while (bucket < 4 && kBucketThreads[bucket] < 32 * warps) bucket++;
     k.variant = (N == 10) ? i : 10 + 5 * i + bucket;
     k.qmax = hmpc::class_qmax(N, i);
-    k.use_T = hmpc::class_use_T(N, i) ? 1 : 0;
-    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, variant_threads(k.variant) / 32, k.use_T != 0);
+    k.tcap = hmpc::class_tcap(N, i);
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, variant_threads(k.variant) / 32, k.tcap);
   }
   {
     ClassCfg& k = cls[2];
@@ -106,11 +106,11 @@ int build_classes(int N, ClassCfg* cls)
     if (N == 10) k.variant = 18;
     const int n = 6 * k.nb_cap, nw = variant_threads(k.variant) / 32;
     k.qmax = n;
-    k.use_T = 0;
-    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, nw, false);
+    k.tcap = 0;
+    k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, nw, 0);
     while (k.L.total > 226 * 1024 && k.qmax > cls[1].qmax) {
       k.qmax -= 4;
-      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, nw, false);
+      k.L = hmpc::make_layout(N, k.nb_cap, k.qmax, rs, nw, 0);
     }
     if (k.qmax <= cls[1].qmax || cls[1].qmax >= n) ncls = 2;
   }
@@ -258,7 +258,7 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.esc_list = (!raw && i + 1 < ncls) ? lists + (size_t)(i + 1) * B : nullptr;
     ka.nb_cap = cls[i].nb_cap;
     ka.qmax = cls[i].qmax;
-    ka.use_T = cls[i].use_T;
+    ka.tcap = cls[i].tcap;
     ka.L = cls[i].L;
     ka.dbg_H = dH; ka.dbg_g = dg; ka.dbg_F = dF; ka.dbg_lb = dlb; ka.dbg_ub = dub;
     launch_variant(cls[i].variant, ka);

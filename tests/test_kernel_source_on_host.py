@@ -406,6 +406,12 @@ def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
         r = subprocess.run([exe, str(f), str(g["horizon"]), *flags], capture_output=True, text=True, env=env, timeout=900)
         assert "ThreadSanitizer" not in r.stderr, (name, flags, r.stderr[:3000])
         assert r.returncode == 0, (name, flags, r.returncode, r.stdout, r.stderr[-500:])
+    # working sets beyond the column cache (the full-product primal steps share gq's memory with zb)
+    big = scenarios.make_batch(2, 1024, horizon=10, seed=scenarios.config_seed(2) + 4000)[0][[217]]
+    f = tmp_path / "beyond_cache.bin"
+    np.ascontiguousarray(interface.pack_records(big, 10)).tofile(f)
+    r = subprocess.run([exe, str(f), "10"], capture_output=True, text=True, env=env, timeout=900)
+    assert "ThreadSanitizer" not in r.stderr and r.returncode == 0, r.stderr[:3000]
 
 
 def test_solve_kernel_source_edge_cases(emul, oracle):
@@ -433,6 +439,25 @@ def test_solve_kernel_source_edge_cases(emul, oracle):
         assert (info[:, 0] == 0).all()
         assert rel_err(w[1:], ref[1:]).max() < 5e-5
         assert (w[ref == 0.0] == 0.0).all()
+
+
+def test_solve_kernel_source_working_sets_beyond_the_column_cache(emul, oracle):
+    """Class 0 caches H^-1 a_j for its first N + 4 working-set slots and holds up to 2N + 4 rows: walking robots whose optimum
+    has more active rows than the cache (15, 16 and 19 here; ~1 % of the configs[1] batches) stay in class 0 — their primal
+    steps go through a full H^-1 product for the slots beyond the cache — instead of being handed to the slower class 1."""
+    if not oracle.has_qpoases():
+        pytest.skip("oracle/_ref without qpOASES")
+    from conftest import rel_err
+
+    N = 10
+    picks = ((1000, [780, 20]), (4000, [217]))
+    recs = np.concatenate([scenarios.make_batch(2, 1024, horizon=N, seed=scenarios.config_seed(2) + off)[0][idx] for off, idx in picks])
+    w, st, _, launched, _ = _solve(emul, recs, N, tau=False)
+    assert launched.tolist() == [3, 0, 0]                              # nobody escalates
+    assert (interface.status_code(st) == 0).all()
+    assert sorted(interface.status_nactive(st).tolist()) == [15, 16, 19]
+    ref, info = oracle.solve_batch(recs, oracle.make_setup(N))
+    assert (info[:, 0] == 0).all() and rel_err(w, ref, 12).max() < 5e-6 and rel_err(w, ref).max() < 5e-5
 
 
 def test_solve_kernel_source_is_insensitive_to_its_two_tolerances(emul):
