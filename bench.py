@@ -292,7 +292,8 @@ def main():
 
     # synthetic states (configs[1] walking gait / configs[2] mixed); each rank gets its own shard (different seed)
     cfg = 2 if args.workload == "walk" else 3
-    recs, inputs = scenarios.make_batch(cfg, B, horizon=N, seed=scenarios.config_seed(cfg) + 1000 * rank)
+    seed_rank = int(os.environ.get("HMPC_BENCH_SEED_RANK", rank))  # (developer knob: another rank's shard on this GPU)
+    recs, inputs = scenarios.make_batch(cfg, B, horizon=N, seed=scenarios.config_seed(cfg) + 1000 * seed_rank)
     mpc = interface.BatchedMPC(B, N, device=local_rank)
     stride = interface.record_bytes(N)
     packed = torch.from_numpy(interface.pack_records(recs, N)).cuda()
@@ -345,7 +346,8 @@ def main():
         factory = lambda bl: sharding.GpuBackend(bl, N, rank, world, local_rank, bcast)
     else:
         factory = None
-    recs_c = np.ascontiguousarray(recs)
+    recs_c = interface.page_aligned(recs.shape, recs.dtype)   # a control loop's registered arrays own their pages
+    recs_c[...] = recs
     if world > 1:
         sh = sharding.ShardedMPC(world * B, N, rank, world, factory, scenarios.UPDATE_DTYPE)
         out_w, out_s = sh.out_w, sh.out_s
@@ -354,8 +356,8 @@ def main():
         def e2e_step():
             sh.tick()
     else:
-        out_w = np.zeros((B, 12 * N), dtype=np.float64)  # caller-owned result buffers, reused every tick
-        out_s = np.zeros(B, dtype=np.int32)
+        out_w = interface.page_aligned((B, 12 * N), np.float64)  # caller-owned result buffers, reused every tick
+        out_s = interface.page_aligned(B, np.int32)
         mpc.pin(recs_c, out_w, out_s)
 
         def e2e_step():

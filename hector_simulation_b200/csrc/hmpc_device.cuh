@@ -1665,7 +1665,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const unsigned cm = __ballot_sync(0xffffffffu, cand);
         if (lane == 0) redi[wid] = __popc(cm);
         __syncthreads();
-        int nadd = 0, rank = __popc(cm & ((1u << lane) - 1u));
+        int nadd = 0, rank = __popc(cm & ((1u << lane) - 1u));  // row order: the earliest steps first
         for (int w = 0; w < NW; w++) {
           const int c = redi[w];
           nadd += c;
@@ -1673,10 +1673,14 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         }
         const unsigned am0 = amask[0];
         __syncthreads();  // everybody has read the counts and the slot mask
-        // no violated row (the iteration below confirms and stops) / no room for the rows or for one S entry per thread
-        // (every slot of a block round needs its cached column: the highest slot must stay below tcap)
-        const int qh_new = 32 - __clz(am0 | ((1u << (q + nadd)) - 1u));
-        if (nadd == 0 || q + nadd > qmax || qh_new > tcap || tri(qh_new) > NT) break;
+        // Every slot of a block round needs its cached column and one thread per entry of S: rows enter only while free
+        // slots below tcap remain (the first candidates in row order take them, the others wait for the next round or for
+        // the dual iteration).  No violated row: the iteration below confirms and stops.
+        if (nadd == 0 || (am0 >> tcap) != 0u) break;
+        const int room = tcap - __popc(am0);
+        if (nadd > room) nadd = room;
+        if (nadd <= 0 || tri(tcap) > NT) break;
+        if (rank >= nadd) cand = false;
         unsigned mybit = 0u;
         if (cand) {  // the rank-th entering row takes the rank-th free slot
           unsigned fm = ~am0;

@@ -191,6 +191,17 @@ def status_nactive(s):
     return (np.asarray(s) >> 20) & 0xFF
 
 
+def page_aligned(shape, dtype) -> np.ndarray:
+    """A zeroed array that owns whole memory pages (start aligned, size rounded up): what a control loop should hand to
+    BatchedMPC.pin / hmpc_pin_host_buffer — a C caller uses posix_memalign the same way."""
+    page = os.sysconf("SC_PAGESIZE") if hasattr(os, "sysconf") else 4096
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    raw = np.zeros((nbytes + page - 1) // page * page + page, dtype=np.uint8)
+    off = (-raw.ctypes.data) % page
+    return raw[off:off + nbytes].view(dt).reshape(shape)
+
+
 class BatchedMPC:
     """Context for `max_batch` robots of `horizon` steps on one GPU (hmpc_create / hmpc_destroy)."""
 
@@ -219,7 +230,9 @@ class BatchedMPC:
     def pin(self, *arrays: np.ndarray) -> None:
         """Register caller-owned arrays (records, wrench, status) for the in-place mode of solve_batch: the GPU then
         reads the records where they lie and writes the results where the caller wants them (hmpc_pin_host_buffer).
-        The arrays must stay alive until unpin()/close()."""
+        The arrays must stay alive until unpin()/close().  Registration pins whole pages: allocate the arrays with
+        page_aligned() so that no unrelated heap object shares their pages (a later cudaMemcpy of such a neighbour, partly
+        inside a registered page range, fails with cudaErrorInvalidValue)."""
         for a in arrays:
             assert a.flags.c_contiguous
             _check(lib().hmpc_pin_host_buffer(self._h, a.ctypes.data, a.nbytes))

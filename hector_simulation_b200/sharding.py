@@ -99,9 +99,11 @@ class ShardedMPC:
         self.lo, self.hi = self.bounds[rank]
         self.b_local = max(h - l for l, h in self.bounds)
         self.backend = backend_factory(self.b_local)
-        self.recs = np.zeros(self.b_local, dtype=record_dtype)
-        self.out_w = np.zeros((self.b_local, 12 * horizon), dtype=np.float64)
-        self.out_s = np.zeros(self.b_local, dtype=np.int32)
+        from .interface import page_aligned   # registered (pinned) arrays own their pages
+
+        self.recs = page_aligned(self.b_local, record_dtype)
+        self.out_w = page_aligned((self.b_local, 12 * horizon), np.float64)
+        self.out_s = page_aligned(self.b_local, np.int32)
         self.backend.register(self.recs, self.out_w, self.out_s)
 
     def local_slice(self, records_global: np.ndarray) -> np.ndarray:

@@ -160,6 +160,9 @@ HMPC_EXTERNC int hmpc_solve_device_ex(hmpc_ctx* ctx, const void* d_records, int 
  * float->double pass on the host.  It is used whenever `in`, `wrench_out` and `status` (if given) of a call all lie
  * inside pinned ranges; results are identical to the staged path.  The caller keeps the memory allocated until
  * hmpc_unpin_host_buffer / hmpc_destroy.  (The reference-style entry points pin their own globals.) */
+/* Registration is page-granular: the pages that hold [ptr, ptr + bytes) are pinned whole.  Give the arrays their own pages
+ * (posix_memalign to the page size, size rounded up): an unrelated host buffer that shares such a page only partly cannot be
+ * the source / destination of a later cudaMemcpy (cudaErrorInvalidValue). */
 HMPC_EXTERNC int hmpc_pin_host_buffer(hmpc_ctx* ctx, void* ptr, size_t bytes);
 HMPC_EXTERNC int hmpc_unpin_host_buffer(hmpc_ctx* ctx, void* ptr);
 

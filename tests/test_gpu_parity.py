@@ -333,8 +333,12 @@ def test_in_place_mode_equals_staged_path():
         recs, _ = scenarios.make_batch(cfg, B, horizon=horizon, seed=31 + horizon)
         mpc = interface.BatchedMPC(B, horizon)
         w_ref, s_ref = mpc.solve_batch(recs)                      # staged: nothing pinned yet
-        w = np.full((B, 12 * horizon), np.nan)
-        s = np.full(B, -1, dtype=np.int32)
+        staged, recs = recs, interface.page_aligned(recs.shape, recs.dtype)   # registered arrays own their pages
+        recs[...] = staged
+        w = interface.page_aligned((B, 12 * horizon), np.float64)
+        s = interface.page_aligned(B, np.int32)
+        w[...] = np.nan
+        s[...] = -1
         mpc.pin(recs, w, s)
         mpc.solve_batch(recs, out=(w, s))
         assert np.array_equal(s, s_ref) and np.array_equal(w.astype(np.float32), w_ref.astype(np.float32)), (horizon, np.abs(w - w_ref).max())
@@ -355,8 +359,10 @@ def test_in_place_mode_escalates_on_the_device():
     recs = np.ascontiguousarray(np.repeat(g["records"].view(scenarios.UPDATE_DTYPE).reshape(-1)[:1], 3))
     mpc = interface.BatchedMPC(3, 10)
     w_ref, s_ref = mpc.solve_batch(recs)
-    w = np.zeros_like(w_ref)
-    s = np.zeros_like(s_ref)
+    staged, recs = recs, interface.page_aligned(recs.shape, recs.dtype)
+    recs[...] = staged
+    w = interface.page_aligned(w_ref.shape, w_ref.dtype)
+    s = interface.page_aligned(s_ref.shape, s_ref.dtype)
     mpc.pin(recs, w, s)
     mpc.solve_batch(recs, out=(w, s))
     assert (interface.status_code(s) == 0).all() and np.array_equal(w.astype(np.float32), w_ref.astype(np.float32))
