@@ -156,6 +156,7 @@ struct hmpc_ctx {
   cudaEvent_t solved = nullptr, gathered[2] = {nullptr, nullptr};
   int* d_ws = nullptr;             // [max_batch][WS_STATE_INTS] working sets of the previous tick (closed-loop warm start)
   int warm_start = 1;              // hmpc_rollout_device proposes them to the next tick (HMPC_WARM_START=0: cold start every tick)
+  int lockstep = 1;                // waves of a multi-wave launch start together (HMPC_LOCKSTEP=0: free-running, for A/B runs)
   int block_rounds = 4;  // block start of the active-set stage (HMPC_BLOCK_ROUNDS=0: plain dual iteration, for A/B runs)
   // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
   // reference records from them and write results to them in place (no packing, no staging copies, no widening)
@@ -579,6 +580,8 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
   if (!bad) {
     const char* br = getenv("HMPC_BLOCK_ROUNDS");
     if (br) c->block_rounds = atoi(br);
+    const char* ls = getenv("HMPC_LOCKSTEP");
+    if (ls) c->lockstep = atoi(ls);
     const char* wm = getenv("HMPC_WARM_START");
     if (wm) c->warm_start = atoi(wm);
   }
@@ -635,6 +638,7 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     ka.list = (i == 0) ? nullptr : lists + (size_t)i * c->max_batch;
     ka.split_nb = (i == 0) ? k.nb_hi : -1;
     ka.counts_next = (i == 0) ? counts_next : nullptr;
+    ka.wave_sync = (i == 0 && c->lockstep) ? reinterpret_cast<unsigned*>(counts + 3) : nullptr;  // 4th length slot: unused
     ka.counts = counts;
     ka.cls = i;
     ka.esc_list = (i + 1 < c->ncls) ? lists + (size_t)(i + 1) * c->max_batch : nullptr;

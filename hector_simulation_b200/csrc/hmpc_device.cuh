@@ -148,6 +148,7 @@ struct KernelArgs {
   int* esc_list;                 // next class's list (working-set overflow escalation, size-class hand-over) or nullptr
   int split_nb;                  // >= 0: classify in this launch — an instance with more stance blocks goes to esc_list
   int* counts_next;              // the next call's list lengths, zeroed by this launch (device-resident chain), or nullptr
+  unsigned* wave_sync;           // arrival counter of the wave barrier of multi-wave launches (zero at launch), or nullptr
   int nb_cap;                    // capacity (blocks of 6 variables) the shared-memory carve is sized for
   int qmax;                      // working-set capacity
   int max_iter;
@@ -532,15 +533,14 @@ __device__ inline double leg_torque(const double* q5, int leg, int j, const doub
   return t;
 }
 
-// fast fp64 reciprocal: MUFU.RCP64H seed + Newton steps (<= 2 ulp; the sweep and ratio tests do not need
-// correctly rounded division, and the IEEE division sequence is ~6x the instructions)
+// fast fp64 reciprocal: MUFU.RCP64H seed (relative error 1e-6 measured, tests/tools/ubench.cu) + two Newton steps:
+// identical to the IEEE quotient on 5e7 probe values, a third step changes nothing; the IEEE division sequence is ~6x
+// the instructions and the reciprocals sit on the critical chains of the tile inversions and the Schur sweeps
 __device__ __forceinline__ double fast_rcp(double x)
 {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double e = fma(-x, r, 1.0);
-  r = fma(e, r, r);
-  e = fma(-x, r, 1.0);
   r = fma(e, r, r);
   e = fma(-x, r, 1.0);
   r = fma(e, r, r);
@@ -1001,7 +1001,32 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
   if (ka.counts_next && blockIdx.x == 0 && tid < 4) ka.counts_next[tid] = 0;
   const int count = ka.list ? ka.counts[ka.cls] : ka.batch;
 
-  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+  // Multi-wave batches: the resident CTAs start every wave together (a bounded global barrier between waves).  All
+  // CTAs of an SM then execute the same stage at the same time and share the instruction cache lines of this ~190 KB
+  // kernel; drifting apart, 28 warps in different stages thrash it (measured at 8192 robots: 237 k cycles per robot
+  // against 140 k in the single-wave 1024-robot batch, same residency).  The wait is bounded: a CTA that is not joined
+  // within ~200 us (something else holds SMs) stops waiting for good — lockstep is an optimisation, not a dependency.
+  const int trips = (count + (int)gridDim.x - 1) / (int)gridDim.x;
+  bool lockstep = ka.wave_sync != nullptr && trips > 1;
+  for (int trip = 0; trip < trips; trip++) {
+    const int idx = blockIdx.x + trip * gridDim.x;
+    if (lockstep && trip > 0) {
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(ka.wave_sync, 1u);
+        const unsigned target = (unsigned)trip * gridDim.x;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (atomicAdd(ka.wave_sync, 0u) < target) {
+          if (clock64() - t0 > 400000ll) { ok = false; break; }
+        }
+        flags[15] = ok ? 1 : 0;
+      }
+      __syncthreads();
+      if (!flags[15]) lockstep = false;
+      __syncthreads();
+    }
+    if (idx >= count) continue;  // the last wave may not fill the grid
     const int inst = ka.list ? ka.list[idx] : idx;
     HMPC_STAMP(0);
     // ---------------- stage 0: record -> shared memory (TMA bulk copy) ----------------

@@ -253,6 +253,7 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.list = fused ? nullptr : lists + (size_t)i * B;
     ka.split_nb = fused ? nb_hi0 : -1;
     ka.counts_next = fused ? counts + 4 : nullptr;
+    ka.wave_sync = fused ? reinterpret_cast<unsigned*>(counts + 3) : nullptr;  // one emulated CTA walks all instances: B waves
     ka.counts = counts;
     ka.cls = i;
     ka.esc_list = (!raw && i + 1 < ncls) ? lists + (size_t)(i + 1) * B : nullptr;
