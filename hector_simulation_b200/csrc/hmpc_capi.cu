@@ -638,7 +638,8 @@ int enqueue_solve(hmpc_ctx* c, const void* d_records, int B, float* d_wrench32, 
     ka.list = (i == 0) ? nullptr : lists + (size_t)i * c->max_batch;
     ka.split_nb = (i == 0) ? k.nb_hi : -1;
     ka.counts_next = (i == 0) ? counts_next : nullptr;
-    ka.wave_sync = (i == 0 && c->lockstep) ? reinterpret_cast<unsigned*>(counts + 3) : nullptr;  // 4th length slot: unused
+    // arrival counters of the wave barriers: the two length slots the chain does not use (class 0: [3], class 1: [0])
+    ka.wave_sync = (c->lockstep && i < 2) ? reinterpret_cast<unsigned*>(counts + (i == 0 ? 3 : 0)) : nullptr;
     ka.counts = counts;
     ka.cls = i;
     ka.esc_list = (i + 1 < c->ncls) ? lists + (size_t)(i + 1) * c->max_batch : nullptr;
