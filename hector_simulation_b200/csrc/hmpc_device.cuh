@@ -1981,8 +1981,10 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
             flags[8] = qhi;
             flags[9] = qhn;
             dsc[0] = dependent ? 0.0 : t;
-            int fn = 0;  // lowest free slot
-            while (fn < qmax && ((amask[fn >> 5] >> (fn & 31)) & 1u)) fn++;  // at most qmax rows are in use: fn <= qmax, a valid slot
+            int fn = 0;  // lowest free slot (at most qmax rows are in use: fn <= qmax, a valid slot)
+            if (qmax <= 31) fn = __ffs(~amask[0]) - 1;
+            else
+              while (fn < qmax && ((amask[fn >> 5] >> (fn & 31)) & 1u)) fn++;
             flags[7] = fn;
           }
         }
