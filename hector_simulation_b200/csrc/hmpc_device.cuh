@@ -1637,6 +1637,11 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     // iteration from the unconstrained minimiser.
     if (qmax <= 31 && tcap > 0) {
       int* newslot = reinterpret_cast<int*>(rr);       // [nadd] slots of the entering rows (rr is not live yet)
+      // slots a block round may use: those with a cached column, as many as one S entry per thread allows (tri(q) <= NT)
+      int slot_cap = (int)((sqrtf(8.f * (float)NT + 1.f) - 1.f) * 0.5f);
+      while (tri(slot_cap + 1) <= NT) slot_cap++;
+      while (tri(slot_cap) > NT) slot_cap--;
+      slot_cap = slot_cap < tcap ? slot_cap : tcap;
       double* colb = dvs;                              // [2][qmax + 3] pivot column, b_p and 1/d, double-buffered
       const int cst = qmax + 3;
       // Warm start (closed loop): the rows that were active at the previous tick's optimum, moved with the horizon, are
@@ -1699,12 +1704,12 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const unsigned am0 = amask[0];
         __syncthreads();  // everybody has read the counts and the slot mask
         // Every slot of a block round needs its cached column and one thread per entry of S: rows enter only while free
-        // slots below tcap remain (the first candidates in row order take them, the others wait for the next round or for
-        // the dual iteration).  No violated row: the iteration below confirms and stops.
-        if (nadd == 0 || (am0 >> tcap) != 0u) break;
-        const int room = tcap - __popc(am0);
+        // slots below slot_cap remain (the first candidates in row order take them, the others wait for the next round or
+        // for the dual iteration).  No violated row: the iteration below confirms and stops.
+        if (nadd == 0 || (am0 >> slot_cap) != 0u) break;
+        const int room = slot_cap - __popc(am0);
         if (nadd > room) nadd = room;
-        if (nadd <= 0 || tri(tcap) > NT) break;
+        if (nadd <= 0) break;
         if (rank >= nadd) cand = false;
         unsigned mybit = 0u;
         if (cand) {  // the rank-th entering row takes the rank-th free slot
