@@ -576,3 +576,70 @@ def test_closed_loop_of_kernel_sources(emul, oracle):
     assert np.array_equal(l_k["iters_total"], loop["iters_total"])
     print("closed loop of kernel sources: working-set changes per tick: cold %.2f, warm %.2f" % (cold_changes / (B * (T - 1)), warm_changes / (B * (T - 1))))
     assert warm_changes < 0.5 * cold_changes
+
+
+def test_solve_kernel_source_warm_start_survives_any_proposal(emul):
+    """The warm start only PROPOSES rows to the block start; what it proposes must not be able to change the optimum.  Hostile
+    states — random rows, all ten rows of a block (linearly dependent: 10 rows on 6 variables), rows of the wrong side of
+    every friction pair, swing-phase blocks, counts out of range, the true working set shifted by the wrong number of steps —
+    all end at the cold solve's optimum with status 0 (dependent proposals are dropped and the plain dual iteration runs)."""
+    from conftest import load_golden
+
+    g = load_golden("cfg3_h10")
+    N, B = 10, 8
+    recs = np.ascontiguousarray(g["records"][:B])   # walking and standing robots
+    packed = np.ascontiguousarray(interface.pack_records(recs, N))
+    W = emul.emul_ws_ints()
+
+    def run(ws, shift):
+        w = np.zeros((B, 12 * N), np.float32)
+        st = np.full(B, -1, np.int32)
+        emul.emul_set_ws(_p(ws) if ws is not None else None, shift)
+        try:
+            rc = emul.emul_solve_ex(_p(packed), None, B, N, ctypes.c_float(0.04), ctypes.c_float(500.0), 500, 1 if ws is not None else 0,
+                                    _p(w), None, _p(st), None, None, None, None, None, None, None)
+        finally:
+            emul.emul_set_ws(None, 0)
+        assert rc == 0
+        return w.astype(np.float64), st
+
+    w0, st0 = run(None, 0)
+    assert (interface.status_code(st0) == 0).all()
+    # the true working sets, written back by a recording pass (warm flag on, empty proposals)
+    true_ws = np.zeros((B, W), np.int32)
+    w1, st1 = run(true_ws, 0)
+    assert np.array_equal(w1, w0) and (true_ws[:, 0] > 0).all()
+    rng = np.random.default_rng(7)
+    cases = {}
+    rnd = np.zeros((B, W), np.int32)
+    for b in range(B):
+        c = int(rng.integers(1, W))
+        rnd[b, 0] = c
+        rnd[b, 1:1 + c] = (rng.integers(0, 2 * N, c) << 8) | rng.integers(0, 20, c)
+    cases["random rows"] = (rnd, 0)
+    dep = np.zeros((B, W), np.int32)
+    dep[:, 0] = 20
+    for b in range(B):
+        blk = int(true_ws[b, 1]) >> 8            # a block that is in stance (it holds an active row)
+        leg = blk & 1
+        dep[b, 1:11] = (blk << 8) | (leg * 10 + np.arange(10))
+        dep[b, 11:21] = (((blk + 2) % (2 * N)) << 8) | (leg * 10 + np.arange(10))
+    cases["all ten rows of two blocks"] = (dep, 0)
+    opp = true_ws.copy()
+    for b in range(B):
+        c = opp[b, 0]
+        t = (opp[b, 1:1 + c] & 0xff) % 10
+        flip = np.where(t < 4, t ^ 1, t)          # the other side of the friction pair (rows 0/1 and 2/3)
+        opp[b, 1:1 + c] = (opp[b, 1:1 + c] & ~0xff) | ((opp[b, 1:1 + c] & 0xff) - t + flip)
+    cases["opposite friction sides"] = (opp, 0)
+    cases["true set, shifted by three steps"] = (true_ws.copy(), 3)
+    cases["true set, shifted backwards"] = (true_ws.copy(), -2)
+    bad = true_ws.copy()
+    bad[::2, 0] = W + 5
+    bad[1::2, 0] = -3
+    cases["counts out of range"] = (bad, 0)
+    for name, (ws, shift) in cases.items():
+        w, st = run(ws.copy(), shift)
+        assert (interface.status_code(st) == 0).all(), (name, st)
+        assert np.abs(w - w0).max() < 1e-5 * np.abs(w0).max(), (name, np.abs(w - w0).max())
+        assert np.array_equal(interface.status_nactive(st), interface.status_nactive(st0)), name
