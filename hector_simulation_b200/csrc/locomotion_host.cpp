@@ -28,6 +28,10 @@ Gait::Gait(int nMPC_segments, int offset0, int offset1, int duration0, int durat
   _offsets[1] = offset1;
   _durations[0] = duration0;
   _durations[1] = duration1;
+  for (int i = 0; i < 2; i++) {  // GaitGenerator.cpp:9-10
+    _offsetsPhase[i] = (double)_offsets[i] / (double)nMPC_segments;
+    _durationsPhase[i] = (double)_durations[i] / (double)nMPC_segments;
+  }
   _mpc_table = new int[nMPC_segments * 2];
   _stance = duration0;
   _swing = nMPC_segments - duration0;
@@ -53,6 +57,29 @@ void Gait::setIterations(int iterationsPerMPC, int currentIteration)
 {
   _iteration = (currentIteration / iterationsPerMPC) % _nIterations;
   _phase = (double)(currentIteration % (iterationsPerMPC * _nIterations)) / (double)(iterationsPerMPC * _nIterations);
+}
+
+// GaitGenerator.cpp:28-47: progress through the stance phase from the continuous _phase; exactly 0 outside it
+void Gait::getContactSubPhase(double out[2]) const
+{
+  for (int i = 0; i < 2; i++) {
+    double progress = _phase - _offsetsPhase[i];
+    if (progress < 0) progress += 1.;
+    out[i] = (progress > _durationsPhase[i]) ? 0. : progress / _durationsPhase[i];
+  }
+}
+
+// GaitGenerator.cpp:53-79: the same for the swing phase, which starts where stance ends (wrapped into [0, 1])
+void Gait::getSwingSubPhase(double out[2]) const
+{
+  for (int i = 0; i < 2; i++) {
+    double swing_offset = _offsetsPhase[i] + _durationsPhase[i];
+    if (swing_offset > 1) swing_offset -= 1.;
+    const double swing_duration = 1. - _durationsPhase[i];
+    double progress = _phase - swing_offset;
+    if (progress < 0) progress += 1.;
+    out[i] = (progress > swing_duration) ? 0. : progress / swing_duration;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -172,13 +199,19 @@ void ConvexMPCLocomotion::run(ControlFSMData& data)
     firstRun = false;
   }
   gait->setIterations(iterationsBetweenMPC, iterationCounter);  // :171
+  double contactStates[2], swingStates[2];                       // :184-185, this tick's continuous gait phase
+  gait->getContactSubPhase(contactStates);
+  gait->getSwingSubPhase(swingStates);
   int* mpcTable = gait->mpc_gait();                              // :187
   updateMPCIfNeeded(mpcTable, data, omniMode);                   // :190
   iterationCounter++;
-  // stance feet receive the MPC wrench as feed-forward force (:241-266); swing legs are the swing controller's
-  for (int foot = 0; foot < 2; foot++)
-    if (lastTable[foot] == 1)
+  // :199-266 — a foot whose swing sub-phase is positive belongs to the swing controller; otherwise, if its contact
+  // sub-phase is positive, it receives the MPC wrench as feed-forward force; on a tick where both are 0 nothing is written
+  for (int foot = 0; foot < 2; foot++) {
+    if (swingStates[foot] > 0) continue;
+    if (contactStates[foot] > 0)
       for (int i = 0; i < 6; i++) data._legCommands[foot].feedforwardForce[i] = f_ff[foot][i];
+  }
 }
 
 void ConvexMPCLocomotion::updateMPCIfNeeded(int* mpcTable, ControlFSMData& data, bool omniMode)
@@ -247,6 +280,15 @@ void hloco_run(void* h, StateEstimate* se, LegControllerData* legs, DesiredState
   d._desiredStateCommand = cmd;
   d._legCommands = out;
   static_cast<ConvexMPCLocomotion*>(h)->run(d);
+}
+// the gait's sub-phases at control iteration `iteration` (what run() gates the feed-forward force with): a test hook
+void hloco_gait_subphases(int nseg, const int* offsets, const int* durations, int iterationsPerMPC, int iteration,
+                          double contact[2], double swing[2])
+{
+  Gait g(nseg, offsets[0], offsets[1], durations[0], durations[1]);
+  g.setIterations(iterationsPerMPC, iteration);
+  g.getContactSubPhase(contact);
+  g.getSwingSubPhase(swing);
 }
 const double* hloco_trajectory(void* h) { return static_cast<ConvexMPCLocomotion*>(h)->trajectory(); }
 const double* hloco_foot_force(void* h, int leg) { return static_cast<ConvexMPCLocomotion*>(h)->footForce(leg); }

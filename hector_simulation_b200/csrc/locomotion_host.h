@@ -47,18 +47,21 @@ struct ControlFSMData {       // include/common/ControlFSMData.h, reduced
   DesiredStateData* _desiredStateCommand;
 };
 
-// Gait::mpc_gait / setIterations — GaitGenerator.cpp:85-113
+// Gait::mpc_gait / setIterations / getContactSubPhase / getSwingSubPhase — GaitGenerator.cpp:6-17, 28-82, 85-113
 class Gait {
  public:
   Gait(int nMPC_segments, int offset0, int offset1, int duration0, int duration1);
   ~Gait();
   int* mpc_gait();
   void setIterations(int iterationsPerMPC, int currentIteration);
+  void getContactSubPhase(double out[2]) const;  // 0 outside stance, else progress through it (continuous _phase)
+  void getSwingSubPhase(double out[2]) const;    // 0 outside swing, else progress through it
   int _stance, _swing;
 
  private:
   int* _mpc_table;
   int _offsets[2], _durations[2];
+  double _offsetsPhase[2], _durationsPhase[2];
   int _iteration, _nIterations;
   double _phase;
 };

@@ -140,3 +140,48 @@ def test_locomotion_class_runs_the_gpu_boundary():
         L.hloco_run(h, ctypes.byref(se), legs, ctypes.byref(cmd), out)
     assert L.hloco_iteration(h) == 6
     L.hloco_destroy(h)
+
+
+@pytest.mark.gpu
+def test_locomotion_class_follows_the_reference_controller_over_a_gait_cycle(oracle):
+    """ConvexMPCLocomotion::run() of the host mirror, ticked through the pose sequence the reference's compiled controller was
+    recorded on (tests/golden/ref_tick_walk.npz: 520 control ticks = 104 MPC updates, 1.3 gait cycles, touch-downs and
+    lift-offs of both feet): the feed-forward force left in the leg commands agrees on EVERY tick — the MPC ticks (GPU solve vs
+    qpOASES, 5e-5) and the ticks between them (the stance gate of ConvexMPCLocomotion.cpp:199-266, from this tick's gait
+    sub-phases) — and so does the desired trajectory handed to the solver."""
+    import test_reference_tick as T
+
+    L = _host()
+    ticks = T.committed_ticks(oracle, "walk")
+    c = T.CASES["walk"]
+    h = ctypes.c_void_p(L.hloco_create(ctypes.c_double(T.DT), T.ITER_MPC))
+    L.hloco_set_gait(h, c["gait"])
+    out = (LegCmd * 2)()
+    cmd = Desired()
+    # DesiredStateCommand::setStateCommands (src/common/DesiredCommand.cpp:15-42): roll, pitch, body velocity, yaw rate
+    cmd.stateDes[3], cmd.stateDes[4] = c["command"]["roll"], c["command"]["pitch"]
+    cmd.stateDes[6], cmd.stateDes[7] = c["command"]["v_des"]
+    cmd.stateDes[11] = c["command"]["yaw_rate"]
+    worst, n_gate_only = 0.0, 0
+    for k, o in enumerate(ticks):
+        pos, rpy, vel, omega, raw = T._pose(k, c["pose"])
+        quat = scenarios.rpy_to_quat(rpy)
+        se = StateEstimate()
+        se.position[:] = pos; se.orientation[:] = quat; se.rBody[:] = o["rBody"]; se.rpy[:] = o["rpy"]
+        se.omegaWorld[:] = omega; se.vWorld[:] = vel
+        legs = (LegData * 2)()
+        for i in range(2):
+            legs[i].q[:] = o["leg_q"][5 * i: 5 * i + 5]
+            legs[i].p[:] = o["leg_p"][3 * i: 3 * i + 3]
+        L.hloco_run(h, ctypes.byref(se), legs, ctypes.byref(cmd), out)
+        assert L.hloco_iteration(h) == o["iteration_counter"]
+        ff = np.concatenate([np.array(out[leg].feedforwardForce[:]) for leg in range(2)])
+        ref = o["ff_cmd"]
+        assert np.array_equal(ff == 0.0, ref == 0.0), k          # written / not yet written, foot by foot
+        scale = max(np.linalg.norm(ref), 1e-9)
+        worst = max(worst, np.linalg.norm(ff - ref) / scale)
+        assert np.linalg.norm(ff - ref) / scale < 5e-5, (k, ff, ref)
+        n_gate_only += int(k % 5 != 0)
+    L.hloco_destroy(h)
+    assert n_gate_only == 416
+    print("host mirror vs reference controller over 520 ticks: worst relative feed-forward difference %.2e" % worst)

@@ -279,3 +279,39 @@ def _host_record(H, st, rBody):
     H.hmpc_prepare_record(ctypes.byref(se), legs, ctypes.byref(cmd), wpd, table.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                           ctypes.c_int(N), ctypes.c_double(DT_MPC), rec.ctypes.data_as(ctypes.c_void_p), None)
     return rec[0]
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_feedforward_gate_follows_the_gait_sub_phases(oracle, case):
+    """ConvexMPCLocomotion.cpp:199-266: a foot receives feedforwardForce = f_ff on the ticks where its swing sub-phase is 0
+    and its contact sub-phase positive — from the continuous Gait::_phase of THIS tick, not from the contact table of the last
+    MPC update.  The host mirror's Gait (getContactSubPhase / getSwingSubPhase restated) reproduces the command the
+    reference's controller left in commands[].feedforwardForce on every recorded tick; gating on the MPC table instead would
+    differ on the ticks around touch-down / lift-off."""
+    O = oracle
+    C = CASES[case]
+    H = _host()
+    off = (ctypes.c_int * 2)(*C["offsets"])
+    dur = (ctypes.c_int * 2)(*C["durations"])
+    prev = np.zeros(12)
+    table_gate_differs = 0
+    last_table = None
+    for k, o in enumerate(committed_ticks(O, case)):
+        cs, ss = (ctypes.c_double * 2)(), (ctypes.c_double * 2)()
+        H.hloco_gait_subphases(N, off, dur, ITER_MPC, k, cs, ss)
+        # the swing controller reads the same sub-phase (standing gait, tick 0: 0/0 = NaN in both, "not swinging")
+        assert np.array_equal(np.array(ss[:]), o["swing_states"], equal_nan=True), k
+        exp, exp_table = prev.copy(), prev.copy()
+        if k % 5 == 0:
+            last_table = o["mpc_table"].copy()
+        for leg in range(2):
+            sl = slice(6 * leg, 6 * leg + 6)
+            if not ss[leg] > 0 and cs[leg] > 0:
+                exp[sl] = o["f_ff"][sl]
+            if last_table[leg] == 1:
+                exp_table[sl] = o["f_ff"][sl]
+        assert np.array_equal(exp, o["ff_cmd"]), k
+        table_gate_differs += int(not np.array_equal(exp_table, o["ff_cmd"]))
+        prev = o["ff_cmd"].copy()
+    if case == "walk":
+        assert table_gate_differs > 0      # the distinction is real on this sequence
