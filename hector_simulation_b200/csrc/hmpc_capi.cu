@@ -157,6 +157,7 @@ struct hmpc_ctx {
   int* d_ws = nullptr;             // [max_batch][WS_STATE_INTS] working sets of the previous tick (closed-loop warm start)
   int warm_start = 1;              // hmpc_rollout_device proposes them to the next tick (HMPC_WARM_START=0: cold start every tick)
   int lockstep = 1;                // waves of a multi-wave launch start together (HMPC_LOCKSTEP=0: free-running, for A/B runs)
+  int block_min = 2;     // later rounds need at least this many entering rows (HMPC_BLOCK_MIN, A/B knob)
   int block_rounds = 4;  // block start of the active-set stage (HMPC_BLOCK_ROUNDS=0: plain dual iteration, for A/B runs)
   // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
   // reference records from them and write results to them in place (no packing, no staging copies, no widening)
@@ -319,6 +320,7 @@ hmpc::KernelArgs base_args(const hmpc_ctx* c, const void* d_records, int B, floa
   ka.tol_kkt = 1e-9;
   ka.tol_dep = 1e-11;
   ka.block_rounds = c->block_rounds;
+  ka.block_min = c->block_min;
   ka.wrench = d_wrench;
   ka.status = d_status;
   return ka;
@@ -580,6 +582,7 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
   if (!bad) {
     const char* br = getenv("HMPC_BLOCK_ROUNDS");
     if (br) c->block_rounds = atoi(br);
+    if (const char* bm = getenv("HMPC_BLOCK_MIN")) c->block_min = atoi(bm);
     const char* ls = getenv("HMPC_LOCKSTEP");
     if (ls) c->lockstep = atoi(ls);
     const char* wm = getenv("HMPC_WARM_START");

@@ -156,6 +156,7 @@ struct KernelArgs {
   double tol_dep;                // an entering row is dependent on the working set when its curvature falls below tol_dep * a'H^-1a (1e-11)
   int tcap;                      // working-set slots with a cached H^-1 a_j column (runtime-layout launches; fixed: class_tcap)
   int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
+  int block_min;                 // rounds after the first run only with at least this many entering rows
   int warm_start;                // 1: propose the working set in `ws_state` (previous tick) to the block start
   int ws_shift;                  // MPC steps the horizon moved since that tick (the closed loop: 1)
   int* ws_state;                 // [batch][WS_STATE_INTS] persistent working sets, read (warm_start) and written back; or nullptr
@@ -1707,6 +1708,8 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         // slots below slot_cap remain (the first candidates in row order take them, the others wait for the next round or
         // for the dual iteration).  No violated row: the iteration below confirms and stops.
         if (nadd == 0 || (am0 >> slot_cap) != 0u) break;
+        // after the first round, few entering rows are cheaper one by one in the dual iteration than as another solve
+        if (round > 0 && nadd < ka.block_min) break;
         const int room = slot_cap - __popc(am0);
         if (nadd > room) nadd = room;
         if (nadd <= 0) break;

@@ -131,12 +131,19 @@ def test_locomotion_class_runs_the_gpu_boundary():
     L.hloco_run(h, ctypes.byref(se), legs, ctypes.byref(cmd), out)
     assert L.hloco_iteration(h) == 1
     u0 = g["q_soln"][0, :12]
+    # tick 0 solves, but the command is not written yet: at gait phase exactly 0 both sub-phases are 0 (the standing
+    # gait's swing sub-phase is 0/0 = NaN, "not swinging"; its contact sub-phase 0/1 = 0, "not in contact") — the
+    # reference's gate (ConvexMPCLocomotion.cpp:199-266, recorded in tests/golden/ref_tick_cases.npz "stand") skips it
     for leg in range(2):
-        f = np.array(out[leg].feedforwardForce[:])
+        assert not np.any(np.array(out[leg].feedforwardForce[:]))
+        f = np.array(L.hloco_foot_force(h, leg)[:6])
         ref = -np.concatenate([u0[3 * leg: 3 * leg + 3], u0[6 + 3 * leg: 9 + 3 * leg]])
         assert np.linalg.norm(f - ref) / np.linalg.norm(ref) < 5e-5
+    L.hloco_run(h, ctypes.byref(se), legs, ctypes.byref(cmd), out)       # tick 1: no solve, the stance feet get f_ff
+    for leg in range(2):
+        assert np.array_equal(np.array(out[leg].feedforwardForce[:]), np.array(L.hloco_foot_force(h, leg)[:6]))
     # ticks 1..4 do not re-solve (MPC gate iterationCounter % 5, quirk Q11); tick 5 does
-    for _ in range(5):
+    for _ in range(4):
         L.hloco_run(h, ctypes.byref(se), legs, ctypes.byref(cmd), out)
     assert L.hloco_iteration(h) == 6
     L.hloco_destroy(h)
