@@ -1117,6 +1117,8 @@ update_data_t g_update_early;  // update_solver_settings may be called before se
 update_data_t& ref_update() { return g_blk ? g_blk->update : g_update_early; }
 int g_soln_len = 0;
 int g_has_solved = 0;
+int g_ref_rc = HMPC_OK;       // result of the last update_problem_data (hmpc_reference_last_rc)
+bool g_ref_failing = false;   // inside an episode of failing ticks (the message is printed once per episode)
 
 [[noreturn]] void die(const char* where)
 {
@@ -1173,8 +1175,19 @@ HMPC_EXTERNC void update_problem_data(double* p, double* v, double* q, double* w
   for (int i = 0; i < 12 * N; i++) ref_update().traj[i] = (float)state_trajectory[i];
   for (int i = 0; i < 2 * N; i++) ref_update().gait[i] = (unsigned char)gait[i];
   int rc = hmpc_solve_batch(g_ctx, &g_blk->update, 1, g_blk->soln, &g_blk->status);
+  g_ref_rc = rc;
   if (rc == HMPC_ERR_NOT_CONVERGED) printf("failed to solve!\n");  // SolverMPC.cpp:714-715 (status word: hmpc_reference_last_status())
-  else if (rc != HMPC_OK) die("update_problem_data");
+  else if (rc != HMPC_OK) {
+    // a run-time failure: the controller keeps running on the last wrench and can ask why (hmpc_reference_last_rc)
+    const char* ab = getenv("HMPC_REFERENCE_ABORT");
+    if (ab && atoi(ab) != 0) die("update_problem_data");
+    if (!g_ref_failing)
+      fprintf(stderr, "[hector_mpc_b200] update_problem_data: %s — keeping the previous solution (hmpc_reference_last_rc() = %d)\n",
+              hmpc_last_error(), rc);
+    g_ref_failing = true;
+    return;
+  }
+  g_ref_failing = false;
   g_has_solved = 1;
 }
 
@@ -1198,3 +1211,5 @@ HMPC_EXTERNC void update_solver_settings(int max_iter, double rho, double sigma,
 
 // status word of the last update_problem_data (additive; not part of the reference boundary)
 HMPC_EXTERNC int hmpc_reference_last_status(void) { return g_blk ? g_blk->status : 0; }
+// result code of the last update_problem_data (additive): see include/hector_mpc_b200.h
+HMPC_EXTERNC int hmpc_reference_last_rc(void) { return g_ref_rc; }

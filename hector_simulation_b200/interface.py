@@ -28,6 +28,7 @@ EXPORTS = [
     "hmpc_prepare_device", "hmpc_solve_batch_states", "hmpc_rollout_device", "hmpc_reset_warm_start",
     "hmpc_shard_unique_id", "hmpc_shard_init", "hmpc_solve_batch_sharded", "hmpc_shard_wait",
     "hmpc_pin_host_buffer", "hmpc_unpin_host_buffer", "hmpc_swing_device",
+    "hmpc_reference_last_status", "hmpc_reference_last_rc",
 ]
 
 SETUP_DTYPE = np.dtype([("dt", "<f4"), ("mu", "<f4"), ("f_max", "<f4"), ("horizon", "<i4")], align=True)
@@ -75,6 +76,7 @@ def lib() -> ctypes.CDLL:
         L.hmpc_assemble_device.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6
         L.hmpc_assemble_device.restype = ctypes.c_int
         L.hmpc_reference_last_status.restype = ctypes.c_int
+        L.hmpc_reference_last_rc.restype = ctypes.c_int
         L.hmpc_solve_batch_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
         L.hmpc_solve_batch_ex.restype = ctypes.c_int
         L.hmpc_solve_device_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
@@ -147,6 +149,11 @@ def update_solver_settings(max_iter, rho, sigma, solver_alpha, terminate, use_jc
 
 def reference_last_status() -> int:
     return lib().hmpc_reference_last_status()
+
+
+def reference_last_rc() -> int:
+    """Result of the last update_problem_data: 0, HMPC_ERR_NOT_CONVERGED, or the error the tick failed with."""
+    return lib().hmpc_reference_last_rc()
 
 
 # ---------------------------------------------------------------------------------------------------

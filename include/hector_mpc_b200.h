@@ -86,6 +86,20 @@ HMPC_EXTERNC void update_problem_data(double* p, double* v, double* q, double* w
                                       double* joint_angles, double yaw, double* weights,
                                       double* state_trajectory, double* Alpha_K, int* gait);
 
+/* The boundary above has no error channel (its functions return void / a double).  Two additive calls give a 1 kHz
+ * controller one without changing the reference's call sites:
+ *   hmpc_reference_last_status  the status word of the last update_problem_data (HMPC_STATUS_* macros below): code,
+ *                               working-set changes, active rows — what "failed to solve!" (SolverMPC.cpp:714-715) hides.
+ *   hmpc_reference_last_rc      HMPC_OK, HMPC_ERR_NOT_CONVERGED, or the error of the last tick.  A tick that fails at run
+ *                               time (a CUDA error after a successful setup_problem) does NOT end the process: the error is
+ *                               printed once per episode, get_solution keeps returning the last tick's wrench, and this call
+ *                               (with hmpc_last_error()) tells the controller, which can fall back to its stand-still
+ *                               behaviour.  HMPC_REFERENCE_ABORT=1 in the environment restores "abort on any failure".
+ * Misuse and start-up failures stay fatal with a message: horizon > 19 (the reference throws), update_problem_data before
+ * setup_problem, no usable GPU at setup_problem. */
+HMPC_EXTERNC int hmpc_reference_last_status(void);
+HMPC_EXTERNC int hmpc_reference_last_rc(void);
+
 /* ------------------------------------------------------------------------------------------
  * Part 2 — batched interface (additive; SURVEY.md §8b "batched extension")
  * ---------------------------------------------------------------------------------------- */

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import load_golden, rel_err
+from conftest import ROOT, load_golden, rel_err
 from hector_simulation_b200 import interface, scenarios
 
 pytestmark = pytest.mark.gpu
@@ -466,3 +466,43 @@ def test_horizon_sweep_batch_4096(torch_cuda, oracle, N):
     print("horizon %d, %d robots: first step worst %.2e, whole horizon worst %.2e vs qpOASES (%d cases above 5e-5 refereed in fp64)"
           % (N, len(idx), e0[good].max(), ef[good].max(), refereed))
     assert ef[good].max() < 3e-4
+
+
+@pytest.mark.gpu
+def test_reference_boundary_survives_a_failing_tick():
+    """The reference's boundary has no error channel; a run-time CUDA failure under update_problem_data must not end a 1 kHz
+    controller's process.  Fault injection: the device's primary context is reset between two ticks (every handle the
+    library holds becomes invalid).  The failing tick prints one line, get_solution keeps the previous wrench,
+    hmpc_reference_last_rc() reports the error; HMPC_REFERENCE_ABORT=1 restores abort-on-failure."""
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes, sys
+import numpy as np
+sys.path.insert(0, %r)
+from hector_simulation_b200 import interface, scenarios
+b = scenarios.stand_inputs(10)
+args = (b["p"], b["v"], b["q"], b["w"], b["r"], b["joint_angles"], b["yaw"], b["weights"], b["state_trajectory"], b["Alpha_K"], b["gait"])
+interface.setup_problem(scenarios.DT_MPC, 10, scenarios.MU_PASSED, scenarios.F_MAX)
+interface.update_problem_data(*args)
+assert interface.reference_last_rc() == 0
+s0 = [interface.get_solution(i) for i in range(12)]
+assert abs(s0[2] - 47.84) < 0.05
+rt = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
+assert rt.cudaDeviceReset() == 0
+interface.update_problem_data(*args)          # fails inside the library
+rc = interface.reference_last_rc()
+s1 = [interface.get_solution(i) for i in range(12)]
+print("RC", rc, "SAME", s1 == s0, "ERR", interface.lib().hmpc_last_error().decode())
+''' % ROOT
+    env = dict(os.environ)
+    env.pop("HMPC_REFERENCE_ABORT", None)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    line = [l for l in r.stdout.splitlines() if l.startswith("RC ")][0].split()
+    assert int(line[1]) != 0 and line[3] == "True", r.stdout
+    assert "keeping the previous solution" in r.stderr
+    env["HMPC_REFERENCE_ABORT"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode != 0 and "RC " not in r.stdout      # aborted inside the failing tick
