@@ -929,7 +929,16 @@ __global__ void hmpc_swing_kernel(const unsigned char* states, const unsigned ch
 // NF > 0 fixes the horizon at compile time (layout offsets and loop bounds fold), NF == 0 reads it from
 // the arguments; CLS = size class (capacity N or 2N blocks of 6 variables).
 // ------------------------------------------------------------------------------------------------
+// Profiling hooks (hmpc_debug_set_clock_buffer): HMPC_STAMP(i) = clock of thread 0 at point i (tests/tools/gpu_check.py).
+// Built with -DHMPC_WARP_STAMPS=<k> instead, lane 0 of EVERY warp stamps the phases of block step k of stage 4
+// (tests/tools/warp_stamps.py: which warp reaches the step's barrier last, and what it did before).
+#ifdef HMPC_WARP_STAMPS
+#define HMPC_STAMP(i) do { } while (0)
+#define HMPC_WSTAMP(e) do { if (ka.dbg_clk && lane == 0 && wid < 4 && k == HMPC_WARP_STAMPS) ka.dbg_clk[(size_t)inst * 32 + wid * 8 + (e)] = clock64(); } while (0)
+#else
 #define HMPC_STAMP(i) do { if (ka.dbg_clk && tid == 0) ka.dbg_clk[(size_t)inst * 32 + (i)] = clock64(); } while (0)
+#define HMPC_WSTAMP(e) do { } while (0)
+#endif
 constexpr int WS_STATE_INTS = 40;  // persistent working set of one robot: [0] = count, then (step*2+leg) << 8 | normal index
 
 template <int NT, int MINB, int NF, int CLS>
@@ -1451,6 +1460,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
         const int kn = k + 1;  // the panel prepared for the next step (look-ahead)
         const bool genA = hasA && rA != k, genB = hasB && rB != k;
         double wA0 = 0.0, wA1 = 0.0, wB0 = 0.0, wB1 = 0.0;
+        HMPC_WSTAMP(0);
         {
           // W_R = P_R D^-1 for the warp's rows, negated: stashed in fragment order (it is also the new column-k tile
           // of the row) and reloaded as the A operand of the rank-8 updates A_RJ -= W_R P_J'
@@ -1472,6 +1482,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           if (genB) { wB0 = WsB[lane]; wB1 = WsB[32 + lane]; }
         }
         if (k == 1) HMPC_STAMP(20);
+        HMPC_WSTAMP(1);
         // look-ahead: the next diagonal tile first — its inversion is the longest chain of the step.  It is an ordinary
         // tile in step k: rank-8 update (on a copy; the slot itself is updated below with the others), then its
         // in-register inverse goes to the next panel.
@@ -1490,6 +1501,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           *reinterpret_cast<double2*>(Pn + kn * 64 + fp) = make_double2(d0, d1);
         }
         if (k == 1) HMPC_STAMP(21);
+        HMPC_WSTAMP(2);
         {
           // rank-8 updates of both rows (they share the P_J fragments); the column-k tile becomes W_R; the column-kn
           // tile goes to the next panel
@@ -1528,6 +1540,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           }
         }
         if (k == 1) HMPC_STAMP(22);
+        HMPC_WSTAMP(3);
         // pivot row k (one warp of the CTA): A_kJ <- D^-1 P_J' for J < k, A_kk <- -D^-1
         if ((hasB && rB == k) || (hasA && rA == k)) {
           const bool inA = hasA && rA == k;
@@ -1560,7 +1573,9 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
           }
         }
         if (k == 1) HMPC_STAMP(23);
+        HMPC_WSTAMP(4);
         __syncthreads();
+        HMPC_WSTAMP(5);
         if (k == 1) HMPC_STAMP(24);
         if (k == 0) HMPC_STAMP(19);
       }
