@@ -732,6 +732,11 @@ static int check_device_records(const hmpc_ctx* c, const void* d_records, int B,
 // profiling hook: device buffer [batch][32] of clock64() stage timestamps, or NULL to switch off
 HMPC_EXTERNC void hmpc_debug_set_clock_buffer(long long* d_buf) { g_dbg_clk = d_buf; }
 
+// fault-injection hook (tests): the next n host-buffer solves return HMPC_ERR_CUDA without touching the device — what a
+// run-time CUDA failure looks like to the callers (the reference boundary's status path, tests/test_gpu_parity.py)
+namespace { int g_fail_next_solves = 0; }
+HMPC_EXTERNC void hmpc_debug_fail_next_solves(int n) { g_fail_next_solves = n; }
+
 HMPC_EXTERNC int hmpc_launches_per_solve(const hmpc_ctx* c) { return c ? c->ncls : 0; }
 
 // launch configuration of class `cls`: out[0..5] = threads, dynamic smem bytes, working-set capacity,
@@ -815,6 +820,11 @@ HMPC_EXTERNC int hmpc_prepare_device(hmpc_ctx* c, const hmpc_state_t* d_states, 
 {
   if (!c || !d_states || !d_records || B < 0) { g_err = "hmpc_prepare_device: bad argument"; return HMPC_ERR_ARG; }
   if (B == 0) return HMPC_OK;
+  if (g_fail_next_solves > 0) {
+    g_fail_next_solves--;
+    g_err = "injected failure (hmpc_debug_fail_next_solves)";
+    return HMPC_ERR_CUDA;
+  }
   CK(cudaSetDevice(c->device));
   hmpc::hmpc_prepare_kernel<<<(B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const unsigned char*>(d_states), B, c->horizon, dtMPC,
