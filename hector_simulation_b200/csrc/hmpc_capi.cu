@@ -733,7 +733,7 @@ static int check_device_records(const hmpc_ctx* c, const void* d_records, int B,
 HMPC_EXTERNC void hmpc_debug_set_clock_buffer(long long* d_buf) { g_dbg_clk = d_buf; }
 
 // fault-injection hook (tests): the next n host-buffer solves return HMPC_ERR_CUDA without touching the device — what a
-// run-time CUDA failure looks like to the callers (the reference boundary's status path, tests/test_gpu_parity.py)
+// run-time CUDA failure looks like to the callers (the reference boundary's status path, tests/test_zzz_reference_status_path.py)
 namespace { int g_fail_next_solves = 0; }
 HMPC_EXTERNC void hmpc_debug_fail_next_solves(int n) { g_fail_next_solves = n; }
 
