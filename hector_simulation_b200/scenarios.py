@@ -335,6 +335,41 @@ def _random_state(rng: np.random.Generator, horizon: int, table, moving: bool) -
                            yaw_rate=yaw_rate, pos_des_err=err)
 
 
+def _stress_state(rng: np.random.Generator, horizon: int, scale: float) -> dict:
+    """A state far outside the operating envelope (perturbations `scale` times the walking batches': tilts of tenths of
+    a radian, metres per second, set-point errors of decimetres) under a walking, standing or RANDOM contact table (flight
+    phases, single steps of support — update_problem_data accepts any table): many friction / moment / force bounds are
+    active at the optimum (60-110 rows against ~12 for a walking robot)."""
+    rpy = rng.normal(0.0, 0.06 * scale, 3)
+    pos = np.array([0.0, 0.0, BODY_HEIGHT]) + rng.normal(0.0, 0.03 * scale, 3)
+    vx = rng.uniform(-0.5, 0.5) * scale
+    vel = rng.normal(0.0, 0.2 * scale, 3) + np.array([vx, 0.0, 0.0])
+    omega = rng.normal(0.0, 0.3 * scale, 3)
+    joints = rng.normal(0.0, 0.08 * scale, 10)
+    yaw_rate = rng.uniform(-0.5, 0.5) * scale
+    err = rng.normal(0.0, 0.05 * scale, 2)
+    mode = int(rng.integers(0, 3))
+    if mode == 0:
+        table = walking_table(horizon, int(rng.integers(0, horizon)))
+    elif mode == 1:
+        table = standing_table(horizon)
+    else:
+        table = (rng.random((horizon, 2)) < 0.6).astype(np.int32).reshape(walking_table(horizon, 0).shape)
+        if table.sum() == 0:
+            table.flat[0] = 1
+    vy = 0.1 * scale * rng.normal()
+    return boundary_inputs(pos, rpy, vel, omega, joints, table, horizon, v_des_body=(vx, vy), yaw_rate=yaw_rate, pos_des_err=err)
+
+
+def make_stress_batch(batch: int, horizon: int, scale: float, seed: int) -> np.ndarray:
+    """records[batch] of _stress_state: the robustness workload of tests/golden/stress_referee.npz."""
+    rng = np.random.default_rng(seed)
+    recs = np.zeros(batch, dtype=UPDATE_DTYPE)
+    for i in range(batch):
+        to_record(_stress_state(rng, horizon, scale), horizon, recs[i])
+    return recs
+
+
 def config_seed(cfg: int) -> int:
     return 20260923 + cfg
 

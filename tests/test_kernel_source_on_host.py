@@ -643,3 +643,28 @@ def test_solve_kernel_source_warm_start_survives_any_proposal(emul):
         assert (interface.status_code(st) == 0).all(), (name, st)
         assert np.abs(w - w0).max() < 1e-5 * np.abs(w0).max(), (name, np.abs(w - w0).max())
         assert np.array_equal(interface.status_nactive(st), interface.status_nactive(st0)), name
+
+
+def test_solve_kernel_source_far_outside_the_operating_envelope(emul):
+    """Robustness workload (tests/golden/stress_referee.npz, scenarios.make_stress_batch): states 4-8 x the walking batches'
+    perturbations under walking / standing / random contact tables, up to ~100 active rows at massively degenerate optima;
+    all three size classes (the last one without column cache).  qpOASES itself is off the exact optimum by up to 4e-4 of
+    the first-step wrench on these problems, so the kernel is held to the tight-tolerance fp64 REFEREE stored in the
+    fixture: every instance converges, sits on the referee's optimum, and where the two CPU answers differ it is the kernel
+    that agrees with the exact one.  Record 9 of the x8 set is the regression case of the noise-level stop: its last
+    "violated" row is a dependent one, violated by round-off only — reported as infeasible before."""
+    from conftest import GOLDEN, rel_err
+
+    g = np.load(os.path.join(GOLDEN, "stress_referee.npz"))
+    n_far = 0
+    for name, N, idx in (("h10_x8", 10, [9, 21, 22]), ("h10_x4", 10, [12, 24]), ("h14_x4", 14, [14])):
+        recs = np.ascontiguousarray(g[name + "_records"]).view(scenarios.UPDATE_DTYPE).reshape(-1)[idx]
+        ref, q = g[name + "_referee"][idx], g[name + "_qpoases"][idx]
+        w, st, _, launched, _ = _solve(emul, recs, N, tau=False)
+        assert (interface.status_code(st) == 0).all(), (name, st)
+        assert interface.status_nactive(st).max() > 30
+        assert rel_err(w, ref, 12).max() < 5e-5 and rel_err(w, ref).max() < 1e-5, (name, rel_err(w, ref, 12), rel_err(w, ref))
+        far = rel_err(q, ref, 12) > 5e-5                 # qpOASES off the exact optimum
+        assert (rel_err(w, ref, 12)[far] < 0.5 * rel_err(q, ref, 12)[far]).all()
+        n_far += int(far.sum())
+    assert n_far >= 3

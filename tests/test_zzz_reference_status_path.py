@@ -1,11 +1,51 @@
-"""The reference boundary's status path (include/hector_mpc_b200.h, part 1): a tick that fails at run time keeps the previous
-wrench and reports through hmpc_reference_last_rc() instead of ending the process.  In its own file, after all others: it
-injects a failure into the library (in a subprocess) and exercises the abort policy."""
+"""Robustness of the boundary, after all other tests.
+
+1. The reference boundary's status path (include/hector_mpc_b200.h, part 1): a tick that fails at run time keeps the previous
+   wrench and reports through hmpc_reference_last_rc() instead of ending the process (failure injected into the library, in a
+   subprocess; the abort policy too).
+2. The stress workload tests/golden/stress_referee.npz on the GPU: states far outside the operating envelope, random contact
+   tables, ~100 active rows — against the tight-tolerance fp64 referee."""
 import os
 
+import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import GOLDEN, ROOT, rel_err
+from hector_simulation_b200 import interface, scenarios
+
+
+def test_stress_fixture_matches_its_generator():
+    """tests/golden/stress_referee.npz holds the records scenarios.make_stress_batch produces (tests/golden/make_stress_fixture.py)."""
+    g = np.load(os.path.join(GOLDEN, "stress_referee.npz"))
+    for name, (N, B, scale, seed) in {"h10_x4": (10, 32, 4.0, 2), "h10_x8": (10, 32, 8.0, 3), "h14_x4": (14, 16, 4.0, 5)}.items():
+        recs = scenarios.make_stress_batch(B, N, scale, seed)
+        assert np.array_equal(recs.view(np.uint8).reshape(B, -1), g[name + "_records"]), name
+        assert g[name + "_referee"].shape == (B, 12 * N) and g[name + "_qpoases_ok"].all()
+
+
+@pytest.mark.gpu
+def test_stress_workload_sits_on_the_referee_optimum():
+    """All 80 records of the stress fixture through hmpc_solve_batch (every size class, escalation on the device): each
+    converges (no false 'infeasible' — the QP always has the feasible point u = 0), agrees with the fp64 referee (first step
+    5e-5, whole horizon 2e-5), and where qpOASES is off the exact optimum (up to 4e-4 here) the GPU is on the referee's
+    side.  The same source on the host: test_solve_kernel_source_far_outside_the_operating_envelope."""
+    g = np.load(os.path.join(GOLDEN, "stress_referee.npz"))
+    n_far = 0
+    for name, N in (("h10_x4", 10), ("h10_x8", 10), ("h14_x4", 14)):
+        recs = np.ascontiguousarray(g[name + "_records"]).view(scenarios.UPDATE_DTYPE).reshape(-1)
+        ref, q = g[name + "_referee"], g[name + "_qpoases"]
+        mpc = interface.BatchedMPC(len(recs), N)
+        w, st = mpc.solve_batch(recs, strict=False)
+        mpc.close()
+        assert (interface.status_code(st) == 0).all(), (name, np.bincount(interface.status_code(st)))
+        e12, ef = rel_err(w, ref, 12), rel_err(w, ref)
+        assert e12.max() < 5e-5 and ef.max() < 2e-5, (name, e12.max(), ef.max())
+        far = rel_err(q, ref, 12) > 5e-5
+        assert (e12[far] < rel_err(q, ref, 12)[far]).all()    # closer to the exact optimum than qpOASES wherever that is off
+        n_far += int(far.sum())
+        print("%s: %d records, up to %d active rows; GPU vs referee first step %.1e / horizon %.1e; qpOASES vs referee first step %.1e"
+              % (name, len(recs), interface.status_nactive(st).max(), e12.max(), ef.max(), rel_err(q, ref, 12).max()))
+    assert n_far >= 5
 
 
 @pytest.mark.gpu
