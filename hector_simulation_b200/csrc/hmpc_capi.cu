@@ -157,6 +157,7 @@ struct hmpc_ctx {
   int* d_ws = nullptr;             // [max_batch][WS_STATE_INTS] working sets of the previous tick (closed-loop warm start)
   int warm_start = 1;              // hmpc_rollout_device proposes them to the next tick (HMPC_WARM_START=0: cold start every tick)
   int lockstep = 1;                // waves of a multi-wave launch start together (HMPC_LOCKSTEP=0: free-running, for A/B runs)
+  double kappa_max = 1.5e5;  // conditioning limit of the fp64 sweep inversion (HMPC_KAPPA_MAX; see the kernel's stage 5)
   int block_min = 2;     // later rounds need at least this many entering rows (HMPC_BLOCK_MIN, A/B knob)
   int block_rounds = 4;  // block start of the active-set stage (HMPC_BLOCK_ROUNDS=0: plain dual iteration, for A/B runs)
   // caller-owned host buffers registered with hmpc_pin_host_buffer: hmpc_solve_batch lets the kernels read the
@@ -321,6 +322,7 @@ hmpc::KernelArgs base_args(const hmpc_ctx* c, const void* d_records, int B, floa
   ka.tol_dep = 1e-11;
   ka.block_rounds = c->block_rounds;
   ka.block_min = c->block_min;
+  ka.kappa_max = c->kappa_max;
   ka.wrench = d_wrench;
   ka.status = d_status;
   return ka;
@@ -583,6 +585,7 @@ HMPC_EXTERNC hmpc_ctx* hmpc_create(int max_batch, int horizon, int device)
     const char* br = getenv("HMPC_BLOCK_ROUNDS");
     if (br) c->block_rounds = atoi(br);
     if (const char* bm = getenv("HMPC_BLOCK_MIN")) c->block_min = atoi(bm);
+    if (const char* km = getenv("HMPC_KAPPA_MAX")) c->kappa_max = atof(km);
     const char* ls = getenv("HMPC_LOCKSTEP");
     if (ls) c->lockstep = atoi(ls);
     const char* wm = getenv("HMPC_WARM_START");

@@ -157,6 +157,7 @@ struct KernelArgs {
   int tcap;                      // working-set slots with a cached H^-1 a_j column (runtime-layout launches; fixed: class_tcap)
   int block_rounds;              // rounds of the block start of the active-set stage (0: plain dual iteration from x0)
   int block_min;                 // rounds after the first run only with at least this many entering rows
+  double kappa_max;              // conditioning limit of the sweep inversion: max_i H_ii (H^-1)_ii beyond it -> ST_NOT_SPD
   int warm_start;                // 1: propose the working set in `ws_state` (previous tick) to the block start
   int ws_shift;                  // MPC steps the horizon moved since that tick (the closed loop: 1)
   int* ws_state;                 // [batch][WS_STATE_INTS] persistent working sets, read (warm_start) and written back; or nullptr
@@ -1419,6 +1420,8 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
       double c0[TS], c1[TS];
 #pragma unroll
       for (int t = 0; t < TS; t++) { c0[t] = 0.0; c1[t] = 0.0; }
+      // the diagonal of H survives the stage (in x0, not live yet): stage 5 checks H_ii (H^-1)_ii against it
+      for (int i = tid; i < n; i += NT) x0[i] = (double)Hf[toff(i >> 3, i >> 3) + (i & 7) * 9];
       {
         const int i = 8 * rB + g, j = 2 * t4;
         const float* src = Hf + toff(rB, 0) + g * 8 + 2 * t4;
@@ -1605,8 +1608,15 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     const bool isvar = vi < n, iscon = lane < 30 && ke < NB;
     const int erow = iscon ? 10 * ke + (lane - 10 * (lane / 10)) : 0x7fffffff;
     double xreg = 0.0;
+    // Conditioning check.  The sweep inversion (Gauss-Jordan without pivoting, in place) loses accuracy like the SQUARE of
+    // the scaled condition number: measured against an fp64 referee the optimum is off by ~1e-13 kappa^2, kappa = max_i
+    // H_ii (H^-1)_ii (2e2 ... 1e4 on every workload of BASELINE.json, 3e5 for a robot lying on its side, where the answer
+    // is 8e-3 off).  Beyond ka.kappa_max the 1e-4 contract cannot be promised: such an instance is reported as not solved
+    // (ST_NOT_SPD: "Hessian not positive definite enough") instead of returning a wrong wrench with a clean status.
+    bool illc = false;
     if (isvar) {
       xreg = -hinv_rowdot(Hd, vi, NT8, gq);
+      illc = x0[vi] * Hd[toff(vi >> 3, vi >> 3) + (vi & 7) * 9] > ka.kappa_max;
       x0[vi] = xreg;
     }
     {
@@ -1616,7 +1626,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
     }
     if (tid < 8) amask[tid] = 0u;
     if (tid == 0) { flags[7] = 0; flags[8] = 0; flags[9] = 0; flags[11] = 0; }
-    __syncthreads();
+    const int ill = __syncthreads_or((int)illc);
     double tol;
     {
       unsigned kx = redk[16];
@@ -1640,6 +1650,7 @@ __global__ void __launch_bounds__(NT, MINB) hmpc_solve_kernel(const KernelArgs k
 
     int q = 0, iters = 0;
     int code = flags[3];
+    if (ill && code == ST_OK) code = ST_NOT_SPD;
 
     // ---- block start ----------------------------------------------------------------------------------------------
     // Rounds of: take the most violated inactive row of EVERY block, solve on the enlarged working set (all multipliers

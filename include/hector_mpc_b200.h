@@ -115,7 +115,10 @@ typedef struct hmpc_ctx hmpc_ctx;
 /* per-instance status word written with every result (never silently stale — contrast
  * SolverMPC.cpp:714-715, which prints and carries on with stale data):
  *   bits  0..7  : termination code  (0 = optimal, 1 = iteration cap, 2 = working-set capacity,
- *                                    3 = infeasible/degenerate step, 4 = Hessian not SPD)
+ *                                    3 = infeasible/degenerate step, 4 = Hessian not positive definite ENOUGH: a
+ *                                    non-positive pivot, or max_i H_ii (H^-1)_ii above the conditioning limit of the
+ *                                    fp64 sweep inversion (1.5e5; 2e2 ... 1e4 on the workloads of BASELINE.json, 3e5
+ *                                    for a robot lying on its side) — the wrench of such an instance is not trusted)
  *   bits  8..19 : working-set changes performed (comparable to qpOASES nWSR)
  *   bits 20..27 : number of active constraints at the solution
  */

@@ -22,13 +22,18 @@ from oracle import oracle_py as O  # noqa: E402
 from oracle import qp_dual_active_set as G  # noqa: E402
 
 SETS = {"h10_x4": (10, 32, 4.0, 2), "h10_x8": (10, 32, 8.0, 3), "h14_x4": (14, 16, 4.0, 5)}   # horizon, batch, scale, seed
+# one record beyond the conditioning limit of the kernel's sweep inversion (a robot lying on its side: max_i H_ii (H^-1)_ii =
+# 2.9e5, cond(H) = 3e8): record 34 of make_stress_batch(40, 10, 8.0, 15).  qpOASES (Cholesky-based) still solves it.
+LYING = ("h10_lying", 10, 40, 8.0, 15, [34])
 
 
 def main():
     assert O.has_qpoases()
     out = {}
-    for name, (N, B, scale, seed) in SETS.items():
-        recs = scenarios.make_stress_batch(B, N, scale, seed)
+    todo = [(name, N, scenarios.make_stress_batch(B, N, scale, seed)) for name, (N, B, scale, seed) in SETS.items()]
+    todo.append((LYING[0], LYING[1], scenarios.make_stress_batch(LYING[2], LYING[1], LYING[3], LYING[4])[LYING[5]]))
+    for name, N, recs in todo:
+        B = len(recs)
         setup = O.make_setup(N)
         q, info = O.solve_batch(recs, setup)
         ref = np.zeros((B, 12 * N))

@@ -242,6 +242,7 @@ int emul_solve_ex(const unsigned char* records, const unsigned char* raw, int B,
     ka.max_iter = max_iter;
     ka.tol_kkt = getenv("HMPC_TOL_KKT") ? atof(getenv("HMPC_TOL_KKT")) : 1e-9;   // hmpc_capi.cu's constants; the
     ka.tol_dep = getenv("HMPC_TOL_DEP") ? atof(getenv("HMPC_TOL_DEP")) : 1e-11;  // tolerance-sweep test overrides them
+    ka.kappa_max = getenv("HMPC_KAPPA_MAX") ? atof(getenv("HMPC_KAPPA_MAX")) : 1.5e5;  // hmpc_capi.cu's default
     ka.block_min = getenv("HMPC_BLOCK_MIN") ? atoi(getenv("HMPC_BLOCK_MIN")) : 2;  // hmpc_capi.cu's default
     ka.block_rounds = getenv("HMPC_BLOCK_ROUNDS") ? atoi(getenv("HMPC_BLOCK_ROUNDS")) : 4;  // hmpc_capi.cu's default
     ka.wrench = wrench;

@@ -668,3 +668,25 @@ def test_solve_kernel_source_far_outside_the_operating_envelope(emul):
         assert (rel_err(w, ref, 12)[far] < 0.5 * rel_err(q, ref, 12)[far]).all()
         n_far += int(far.sum())
     assert n_far >= 3
+
+
+def test_solve_kernel_source_reports_a_hessian_beyond_its_conditioning_limit(emul):
+    """The in-place sweep inversion loses accuracy like the square of the scaled condition number.  A robot
+    lying on its side (fixture record h10_lying: max_i H_ii (H^-1)_ii = 2.9e5 against 2e2 ... 1e4 on BASELINE's workloads)
+    would come back 8e-3 off the exact optimum with a clean status; the conditioning check of stage 5 reports it as not
+    solved instead (status code 4, 'failed to solve!' at the reference boundary).  With the check lifted (HMPC_KAPPA_MAX)
+    the same record shows what it guards against."""
+    from conftest import GOLDEN, rel_err
+
+    g = np.load(os.path.join(GOLDEN, "stress_referee.npz"))
+    recs = np.ascontiguousarray(g["h10_lying_records"]).view(scenarios.UPDATE_DTYPE).reshape(-1)
+    ref = g["h10_lying_referee"]
+    assert rel_err(g["h10_lying_qpoases"], ref, 12).max() < 2e-5       # the reference's solver handles it
+    w, st, _, launched, _ = _solve(emul, recs, 10, tau=False)
+    assert interface.status_code(st).tolist() == [4]
+    os.environ["HMPC_KAPPA_MAX"] = "1e12"
+    try:
+        w, st, _, _, _ = _solve(emul, recs, 10, tau=False)
+    finally:
+        del os.environ["HMPC_KAPPA_MAX"]
+    assert interface.status_code(st).tolist() == [0] and 1e-3 < rel_err(w, ref, 12)[0] < 5e-2

@@ -21,6 +21,8 @@ def test_stress_fixture_matches_its_generator():
         recs = scenarios.make_stress_batch(B, N, scale, seed)
         assert np.array_equal(recs.view(np.uint8).reshape(B, -1), g[name + "_records"]), name
         assert g[name + "_referee"].shape == (B, 12 * N) and g[name + "_qpoases_ok"].all()
+    lying = scenarios.make_stress_batch(40, 10, 8.0, 15)[[34]]
+    assert np.array_equal(lying.view(np.uint8).reshape(1, -1), g["h10_lying_records"])
 
 
 @pytest.mark.gpu
@@ -89,3 +91,16 @@ print("NEXT", interface.reference_last_rc(), [interface.get_solution(i) for i in
     env["HMPC_REFERENCE_ABORT"] = "1"
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode != 0 and "RC " not in r.stdout      # aborted inside the failing tick
+
+
+@pytest.mark.gpu
+def test_hessian_beyond_the_conditioning_limit_is_reported():
+    """Fixture record h10_lying (a robot lying on its side, max_i H_ii (H^-1)_ii = 2.9e5): status code 4 instead of a wrench
+    8e-3 off the exact optimum with a clean status; the reference boundary prints 'failed to solve!' for it.  The same
+    source on the host: test_solve_kernel_source_reports_a_hessian_beyond_its_conditioning_limit."""
+    g = np.load(os.path.join(GOLDEN, "stress_referee.npz"))
+    recs = np.ascontiguousarray(g["h10_lying_records"]).view(scenarios.UPDATE_DTYPE).reshape(-1)
+    mpc = interface.BatchedMPC(4, 10)
+    w, st = mpc.solve_batch(recs, strict=False)
+    mpc.close()
+    assert interface.status_code(st).tolist() == [4]
