@@ -412,6 +412,15 @@ def test_solve_kernel_source_has_no_data_races(emul, tmp_path):
     np.ascontiguousarray(interface.pack_records(big, 10)).tofile(f)
     r = subprocess.run([exe, str(f), "10"], capture_output=True, text=True, env=env, timeout=900)
     assert "ThreadSanitizer" not in r.stderr and r.returncode == 0, r.stderr[:3000]
+    # the stress workload: the no-cache class with ~80 rows, the noise-level stop (record 9) and the conditioning check
+    gs = np.load(os.path.join(ROOT, "tests", "golden", "stress_referee.npz"))
+    for key, idx in (("h10_x8_records", [9, 21]), ("h10_lying_records", [0])):
+        recs = np.ascontiguousarray(gs[key]).view(scenarios.UPDATE_DTYPE).reshape(-1)[idx]
+        f = tmp_path / (key + ".bin")
+        np.ascontiguousarray(interface.pack_records(recs, 10)).tofile(f)
+        r = subprocess.run([exe, str(f), "10"], capture_output=True, text=True, env=env, timeout=1800)
+        assert "ThreadSanitizer" not in r.stderr, (key, r.stderr[:3000])
+        assert r.returncode == (0 if key.startswith("h10_x8") else 1), (key, r.returncode, r.stdout)   # lying: reported, not solved
 
 
 def test_solve_kernel_source_edge_cases(emul, oracle):
