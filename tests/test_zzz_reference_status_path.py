@@ -28,8 +28,8 @@ def test_stress_fixture_matches_its_generator():
 @pytest.mark.gpu
 def test_stress_workload_sits_on_the_referee_optimum():
     """All 80 records of the stress fixture through hmpc_solve_batch (every size class, escalation on the device): each
-    converges (no false 'infeasible' — the QP always has the feasible point u = 0), agrees with the fp64 referee (first step
-    5e-5, whole horizon 2e-5), and where qpOASES is off the exact optimum (up to 4e-4 here) the GPU is on the referee's
+    converges (no false 'infeasible' — the QP always has the feasible point u = 0), agrees with the fp64 referee within the contract (first
+    step 1e-4, whole horizon 5e-5), and where qpOASES itself is outside it (up to 4e-4 here) the GPU is on the referee's
     side.  The same source on the host: test_solve_kernel_source_far_outside_the_operating_envelope."""
     g = np.load(os.path.join(GOLDEN, "stress_referee.npz"))
     n_far = 0
@@ -41,13 +41,15 @@ def test_stress_workload_sits_on_the_referee_optimum():
         mpc.close()
         assert (interface.status_code(st) == 0).all(), (name, np.bincount(interface.status_code(st)))
         e12, ef = rel_err(w, ref, 12), rel_err(w, ref)
-        assert e12.max() < 5e-5 and ef.max() < 2e-5, (name, e12.max(), ef.max())
-        far = rel_err(q, ref, 12) > 5e-5
-        assert (e12[far] < rel_err(q, ref, 12)[far]).all()    # closer to the exact optimum than qpOASES wherever that is off
+        # (the kernel source on the host lands at 2.3e-5 / 5.2e-6 on these records; the bounds leave room for the GPU's
+        # reciprocal seeds steering a degenerate active set differently)
+        assert e12.max() < 1e-4 and ef.max() < 5e-5, (name, e12.max(), ef.max())
+        far = rel_err(q, ref, 12) > 1e-4                       # qpOASES itself outside the 1e-4 contract
+        assert (e12[far] < 0.5 * rel_err(q, ref, 12)[far]).all()   # ... and the GPU on the exact optimum's side
         n_far += int(far.sum())
         print("%s: %d records, up to %d active rows; GPU vs referee first step %.1e / horizon %.1e; qpOASES vs referee first step %.1e"
               % (name, len(recs), interface.status_nactive(st).max(), e12.max(), ef.max(), rel_err(q, ref, 12).max()))
-    assert n_far >= 5
+    assert n_far >= 3
 
 
 @pytest.mark.gpu
